@@ -1,0 +1,241 @@
+"""Batched, device-resident API: many controllers / many closed loops at once.
+
+``ControllerSet`` is the batched counterpart of the reference constructor
+(controller.py:95-387) - ``count`` controllers set up by one call, all on the
+GPU - and ``solve_batch`` / ``closed_loop`` are the batched counterparts of
+``update_and_solve_data_driven_mpc`` (controller.py:389-407) and
+``simulate_data_driven_mpc_control_loop`` (controller_operation.py:201-331).
+Tensors are torch CUDA tensors; torch is only the allocator and the stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def _f64(a) -> np.ndarray:
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+
+
+@dataclass
+class LTIPlant:
+    """State-space plant of utilities/model_simulation.py:31-98 (matrices on the host)."""
+    A: np.ndarray
+    B: np.ndarray
+    C: np.ndarray
+    D: np.ndarray
+    eps_max: float = 0.0
+
+    def __post_init__(self):
+        self.A, self.B, self.C, self.D = _f64(self.A), _f64(self.B), _f64(self.C), _f64(self.D)
+        self.n_x, self.m, self.p = self.A.shape[0], self.B.shape[1], self.C.shape[0]
+        if self.A.shape != (self.n_x, self.n_x) or self.B.shape[0] != self.n_x or self.C.shape[1] != self.n_x \
+                or self.D.shape != (self.p, self.m):
+            raise ValueError("inconsistent state-space matrix shapes")
+
+    def c_struct(self) -> _lib.Plant:
+        return _lib.Plant(n_x=self.n_x, m=self.m, p=self.p, A=self.A.ctypes.data, B=self.B.ctypes.data,
+                          C=self.C.ctypes.data, D=self.D.ctypes.data)
+
+    def equilibrium_gain(self) -> np.ndarray:
+        """C (I - A)^-1 B + D  (utilities/initial_state_estimation.py:162-169)."""
+        return self.C @ np.linalg.solve(np.eye(self.n_x) - self.A, self.B) + self.D
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _dev_f64(x, device, shape=None) -> torch.Tensor:
+    t = x if isinstance(x, torch.Tensor) else torch.from_numpy(_f64(x))
+    t = t.to(device=device, dtype=torch.float64).contiguous()
+    if shape is not None:
+        t = t.reshape(shape)
+    return t
+
+
+class ControllerSet:
+    """``count`` DD-MPC controllers with identical structure, set up on the GPU.
+
+    u_d: (N, m) shared by every controller, or (count, N, m) one data set each.
+    lamb_alpha / lamb_sigma: scalars or length-``count`` sequences.
+    """
+
+    def __init__(self, n: int, m: int, p: int, u_d, y_d, L: int, Q, R, eps_max: Optional[float] = None,
+                 lamb_alpha=None, lamb_sigma=None, c: Optional[float] = None, slack_type: int = _lib.SLACK_CONVEX,
+                 controller_type: int = _lib.NOMINAL, n_mpc_step: int = 1, use_terminal_constraint: bool = True,
+                 count: Optional[int] = None, check_pe: bool = True, device: Optional[torch.device] = None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("ControllerSet needs a CUDA device (no CPU fallback)")
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.n, self.m, self.p, self.L = n, m, p, L
+        self.n_mpc_step = n_mpc_step
+        ud = _dev_f64(u_d, self.device)
+        yd = _dev_f64(y_d, self.device)
+        shared = ud.dim() == 2
+        if count is None:
+            count = 1 if shared else ud.shape[0]
+        self.count = count
+        self.N = ud.shape[-2]
+        if ud.shape[-1] != m:
+            raise ValueError(f"The length of the elements of the data sequence ({ud.shape[-1]}) should match the "
+                             f"number of inputs of the system ({m}).")
+        Qd = _dev_f64(Q, self.device)
+        Rd = _dev_f64(R, self.device)
+        if tuple(Qd.shape) != (p * L, p * L):
+            raise ValueError("Output weighting square matrix Q should be of order (p * L)")
+        if tuple(Rd.shape) != (m * L, m * L):
+            raise ValueError("Input weighting square matrix R should be of order (m * L)")
+        robust = controller_type == _lib.ROBUST
+        self.robust = robust
+        nan = float("nan")
+
+        def scalar(v):
+            if v is None:
+                return nan if robust else 0.0
+            return float(np.asarray(v).reshape(-1)[0])
+
+        def per_ctrl(v):
+            if v is None or np.ndim(v) == 0:
+                return None
+            arr = _f64(v).reshape(-1)
+            if arr.size != count:
+                raise ValueError("per-controller weights must have `count` entries")
+            return arr
+
+        la_arr, ls_arr = per_ctrl(lamb_alpha), per_ctrl(lamb_sigma)
+        prm = _lib.Params(n=n, m=m, p=p, N=self.N, L=L, controller_type=controller_type, slack_type=slack_type,
+                          use_terminal=1 if use_terminal_constraint else 0, n_mpc_step=n_mpc_step,
+                          check_pe=1 if check_pe else 0,
+                          eps_max=scalar(eps_max), lamb_alpha=scalar(lamb_alpha), lamb_sigma=scalar(lamb_sigma),
+                          c=scalar(c))
+        self.eps_max = eps_max
+        handle = C.c_void_p()
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            _lib.check(_lib.lib.ddmpc_set_create(
+                C.byref(prm), count, ud.data_ptr(), 0 if shared else self.N * m, yd.data_ptr(),
+                0 if shared else self.N * p, Qd.data_ptr(), Rd.data_ptr(),
+                None if la_arr is None else la_arr.ctypes.data, None if ls_arr is None else ls_arr.ctypes.data,
+                stream, C.byref(handle)))
+        self._h = handle
+
+    # ---- introspection ---------------------------------------------------------
+    def info(self, index: int = 0) -> Tuple[int, int]:
+        rank, status = C.c_int(), C.c_int()
+        _lib.check(_lib.lib.ddmpc_set_info(self._h, index, C.byref(rank), C.byref(status)))
+        return rank.value, status.value
+
+    def statuses(self) -> np.ndarray:
+        return np.array([self.info(i)[1] for i in range(self.count)], dtype=np.int32)
+
+    def get(self, name: str, index: int = 0) -> np.ndarray:
+        n_elem = C.c_size_t()
+        _lib.check(_lib.lib.ddmpc_set_get(self._h, name.encode(), index, None, 0, C.byref(n_elem)))
+        out = np.empty(n_elem.value, dtype=np.float64)
+        _lib.check(_lib.lib.ddmpc_set_get(self._h, name.encode(), index, out.ctypes.data, out.size, C.byref(n_elem)))
+        return out
+
+    # ---- batched solve ------------------------------------------------------------
+    def solve_batch(self, u_past, y_past, u_s, y_s, ctrl_idx=None, tol: float = 1e-8, max_iter: int = 2000,
+                    want_cost: bool = True):
+        """B QP solves.  Returns (optimal_u (B, L*m), cost (B) or None, status (B) int32, iters (B) int32)."""
+        dev = self.device
+        up = _dev_f64(u_past, dev)
+        B = up.shape[0]
+        up = up.reshape(B, self.n * self.m)
+        yp = _dev_f64(y_past, dev, (B, self.n * self.p))
+        us = _dev_f64(u_s, dev, (B, self.m))
+        ys = _dev_f64(y_s, dev, (B, self.p))
+        ci = None if ctrl_idx is None else torch.as_tensor(ctrl_idx, device=dev).to(torch.int32).contiguous()
+        out = torch.empty(B, self.L * self.m, dtype=torch.float64, device=dev)
+        cost = torch.empty(B, dtype=torch.float64, device=dev) if want_cost else None
+        status = torch.empty(B, dtype=torch.int32, device=dev)
+        iters = torch.empty(B, dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib.ddmpc_solve_batch(
+                self._h, B, _ptr(ci), up.data_ptr(), yp.data_ptr(), us.data_ptr(), ys.data_ptr(), tol, max_iter,
+                out.data_ptr(), _ptr(cost), status.data_ptr(), iters.data_ptr(),
+                torch.cuda.current_stream().cuda_stream))
+        return out, cost, status, iters
+
+    def solve_full_batch(self, u_past, y_past, u_s, y_s, ctrl_idx=None, tol: float = 1e-8, max_iter: int = 2000,
+                         want_alpha: bool = True):
+        """Full primal (ubar, ybar, sigma, alpha) of B solves (sigma/alpha are None for NOMINAL)."""
+        dev = self.device
+        up = _dev_f64(u_past, dev)
+        B = up.shape[0]
+        up = up.reshape(B, self.n * self.m)
+        yp = _dev_f64(y_past, dev, (B, self.n * self.p))
+        us = _dev_f64(u_s, dev, (B, self.m))
+        ys = _dev_f64(y_s, dev, (B, self.p))
+        ci = None if ctrl_idx is None else torch.as_tensor(ctrl_idx, device=dev).to(torch.int32).contiguous()
+        Lp = self.L + self.n
+        robust = self.robust
+        ub = torch.empty(B, Lp * self.m, dtype=torch.float64, device=dev)
+        yb = torch.empty(B, Lp * self.p, dtype=torch.float64, device=dev)
+        sg = torch.empty(B, Lp * self.p, dtype=torch.float64, device=dev) if robust else None
+        al = torch.empty(B, self.N - Lp + 1, dtype=torch.float64, device=dev) if (robust and want_alpha) else None
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib.ddmpc_solve_full_batch(
+                self._h, B, _ptr(ci), up.data_ptr(), yp.data_ptr(), us.data_ptr(), ys.data_ptr(), tol, max_iter,
+                ub.data_ptr(), yb.data_ptr(), _ptr(sg), _ptr(al), torch.cuda.current_stream().cuda_stream))
+        return ub, yb, sg, al
+
+    # ---- fused closed loops ------------------------------------------------------
+    def closed_loop(self, plant: LTIPlant, x0, u_past0, y_past0, u_s, y_s, n_steps: int, w=None,
+                    noise_seed: int = 0, scenario_id0: int = 0, noise_eps: Optional[float] = None, ctrl_idx=None,
+                    tol: float = 1e-8, max_iter: int = 2000, out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
+                    want_x_final: bool = False):
+        """B closed loops of ``n_steps`` steps, in lockstep on the device.
+
+        w: (B, n_steps, p) pre-scaled noise (parity mode) or None for device Philox noise
+        ``noise_eps * U(-1, 1)`` keyed by (noise_seed, scenario_id0 + b).
+        Returns (u_sys (B, n_steps, m), y_sys (B, n_steps, p), status (B), iters (B)[, x_final]).
+        """
+        dev = self.device
+        x0t = _dev_f64(x0, dev)
+        B = x0t.shape[0]
+        x0t = x0t.reshape(B, plant.n_x)
+        up = _dev_f64(u_past0, dev, (B, self.n * self.m))
+        yp = _dev_f64(y_past0, dev, (B, self.n * self.p))
+        us = _dev_f64(u_s, dev, (B, self.m))
+        ys = _dev_f64(y_s, dev, (B, self.p))
+        wt = None if w is None else _dev_f64(w, dev, (B, n_steps, self.p))
+        ci = None if ctrl_idx is None else torch.as_tensor(ctrl_idx, device=dev).to(torch.int32).contiguous()
+        if out is None:
+            u_sys = torch.empty(B, n_steps, self.m, dtype=torch.float64, device=dev)
+            y_sys = torch.empty(B, n_steps, self.p, dtype=torch.float64, device=dev)
+        else:
+            u_sys, y_sys = out
+        status = torch.empty(B, dtype=torch.int32, device=dev)
+        iters = torch.empty(B, dtype=torch.int32, device=dev)
+        xf = torch.empty(B, plant.n_x, dtype=torch.float64, device=dev) if want_x_final else None
+        eps = plant.eps_max if noise_eps is None else noise_eps
+        ps = plant.c_struct()
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib.ddmpc_closed_loop_batch(
+                self._h, C.byref(ps), B, _ptr(ci), x0t.data_ptr(), up.data_ptr(), yp.data_ptr(), us.data_ptr(),
+                ys.data_ptr(), _ptr(wt), noise_seed, scenario_id0, float(eps), n_steps, tol, max_iter,
+                u_sys.data_ptr(), y_sys.data_ptr(), status.data_ptr(), iters.data_ptr(), _ptr(xf),
+                torch.cuda.current_stream().cuda_stream))
+        if want_x_final:
+            return u_sys, y_sys, status, iters, xf
+        return u_sys, y_sys, status, iters
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            _lib.lib.ddmpc_set_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

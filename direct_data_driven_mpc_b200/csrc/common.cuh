@@ -1,0 +1,74 @@
+// Shared host/device helpers for libddmpc (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <atomic>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "../../include/ddmpc.h"
+
+namespace ddmpc {
+
+extern thread_local char g_last_error[512];
+extern std::atomic<uint64_t> g_launches;
+
+inline int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_last_error, sizeof(g_last_error), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define DDMPC_CUDA(expr)                                                                  \
+    do {                                                                                  \
+        cudaError_t _e = (expr);                                                          \
+        if (_e != cudaSuccess)                                                            \
+            return ::ddmpc::fail(DDMPC_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,          \
+                                 cudaGetErrorString(_e), __FILE__, __LINE__);             \
+    } while (0)
+
+#define DDMPC_LAUNCH_CHECK()                                                              \
+    do {                                                                                  \
+        ::ddmpc::g_launches.fetch_add(1, std::memory_order_relaxed);                      \
+        cudaError_t _e = cudaGetLastError();                                              \
+        if (_e != cudaSuccess)                                                            \
+            return ::ddmpc::fail(DDMPC_ERR_CUDA, "kernel launch failed: %s (%s:%d)",      \
+                                 cudaGetErrorString(_e), __FILE__, __LINE__);             \
+    } while (0)
+
+#define DDMPC_TRY(expr)                                                                   \
+    do {                                                                                  \
+        int _s = (expr);                                                                  \
+        if (_s != DDMPC_OK) return _s;                                                    \
+    } while (0)
+
+inline int ceil_div(long a, long b) { return (int)((a + b - 1) / b); }
+
+// RAII device buffer (setup scratch + plan storage)
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    ~DevBuf() { release(); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+    }
+    cudaError_t alloc(size_t n) {
+        release();
+        if (n == 0) n = 8;
+        bytes = n;
+        return cudaMalloc(&p, n);
+    }
+    double *d() const { return (double *)p; }
+    int *i() const { return (int *)p; }
+};
+
+}  // namespace ddmpc

@@ -1,0 +1,324 @@
+// Batched FP64 dense linear algebra used by the per-controller setup:
+// strided GEMM (optional diagonal scaling), Cholesky, triangular solves and a
+// parallel-ordered cyclic Jacobi eigensolver.  One batch entry per controller.
+#pragma once
+#include "common.cuh"
+
+namespace ddmpc {
+
+// ---------------------------------------------------------------------------
+// C(MxN) = alpha * A(MxK) * diag(d) * B(KxN) + beta * C     (d optional)
+// element (i,j) of X lives at X[i*rsX + j*csX]; batch b adds b*bsX.
+// 64x64 tile, 256 threads, 4x4 per thread, K-tile 16.
+// ---------------------------------------------------------------------------
+constexpr int GT = 64, GK = 16;
+
+__global__ void __launch_bounds__(256)
+k_gemm(int M, int N, int K, double alpha,
+       const double *__restrict__ A, long rsA, long csA, long bsA,
+       const double *__restrict__ Bm, long rsB, long csB, long bsB,
+       const double *__restrict__ dvec, long bsd,
+       double beta, double *__restrict__ C, long rsC, long csC, long bsC) {
+    __shared__ double As[GK][GT + 1];
+    __shared__ double Bs[GK][GT + 1];
+    const int b = blockIdx.z;
+    A += (long)b * bsA;
+    Bm += (long)b * bsB;
+    C += (long)b * bsC;
+    if (dvec) dvec += (long)b * bsd;
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+    const int i0 = blockIdx.y * GT, j0 = blockIdx.x * GT;
+    double acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[a][c] = 0.0;
+
+    for (int k0 = 0; k0 < K; k0 += GK) {
+        // stage A tile (GT x GK) and B tile (GK x GT)
+#pragma unroll
+        for (int e = tid; e < GT * GK; e += 256) {
+            int i, k;
+            if (csA == 1) { i = e / GK; k = e % GK; } else { k = e / GT; i = e % GT; }
+            double v = 0.0;
+            if (i0 + i < M && k0 + k < K) {
+                v = A[(long)(i0 + i) * rsA + (long)(k0 + k) * csA];
+                if (dvec) v *= dvec[k0 + k];
+            }
+            As[k][i] = v;
+        }
+#pragma unroll
+        for (int e = tid; e < GT * GK; e += 256) {
+            int j, k;
+            if (csB == 1) { k = e / GT; j = e % GT; } else { j = e / GK; k = e % GK; }
+            double v = 0.0;
+            if (j0 + j < N && k0 + k < K) v = Bm[(long)(k0 + k) * rsB + (long)(j0 + j) * csB];
+            Bs[k][j] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < GK; ++k) {
+            double av[4], bv[4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) av[a] = As[k][ty + 16 * a];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) bv[c] = Bs[k][tx + 16 * c];
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[a][c] = fma(av[a], bv[c], acc[a][c]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        const int i = i0 + ty + 16 * a;
+        if (i >= M) continue;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int j = j0 + tx + 16 * c;
+            if (j >= N) continue;
+            double *cp = C + (long)i * rsC + (long)j * csC;
+            double v = alpha * acc[a][c];
+            if (beta != 0.0) v += beta * (*cp);
+            *cp = v;
+        }
+    }
+}
+
+struct Mat {  // strided batched matrix view
+    const double *p;
+    long rs, cs, bs;
+};
+inline Mat mat(const double *p, long rs, long cs, long bs) { return Mat{p, rs, cs, bs}; }
+inline Mat tr(Mat a) { return Mat{a.p, a.cs, a.rs, a.bs}; }
+
+inline int gemm(cudaStream_t st, int batch, int M, int N, int K, double alpha, Mat A, Mat B,
+                double beta, double *C, long rsC, long csC, long bsC,
+                const double *dvec = nullptr, long bsd = 0) {
+    if (M <= 0 || N <= 0 || batch <= 0) return DDMPC_OK;
+    dim3 grid(ceil_div(N, GT), ceil_div(M, GT), batch);
+    k_gemm<<<grid, 256, 0, st>>>(M, N, K, alpha, A.p, A.rs, A.cs, A.bs, B.p, B.rs, B.cs, B.bs,
+                                 dvec, bsd, beta, C, rsC, csC, bsC);
+    DDMPC_LAUNCH_CHECK();
+    return DDMPC_OK;
+}
+
+// ---------------------------------------------------------------------------
+// In-place lower Cholesky of a row-major n x n matrix (ld), one CTA per batch
+// entry.  info[b] = 0 or (1 + index of the first non-positive pivot).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+k_potrf(int n, double *__restrict__ A, long ld, long bs, int *__restrict__ info) {
+    A += (long)blockIdx.x * bs;
+    const int tid = threadIdx.x, T = blockDim.x;
+    __shared__ double piv;
+    __shared__ int bad;
+    if (tid == 0) bad = 0;
+    __syncthreads();
+    for (int j = 0; j < n; ++j) {
+        if (tid == 0) {
+            double d = A[(long)j * ld + j];
+            if (!(d > 0.0) || !isfinite(d)) {
+                if (!bad) bad = j + 1;
+                d = 1.0;  // keep going with finite numbers; the verdict is in info
+            }
+            d = sqrt(d);
+            A[(long)j * ld + j] = d;
+            piv = d;
+        }
+        __syncthreads();
+        const double inv = 1.0 / piv;
+        for (int i = j + 1 + tid; i < n; i += T) A[(long)i * ld + j] *= inv;
+        __syncthreads();
+        const int rem = n - j - 1;
+        for (long idx = tid; idx < (long)rem * rem; idx += T) {
+            const int i = j + 1 + (int)(idx / rem);
+            const int k = j + 1 + (int)(idx % rem);
+            if (k <= i) A[(long)i * ld + k] = fma(-A[(long)i * ld + j], A[(long)k * ld + j], A[(long)i * ld + k]);
+        }
+        __syncthreads();
+    }
+    if (tid == 0 && info) info[blockIdx.x] = bad;
+}
+
+inline int potrf(cudaStream_t st, int batch, int n, double *A, long ld, long bs, int *info) {
+    if (n <= 0 || batch <= 0) return DDMPC_OK;
+    int threads = n >= 256 ? 1024 : (n >= 96 ? 512 : 256);
+    k_potrf<<<batch, threads, 0, st>>>(n, A, ld, bs, info);
+    DDMPC_LAUNCH_CHECK();
+    return DDMPC_OK;
+}
+
+// ---------------------------------------------------------------------------
+// Triangular solves with the lower Cholesky factor L (row-major, ldl):
+//   trans == 0:  L   X = B        trans == 1:  L^T X = B
+// B (n x nrhs, row-major, ldb) is overwritten by X.  One thread per RHS column.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_trsm(int n, int nrhs, int trans, const double *__restrict__ Lm, long ldl, long bsl,
+       double *__restrict__ Bm, long ldb, long bsb) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nrhs) return;
+    Lm += (long)blockIdx.y * bsl;
+    Bm += (long)blockIdx.y * bsb;
+    if (!trans) {
+        for (int i = 0; i < n; ++i) {
+            double a0 = Bm[(long)i * ldb + j], a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            const double *Li = Lm + (long)i * ldl;
+            int k = 0;
+            for (; k + 3 < i; k += 4) {
+                a0 = fma(-Li[k], Bm[(long)k * ldb + j], a0);
+                a1 = fma(-Li[k + 1], Bm[(long)(k + 1) * ldb + j], a1);
+                a2 = fma(-Li[k + 2], Bm[(long)(k + 2) * ldb + j], a2);
+                a3 = fma(-Li[k + 3], Bm[(long)(k + 3) * ldb + j], a3);
+            }
+            for (; k < i; ++k) a0 = fma(-Li[k], Bm[(long)k * ldb + j], a0);
+            Bm[(long)i * ldb + j] = ((a0 + a1) + (a2 + a3)) / Li[i];
+        }
+    } else {
+        for (int i = n - 1; i >= 0; --i) {
+            double a0 = Bm[(long)i * ldb + j], a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            int k = i + 1;
+            for (; k + 3 < n; k += 4) {
+                a0 = fma(-Lm[(long)k * ldl + i], Bm[(long)k * ldb + j], a0);
+                a1 = fma(-Lm[(long)(k + 1) * ldl + i], Bm[(long)(k + 1) * ldb + j], a1);
+                a2 = fma(-Lm[(long)(k + 2) * ldl + i], Bm[(long)(k + 2) * ldb + j], a2);
+                a3 = fma(-Lm[(long)(k + 3) * ldl + i], Bm[(long)(k + 3) * ldb + j], a3);
+            }
+            for (; k < n; ++k) a0 = fma(-Lm[(long)k * ldl + i], Bm[(long)k * ldb + j], a0);
+            Bm[(long)i * ldb + j] = ((a0 + a1) + (a2 + a3)) / Lm[(long)i * ldl + i];
+        }
+    }
+}
+
+// X = (L L^T)^-1 B in place
+inline int potrs(cudaStream_t st, int batch, int n, int nrhs, const double *L, long ldl, long bsl,
+                 double *B, long ldb, long bsb) {
+    if (n <= 0 || nrhs <= 0 || batch <= 0) return DDMPC_OK;
+    const int threads = nrhs >= 128 ? 128 : (nrhs >= 64 ? 64 : 32);
+    dim3 grid(ceil_div(nrhs, threads), batch);
+    k_trsm<<<grid, threads, 0, st>>>(n, nrhs, 0, L, ldl, bsl, B, ldb, bsb);
+    DDMPC_LAUNCH_CHECK();
+    k_trsm<<<grid, threads, 0, st>>>(n, nrhs, 1, L, ldl, bsl, B, ldb, bsb);
+    DDMPC_LAUNCH_CHECK();
+    return DDMPC_OK;
+}
+
+// ---------------------------------------------------------------------------
+// Symmetric eigen-decomposition by parallel-ordered cyclic Jacobi.  One CTA per
+// batch entry; A (n x n, ld) is destroyed (its diagonal ends as the spectrum),
+// V (n x n, ldv; may be NULL) receives the eigenvectors as columns, lam (n) the
+// eigenvalues (unsorted).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void jacobi_pair(int n2, int r, int k, int &p, int &q) {
+    int a, b;
+    if (k == 0) { a = n2 - 1; b = r; }
+    else { a = (r + k) % (n2 - 1); b = (r - k + (n2 - 1)) % (n2 - 1); }
+    p = a < b ? a : b;
+    q = a < b ? b : a;
+}
+
+__global__ void __launch_bounds__(1024)
+k_jacobi(int n, double *__restrict__ A, long ld, long bsA, double *__restrict__ V, long ldv, long bsV,
+         double *__restrict__ lam, long bsl, int max_sweeps) {
+    extern __shared__ double sh[];  // c[n2/2], s[n2/2], red[32]
+    A += (long)blockIdx.x * bsA;
+    if (V) V += (long)blockIdx.x * bsV;
+    lam += (long)blockIdx.x * bsl;
+    const int tid = threadIdx.x, T = blockDim.x;
+    const int n2 = n + (n & 1), np2 = n2 / 2;
+    double *cs_c = sh, *cs_s = sh + np2, *red = sh + 2 * np2;
+    __shared__ int done;
+    if (V)
+        for (long e = tid; e < (long)n * n; e += T) V[(e / n) * ldv + (e % n)] = (e / n == e % n) ? 1.0 : 0.0;
+    __syncthreads();
+    for (int sweep = 0; sweep < max_sweeps; ++sweep) {
+        // off-diagonal and total Frobenius mass
+        double off = 0.0, tot = 0.0;
+        for (long e = tid; e < (long)n * n; e += T) {
+            const int i = (int)(e / n), j = (int)(e % n);
+            const double v = A[(long)i * ld + j];
+            tot += v * v;
+            if (i != j) off += v * v;
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            off += __shfl_xor_sync(0xffffffffu, off, o);
+            tot += __shfl_xor_sync(0xffffffffu, tot, o);
+        }
+        if ((tid & 31) == 0) { red[tid >> 5] = off; red[32 + (tid >> 5)] = tot; }
+        __syncthreads();
+        if (tid == 0) {
+            double so = 0.0, stt = 0.0;
+            for (int w = 0; w < (T + 31) / 32; ++w) { so += red[w]; stt += red[32 + w]; }
+            done = (so <= 1e-29 * stt) ? 1 : 0;
+        }
+        __syncthreads();
+        if (done) break;
+        for (int r = 0; r < n2 - 1; ++r) {
+            for (int k = tid; k < np2; k += T) {
+                int p, q;
+                jacobi_pair(n2, r, k, p, q);
+                double c = 1.0, s = 0.0;
+                if (q < n) {
+                    const double apq = A[(long)p * ld + q];
+                    if (fabs(apq) > 1e-300) {
+                        const double tau = (A[(long)q * ld + q] - A[(long)p * ld + p]) / (2.0 * apq);
+                        const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+                        c = 1.0 / sqrt(1.0 + t * t);
+                        s = t * c;
+                    }
+                }
+                cs_c[k] = c;
+                cs_s[k] = s;
+            }
+            __syncthreads();
+            // column rotations  A <- A J,  V <- V J
+            for (long e = tid; e < (long)np2 * n; e += T) {
+                const int k = (int)(e / n), i = (int)(e % n);
+                int p, q;
+                jacobi_pair(n2, r, k, p, q);
+                if (q >= n) continue;
+                const double c = cs_c[k], s = cs_s[k];
+                if (s == 0.0) continue;
+                const double ap = A[(long)i * ld + p], aq = A[(long)i * ld + q];
+                A[(long)i * ld + p] = c * ap - s * aq;
+                A[(long)i * ld + q] = s * ap + c * aq;
+                if (V) {
+                    const double vp = V[(long)i * ldv + p], vq = V[(long)i * ldv + q];
+                    V[(long)i * ldv + p] = c * vp - s * vq;
+                    V[(long)i * ldv + q] = s * vp + c * vq;
+                }
+            }
+            __syncthreads();
+            // row rotations  A <- J^T A
+            for (long e = tid; e < (long)np2 * n; e += T) {
+                const int k = (int)(e / n), j = (int)(e % n);
+                int p, q;
+                jacobi_pair(n2, r, k, p, q);
+                if (q >= n) continue;
+                const double c = cs_c[k], s = cs_s[k];
+                if (s == 0.0) continue;
+                const double ap = A[(long)p * ld + j], aq = A[(long)q * ld + j];
+                A[(long)p * ld + j] = c * ap - s * aq;
+                A[(long)q * ld + j] = s * ap + c * aq;
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = tid; i < n; i += T) lam[i] = A[(long)i * ld + i];
+}
+
+inline int jacobi_eig(cudaStream_t st, int batch, int n, double *A, long ld, long bsA, double *V,
+                      long ldv, long bsV, double *lam, long bsl) {
+    if (n <= 0 || batch <= 0) return DDMPC_OK;
+    const int n2 = n + (n & 1);
+    const size_t sh = (size_t)(n2 + 64) * sizeof(double);
+    const int threads = n >= 128 ? 1024 : (n >= 48 ? 512 : 256);
+    k_jacobi<<<batch, threads, sh, st>>>(n, A, ld, bsA, V, ldv, bsV, lam, bsl, 40);
+    DDMPC_LAUNCH_CHECK();
+    return DDMPC_OK;
+}
+
+}  // namespace ddmpc

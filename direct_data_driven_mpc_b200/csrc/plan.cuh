@@ -1,0 +1,50 @@
+// Per-controller "plan": dimensions, index maps and the device-resident
+// condensed solve operators produced by the setup pipeline (setup.cu) and
+// consumed by the batched solver / fused closed loop (solve.cu).
+#pragma once
+#include <vector>
+
+#include "common.cuh"
+
+namespace ddmpc {
+
+struct Dims {
+    int n, m, p, N, L, Lp;
+    int nu, ny;        // (L+n)*m, (L+n)*p
+    int r, cols;       // Hankel stack: r = nu+ny rows, cols = N-L-n+1
+    int nx;            // primal x = [ubar; ybar; sigma(robust)]
+    int nfix, nf;      // fixed (initial/terminal) and free coordinates
+    int nth;           // theta = [u_past; y_past; u_s; y_s]
+    int nb;            // box rows (CONVEX: sigma_pred = L*p), else 0
+    int Lm;            // L*m = len(optimal_u)
+    int robust, convex, terminal;
+};
+
+// Device operators, each stored as [count][rows][cols] row-major FP64.
+struct Plan {
+    Dims d{};
+    int count = 0;
+    DevBuf H;      // (r, cols)      stacked Hankel [H_u; H_y]   (HLn_ud / HLn_yd)
+    DevBuf Om;     // (r, r)         W^-1, W = H H^T             (robust; alpha recovery)
+    DevBuf W;      // (r, r)         Gram matrix (kept for inspection)
+    DevBuf Ku;     // (Lm, nth)      optimal_u = Ku theta
+    DevBuf Z;      // (nth, nth)     unconstrained optimal cost = theta^T Z theta
+    DevBuf X0;     // (nx, nth)      full primal x0 = X0 theta
+    DevBuf Ks;     // (nb, nth)      s_unc = Ks theta             (convex)
+    DevBuf Phi;    // (nb, nb)       (I + rho/2 Lam)^-1           (convex)
+    DevBuf Psi;    // (Lm, nb)       u = u0 + Psi (v - s)         (convex)
+    DevBuf Lam;    // (nb, nb)       B A^-1 B^T                   (convex)
+    DevBuf Yf;     // (nx, nb)       rho/2 * A^-1 B^T scattered   (convex; full primal)
+    DevBuf rho2;   // (1)            rho/2
+    DevBuf F;      // (nfix, nth)    feasibility residual map     (nominal)
+    DevBuf lamA, lamS;  // per-controller lamb_alpha*eps_max, lamb_sigma
+    std::vector<int> pe_rank, status;
+    double bound = 0.0;   // c * eps_max
+};
+
+}  // namespace ddmpc
+
+struct ddmpc_set {
+    ddmpc_params prm;
+    ddmpc::Plan plan;
+};

@@ -1,0 +1,178 @@
+"""GPU: fused closed loops (C ABI) vs the golden fixtures and the oracle.
+
+Tolerance: 1e-5 relative on u (north_star); trajectories of the stable schemes
+are compared over the whole run ("no divergence over t_sim"), the unstable UCON
+scheme over its first 150 steps and through per-step open-loop solves."""
+import numpy as np
+import pytest
+
+from oracle import ddmpc_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _plant():
+    from direct_data_driven_mpc_b200 import LTIPlant
+    return LTIPlant(**{k: O.FOUR_TANK[k] for k in "ABCD"}, eps_max=0.002)
+
+
+def _set(u_d, y_d, slack=0, term=True, n_mpc=4, c=1.0):
+    from direct_data_driven_mpc_b200 import ControllerSet
+    prm = O.four_tank_params()
+    return ControllerSet(4, 2, 2, u_d, y_d, 30, prm["Q"], prm["R"], prm["eps_max"], prm["lamb_alpha"],
+                         prm["lamb_sigma"], c, slack, 1, n_mpc, term), prm
+
+
+def _rel(a, b):
+    return np.abs(a - b).max() / max(1.0, np.abs(b).max())
+
+
+def test_config1_example_seed0_parity(golden_example):
+    """BASELINE config 1: examples/direct_data_driven_mpc_example.py --seed 0 --t_sim 400."""
+    g = golden_example
+    cs, prm = _set(g["u_d"], g["y_d"])
+    u, y, status, iters = cs.closed_loop(_plant(), g["x_loop0"][None], g["u_d"][-4:].reshape(1, -1),
+                                         g["y_d"][-4:].reshape(1, -1), prm["u_s"].reshape(1, -1),
+                                         prm["y_s"].reshape(1, -1), 401, w=g["w_sys"][None])
+    u, y = u.cpu().numpy()[0], y.cpu().numpy()[0]
+    assert int(status[0]) == 0 and int(iters[0]) == 101
+    assert _rel(u, g["u_sys"]) < 1e-5 and _rel(y, g["y_sys"]) < 1e-5
+    assert np.isfinite(y).all() and np.allclose(y[400], [0.652, 0.770], atol=1e-3)
+    assert np.allclose(u[0], [21.22, 20.30], atol=0.01)
+
+
+def test_reproduction_three_schemes(golden_repro):
+    """examples/robust_data_driven_mpc_reproduction.py (seed 4, t_sim 600): TEC, TEC-n-step, UCON."""
+    g = golden_repro
+    prm = O.four_tank_params()
+    for name, n_mpc, term in (("TEC", 1, True), ("TEC_N_STEP", 4, True), ("UCON", 1, False)):
+        cs, _ = _set(g["u_d"], g["y_d"], 0, term, n_mpc)
+        u, y, status, iters = cs.closed_loop(_plant(), g["x_start"][None], g["U_n"].reshape(1, -1),
+                                             g["Y_n"].reshape(1, -1), prm["u_s"].reshape(1, -1),
+                                             prm["y_s"].reshape(1, -1), 597, w=g[f"w_{name}"][None])
+        u, y = u.cpu().numpy()[0], y.cpu().numpy()[0]
+        if name == "UCON":
+            assert _rel(u[:150], g["u_UCON"][:150]) < 1e-5
+            assert np.abs(y).max() > 10.0                                  # diverges by design
+        else:
+            assert _rel(u, g[f"u_{name}"]) < 1e-5 and _rel(y, g[f"y_{name}"]) < 1e-5
+            assert int(status[0]) == 0
+            assert abs(np.abs(u).max() - 8.66) < 0.01
+
+
+@pytest.mark.parametrize("n_mpc,n_steps", [(1, 23), (4, 41), (3, 20), (4, 4), (7, 9)])
+def test_partial_blocks_and_step_counts(n_mpc, n_steps):
+    """last n-step block may be partial (controller_operation.py:278)."""
+    plant_o, prm, rng, x0, u_d, y_d = O.example_scenario(2)
+    w = plant_o.eps_max * rng.uniform(-1, 1, (n_steps, 2))
+    xs = plant_o.x.copy()
+    ctrl = O.make_controller(prm, u_d, y_d, n_mpc_step=n_mpc)
+    u_ref, y_ref = O.closed_loop(plant_o, ctrl, n_steps, w)
+    cs, _ = _set(u_d, y_d, 0, True, n_mpc)
+    u, y, status, iters, xf = cs.closed_loop(_plant(), xs[None], u_d[-4:].reshape(1, -1), y_d[-4:].reshape(1, -1),
+                                             prm["u_s"].reshape(1, -1), prm["y_s"].reshape(1, -1), n_steps, w=w[None],
+                                             want_x_final=True)
+    assert _rel(u.cpu().numpy()[0], u_ref) < 1e-7 and _rel(y.cpu().numpy()[0], y_ref) < 1e-7
+    assert int(iters[0]) == -(-n_steps // n_mpc)
+    assert np.allclose(xf.cpu().numpy()[0], plant_o.x, atol=1e-9)
+
+
+def test_convex_closed_loop_vs_oracle():
+    """CONVEX slack bound active in the loop (tight c so that it binds)."""
+    plant_o, prm, rng, x0, u_d, y_d = O.example_scenario(0)
+    n_steps = 24
+    w = plant_o.eps_max * rng.uniform(-1, 1, (n_steps, 2))
+    xs = plant_o.x.copy()
+    ctrl = O.make_controller(prm, u_d, y_d, n_mpc_step=2, slack_type=O.SLACK_CONVEX, c=0.3)
+    u_ref, y_ref = O.closed_loop(plant_o, ctrl, n_steps, w)
+    cs, _ = _set(u_d, y_d, 1, True, 2, c=0.3)
+    u, y, status, iters = cs.closed_loop(_plant(), xs[None], u_d[-4:].reshape(1, -1), y_d[-4:].reshape(1, -1),
+                                         prm["u_s"].reshape(1, -1), prm["y_s"].reshape(1, -1), n_steps, w=w[None])
+    assert int(status[0]) == 0 and int(iters[0]) > 12
+    assert _rel(u.cpu().numpy()[0], u_ref) < 1e-5 and _rel(y.cpu().numpy()[0], y_ref) < 1e-5
+
+
+def test_batch_of_loops_per_seed_controllers_and_philox():
+    """config-2 style: loop b has its own data/controller; Philox noise replayed by the oracle."""
+    from direct_data_driven_mpc_b200 import ControllerSet
+    B, n_steps = 6, 33
+    prm = O.four_tank_params()
+    data = [O.example_scenario(s) for s in range(B)]
+    ud, yd = np.stack([d[4] for d in data]), np.stack([d[5] for d in data])
+    xs = np.stack([d[0].x for d in data])
+    cs = ControllerSet(4, 2, 2, ud, yd, 30, prm["Q"], prm["R"], prm["eps_max"], prm["lamb_alpha"], prm["lamb_sigma"],
+                       1.0, 0, 1, 4, True)
+    seed, id0 = 1234567890123, 77
+    u, y, status, iters = cs.closed_loop(_plant(), xs, ud[:, -4:].reshape(B, -1), yd[:, -4:].reshape(B, -1),
+                                         np.tile(prm["u_s"].T, (B, 1)), np.tile(prm["y_s"].T, (B, 1)), n_steps,
+                                         w=None, noise_seed=seed, scenario_id0=id0, noise_eps=0.002,
+                                         ctrl_idx=np.arange(B))
+    u, y = u.cpu().numpy(), y.cpu().numpy()
+    w = O.philox_noise(seed, id0 + np.arange(B), n_steps, 2, 0.002)
+    for b in range(B):
+        plant_o = data[b][0]
+        ctrl = O.make_controller(prm, ud[b], yd[b])
+        u_ref, y_ref = O.closed_loop(plant_o, ctrl, n_steps, w[b])
+        assert _rel(u[b], u_ref) < 1e-6 and _rel(y[b], y_ref) < 1e-6, b
+    # sharding invariance: a shard launched with an id offset equals the slice of the full run
+    u2, y2, _, _ = cs.closed_loop(_plant(), xs[3:], ud[3:, -4:].reshape(3, -1), yd[3:, -4:].reshape(3, -1),
+                                  np.tile(prm["u_s"].T, (3, 1)), np.tile(prm["y_s"].T, (3, 1)), n_steps, w=None,
+                                  noise_seed=seed, scenario_id0=id0 + 3, noise_eps=0.002, ctrl_idx=np.arange(3, 6))
+    assert np.array_equal(u2.cpu().numpy(), u[3:]) and np.array_equal(y2.cpu().numpy(), y[3:])
+
+
+def test_controller_class_drives_reference_style_loop(golden_example):
+    """The drop-in class (B = 1) stepping through the reference's loop semantics."""
+    from direct_data_driven_mpc_b200 import (DataDrivenMPCType, DirectDataDrivenMPCController,
+                                             SlackVarConstraintTypes)
+    g = golden_example
+    prm = O.four_tank_params()
+    ctrl = DirectDataDrivenMPCController(
+        n=4, m=2, p=2, u_d=g["u_d"], y_d=g["y_d"], L=30, Q=prm["Q"], R=prm["R"], u_s=prm["u_s"], y_s=prm["y_s"],
+        eps_max=0.002, lamb_alpha=prm["lamb_alpha"], lamb_sigma=1000, c=1.0,
+        slack_var_constraint_type=SlackVarConstraintTypes.NONE, controller_type=DataDrivenMPCType.ROBUST,
+        n_mpc_step=4, use_terminal_constraint=True)
+    assert ctrl.HLn_ud.shape == (68, 367) and np.array_equal(ctrl.HLn_ud, O.hankel_matrix(g["u_d"], 34))
+    assert ctrl.get_problem_solve_status() == "optimal"
+    plant_o = O.four_tank_plant()
+    plant_o.x = g["x_loop0"].copy()
+    n_steps = 61
+    u_sys, y_sys = O.closed_loop(plant_o, ctrl, n_steps, g["w_sys"][:n_steps])   # duck-typed reference loop
+    assert _rel(u_sys, g["u_sys"][:n_steps]) < 1e-5 and _rel(y_sys, g["y_sys"][:n_steps]) < 1e-5
+    assert abs(ctrl.get_optimal_cost_value() - g["cost"][15]) < 1e-6 * max(1.0, abs(g["cost"][15]))
+    assert _rel(ctrl.optimal_u, g["optimal_u"][15]) < 1e-5
+    # full primal on demand; dynamics constraint [ubar; ybar + sigma] = H alpha holds
+    ub, yb, sg, al = ctrl.ubar.value, ctrl.ybar.value, ctrl.sigma.value, ctrl.alpha.value
+    assert ub.shape == (68, 1) and al.shape == (367, 1)
+    H = np.vstack([ctrl.HLn_ud, ctrl.HLn_yd])
+    assert np.abs(H @ al - np.vstack([ub, yb + sg])).max() < 1e-7
+    assert np.abs(ub[8:].ravel() - ctrl.optimal_u).max() < 1e-9
+    with pytest.raises(ValueError):
+        ctrl.get_optimal_control_input_at_step(30)
+    with pytest.raises(ValueError):
+        ctrl.store_input_output_measurement(np.zeros(2), np.zeros((2, 1)))
+    with pytest.raises(ValueError):
+        ctrl.set_past_input_output_data(np.zeros((8, 1)), np.zeros((7, 1)))
+    ctrl.set_input_output_setpoints(np.array([[0.9], [1.1]]), np.array([[0.6], [0.8]]))
+    assert ctrl.get_problem_solve_status() == "optimal"
+
+
+def test_many_loops_linearity_property():
+    """Size-independent property at a larger batch: equality-only closed loops are affine in
+    (x0, set-point, noise): loop(a) + loop(b) - loop(c) == loop(a + b - c)."""
+    import torch
+    plant_o, prm, rng, x0, u_d, y_d = O.example_scenario(0)
+    cs, _ = _set(u_d, y_d)
+    B, n_steps = 4096, 101
+    r = np.random.default_rng(11)
+    x = r.uniform(-0.5, 0.5, (3, B, 4))
+    us = r.uniform(0.5, 1.5, (3, B, 2))
+    ys = r.uniform(0.4, 0.9, (3, B, 2))
+    up = r.uniform(-1, 1, (3, B, 8))
+    yp = r.uniform(-0.1, 0.1, (3, B, 8))
+    w = 0.002 * r.uniform(-1, 1, (3, B, n_steps, 2))
+    comb = lambda a: a[0] + a[1] - a[2]
+    outs = [cs.closed_loop(_plant(), x[i], up[i], yp[i], us[i], ys[i], n_steps, w=w[i])[0] for i in range(3)]
+    uc = cs.closed_loop(_plant(), comb(x), comb(up), comb(yp), comb(us), comb(ys), n_steps, w=comb(w))[0]
+    lhs = outs[0] + outs[1] - outs[2]
+    assert (torch.abs(lhs - uc).max() / torch.abs(uc).max()).item() < 1e-9

@@ -1,0 +1,136 @@
+"""GPU: batched QP solves (through the C ABI) against the literal-KKT oracle.
+
+Tolerance (north_star): 1e-5 relative on u at solver tolerance 1e-8; the
+equality-only variants are direct solves and are held to 1e-8."""
+import numpy as np
+import pytest
+
+from oracle import ddmpc_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _set(slack, term, c=1.0, n_mpc=1, seed=0, ctrl=1, data=None):
+    from direct_data_driven_mpc_b200 import ControllerSet
+    plant, prm, rng, x0, u_d, y_d = O.example_scenario(seed)
+    if data is not None:
+        u_d, y_d = data
+    cs = ControllerSet(4, 2, 2, u_d, y_d, 30, prm["Q"], prm["R"], prm["eps_max"], prm["lamb_alpha"],
+                       prm["lamb_sigma"], c, slack, ctrl, n_mpc, term)
+    qp = O.OracleQP(4, 2, 2, u_d, y_d, 30, prm["Q"], prm["R"], prm["eps_max"], prm["lamb_alpha"], prm["lamb_sigma"],
+                    c, slack, ctrl, term)
+    return cs, qp, prm, u_d, y_d
+
+
+def _thetas(u_d, y_d, prm, B, seed=0):
+    r = np.random.default_rng(seed)
+    ks = r.integers(0, u_d.shape[0] - 4, B)
+    up = np.stack([u_d[k:k + 4].reshape(-1) for k in ks])
+    yp = np.stack([y_d[k:k + 4].reshape(-1) for k in ks])
+    us = prm["u_s"].reshape(1, -1) * r.uniform(0.5, 1.5, (B, 1))
+    ys = prm["y_s"].reshape(1, -1) * r.uniform(0.5, 1.5, (B, 1))
+    return up, yp, us, ys
+
+
+@pytest.mark.parametrize("slack,term,c,tol", [(0, True, 1.0, 1e-8), (0, False, 1.0, 1e-8), (1, True, 1.0, 1e-5),
+                                              (1, False, 0.3, 1e-5), (1, True, 0.2, 1e-5)])
+def test_solve_batch_vs_oracle(slack, term, c, tol):
+    cs, qp, prm, u_d, y_d = _set(slack, term, c)
+    B = 24
+    up, yp, us, ys = _thetas(u_d, y_d, prm, B)
+    u, cost, status, iters = cs.solve_batch(up, yp, us, ys, tol=1e-8)
+    u, cost, status, iters = u.cpu().numpy(), cost.cpu().numpy(), status.cpu().numpy(), iters.cpu().numpy()
+    assert (status == 0).all()
+    n_active = 0
+    for b in range(B):
+        so = qp.solve(up[b], yp[b], us[b], ys[b])
+        n_active += so.n_active
+        rel = np.abs(u[b] - so.optimal_u).max() / max(1.0, np.abs(so.optimal_u).max())
+        assert rel < tol, (b, rel, so.n_active, iters[b])
+        assert abs(cost[b] - so.cost) <= 1e-6 * max(1.0, abs(so.cost))
+        if slack == 0:
+            assert iters[b] == 1
+    if slack == 1 and c < 1.0:
+        assert n_active > 0 and iters.max() > 1          # the box path was really exercised
+
+
+def test_solve_full_primal_vs_oracle():
+    cs, qp, prm, u_d, y_d = _set(1, True, 0.3)
+    up, yp, us, ys = _thetas(u_d, y_d, prm, 6, seed=3)
+    ub, yb, sg, al = cs.solve_full_batch(up, yp, us, ys)
+    for b in range(6):
+        so = qp.solve(up[b], yp[b], us[b], ys[b])
+        assert np.abs(ub[b].cpu().numpy() - so.ubar).max() < 1e-5 * max(1, np.abs(so.ubar).max())
+        assert np.abs(yb[b].cpu().numpy() - so.ybar).max() < 1e-6
+        assert np.abs(sg[b].cpu().numpy() - so.sigma).max() < 1e-7
+        assert np.abs(al[b].cpu().numpy() - so.alpha).max() < 1e-6 * max(1, np.abs(so.alpha).max())
+        assert np.abs(sg[b].cpu().numpy()[8:]).max() <= 0.3 * 0.002 * (1 + 1e-6)
+
+
+def test_solve_batch_per_scenario_controller_index():
+    from direct_data_driven_mpc_b200 import ControllerSet
+    data = [O.example_scenario(s) for s in range(3)]
+    prm = data[0][1]
+    ud, yd = np.stack([d[4] for d in data]), np.stack([d[5] for d in data])
+    cs = ControllerSet(4, 2, 2, ud, yd, 30, prm["Q"], prm["R"], prm["eps_max"], prm["lamb_alpha"], prm["lamb_sigma"],
+                       1.0, 0, 1, 4, True)
+    qps = [O.OracleQP(4, 2, 2, ud[i], yd[i], 30, prm["Q"], prm["R"], prm["eps_max"], prm["lamb_alpha"],
+                      prm["lamb_sigma"], 1.0, 0, 1, True) for i in range(3)]
+    B = 9
+    idx = np.arange(B) % 3
+    up, yp, us, ys = _thetas(ud[0], yd[0], prm, B, seed=5)
+    u, cost, status, iters = cs.solve_batch(up, yp, us, ys, ctrl_idx=idx)
+    u = u.cpu().numpy()
+    for b in range(B):
+        so = qps[idx[b]].solve(up[b], yp[b], us[b], ys[b])
+        assert np.abs(u[b] - so.optimal_u).max() < 1e-8 * max(1.0, np.abs(so.optimal_u).max())
+
+
+def test_nominal_noisy_and_noise_free():
+    from direct_data_driven_mpc_b200 import ControllerSet
+    prm = O.four_tank_params()
+    # noisy data: H has full row rank -> free coordinates sit on the set-point
+    plant, _, rng, x0, u_d, y_d = O.example_scenario(0)
+    cs = ControllerSet(4, 2, 2, u_d, y_d, 30, prm["Q"], prm["R"], controller_type=0, n_mpc_step=1)
+    up, yp, us, ys = _thetas(u_d, y_d, prm, 4)
+    u, cost, status, iters = cs.solve_batch(up, yp, us, ys)
+    assert (status.cpu().numpy() == 0).all()
+    assert np.abs(u.cpu().numpy() - np.tile(us, (1, 30))).max() < 1e-7
+    # noise-free data: rank(H) = m(L+n) + n_sys
+    pl = O.four_tank_plant()
+    pl.eps_max = 0.0
+    r = np.random.default_rng(5)
+    pl.x = r.uniform(-1, 1, 4)
+    u_d = r.uniform(-1, 1, (400, 2))
+    y_d = pl.simulate(u_d, np.zeros((400, 2)), 400)
+    u_eq = np.array([1.0, 1.0])
+    y_eq = pl.equilibrium_output_from_input(u_eq)
+    for term in (True, False):
+        cs = ControllerSet(4, 2, 2, u_d, y_d, 30, prm["Q"], prm["R"], controller_type=0, use_terminal_constraint=term)
+        qp = O.OracleQP(4, 2, 2, u_d, y_d, 30, prm["Q"], prm["R"], ctrl_type=O.NOMINAL, use_terminal=term)
+        ks = [0, 100, 396]
+        up = np.stack([u_d[k:k + 4].reshape(-1) for k in ks])
+        yp = np.stack([y_d[k:k + 4].reshape(-1) for k in ks])
+        us, ys = np.tile(u_eq, (3, 1)), np.tile(y_eq, (3, 1))
+        u, cost, status, iters = cs.solve_batch(up, yp, us, ys)
+        assert (status.cpu().numpy() == 0).all()
+        for b in range(3):
+            so = qp.solve(up[b], yp[b], us[b], ys[b])
+            rel = np.abs(u[b].cpu().numpy() - so.optimal_u).max() / max(1.0, np.abs(so.optimal_u).max())
+            assert rel < 1e-5, (term, b, rel)
+    # inconsistent window -> "infeasible" status, like the oracle
+    yp_bad = yp + 0.05
+    _, _, status, _ = cs.solve_batch(up, yp_bad, us, ys)
+    cs_t = ControllerSet(4, 2, 2, u_d, y_d, 30, prm["Q"], prm["R"], controller_type=0, use_terminal_constraint=True)
+    _, _, status, _ = cs_t.solve_batch(up, yp_bad, us, ys)
+    assert (status.cpu().numpy() == 2).all()
+
+
+def test_empty_and_single():
+    cs, qp, prm, u_d, y_d = _set(0, True)
+    up, yp, us, ys = _thetas(u_d, y_d, prm, 1)
+    u, cost, status, iters = cs.solve_batch(up, yp, us, ys)
+    so = qp.solve(up[0], yp[0], us[0], ys[0])
+    assert np.abs(u[0].cpu().numpy() - so.optimal_u).max() < 1e-8 * max(1.0, np.abs(so.optimal_u).max())
+    u0, _, s0, _ = cs.solve_batch(up[:0], yp[:0], us[:0], ys[:0])
+    assert u0.shape == (0, 60)
