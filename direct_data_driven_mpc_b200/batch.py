@@ -229,6 +229,55 @@ class ControllerSet:
             return u_sys, y_sys, status, iters, xf
         return u_sys, y_sys, status, iters
 
+    def closed_loop_host(self, plant: LTIPlant, x0, u_past0, y_past0, u_s, y_s, n_steps: int, w=None,
+                         noise_seed: int = 0, scenario_id0: int = 0, noise_eps: Optional[float] = None,
+                         ctrl_idx=None, tol: float = 1e-8, max_iter: int = 2000, chunks: int = 8,
+                         out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None):
+        """Host-buffer entry point (what a user of the reference's loop function calls): inputs are
+        host arrays (pinned torch tensors are used as they are), outputs are pinned host tensors
+        ``u_sys (B, n_steps, m)``, ``y_sys (B, n_steps, p)``, ``status (B)``.  The batch is cut into
+        ``chunks`` pieces that alternate between two streams so the device->host copy of one piece
+        overlaps the closed loops of the next."""
+        def host(a, cols):
+            t = a if isinstance(a, torch.Tensor) else torch.from_numpy(_f64(a))
+            return t.reshape(-1, cols)
+        x0h, uph, yph = host(x0, plant.n_x), host(u_past0, self.n * self.m), host(y_past0, self.n * self.p)
+        ush, ysh = host(u_s, self.m), host(y_s, self.p)
+        B = x0h.shape[0]
+        wh = None if w is None else (w if isinstance(w, torch.Tensor) else torch.from_numpy(_f64(w))).reshape(B, n_steps, self.p)
+        cih = None if ctrl_idx is None else torch.as_tensor(ctrl_idx).to(torch.int32).reshape(B)
+        if out is None:
+            u_out = torch.empty(B, n_steps, self.m, dtype=torch.float64, pin_memory=True)
+            y_out = torch.empty(B, n_steps, self.p, dtype=torch.float64, pin_memory=True)
+        else:
+            u_out, y_out = out
+        st_out = torch.empty(B, dtype=torch.int32, pin_memory=True)
+        chunks = max(1, min(chunks, B))
+        bounds = [(B * i) // chunks for i in range(chunks + 1)]
+        dev = self.device
+        with torch.cuda.device(dev):
+            cur = torch.cuda.current_stream()
+            streams = [torch.cuda.Stream(), torch.cuda.Stream()] if chunks > 1 else [cur]
+            for s in streams:
+                s.wait_stream(cur)
+            for i in range(chunks):
+                lo, hi = bounds[i], bounds[i + 1]
+                if hi == lo:
+                    continue
+                with torch.cuda.stream(streams[i % len(streams)]):
+                    d = lambda t: t[lo:hi].to(dev, non_blocking=True)
+                    u_d_, y_d_, st_, _ = self.closed_loop(
+                        plant, d(x0h), d(uph), d(yph), d(ush), d(ysh), n_steps, w=None if wh is None else d(wh),
+                        noise_seed=noise_seed, scenario_id0=scenario_id0 + lo, noise_eps=noise_eps,
+                        ctrl_idx=None if cih is None else d(cih), tol=tol, max_iter=max_iter)
+                    u_out[lo:hi].copy_(u_d_, non_blocking=True)
+                    y_out[lo:hi].copy_(y_d_, non_blocking=True)
+                    st_out[lo:hi].copy_(st_, non_blocking=True)
+            for s in streams:
+                cur.wait_stream(s)
+            cur.synchronize()
+        return u_out, y_out, st_out
+
     def close(self) -> None:
         if getattr(self, "_h", None):
             _lib.lib.ddmpc_set_destroy(self._h)

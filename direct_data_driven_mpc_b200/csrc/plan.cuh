@@ -47,4 +47,11 @@ struct Plan {
 struct ddmpc_set {
     ddmpc_params prm;
     ddmpc::Plan plan;
+    // last plant uploaded by ddmpc_closed_loop_batch (re-used while unchanged, so the
+    // launch path stays asynchronous)
+    mutable std::vector<double> plant_host;
+    mutable ddmpc::DevBuf plant_dev;
+    // fast_loop.cu: host copy of the applied gain rows + device copy of their set-point block
+    mutable std::vector<double> fast_host;
+    mutable ddmpc::DevBuf fast_ksp;
 };

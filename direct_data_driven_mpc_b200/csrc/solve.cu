@@ -255,8 +255,9 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
     }
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
-__device__ __forceinline__ double u53(uint32_t a, uint32_t b) {
-    return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) * (1.0 / 9007199254740992.0);
+// 52 random mantissa bits -> v in [1, 2); the noise sample is eps * (2 v - 3) in [-eps, eps)
+__device__ __forceinline__ double unit12(uint32_t hi, uint32_t lo) {
+    return __hiloint2double((int)(0x3FF00000u | (hi >> 12)), (int)((hi << 20) | (lo >> 12)));
 }
 
 struct LoopArgs {
@@ -343,8 +344,8 @@ __global__ void k_closed_loop(KArgs a, LoopArgs la, int B, const int *__restrict
                     uint32_t o[4];
                     philox4x32_10((uint32_t)k, (uint32_t)ch, (uint32_t)(sid & 0xffffffffu), (uint32_t)(sid >> 32),
                                   (uint32_t)(la.seed & 0xffffffffu), (uint32_t)(la.seed >> 32), o);
-                    SMV(yk, 2 * ch) = la.eps * (2.0 * u53(o[0], o[1]) - 1.0);
-                    if (2 * ch + 1 < p) SMV(yk, 2 * ch + 1) = la.eps * (2.0 * u53(o[2], o[3]) - 1.0);
+                    SMV(yk, 2 * ch) = la.eps * (2.0 * unit12(o[0], o[1]) - 3.0);
+                    if (2 * ch + 1 < p) SMV(yk, 2 * ch + 1) = la.eps * (2.0 * unit12(o[2], o[3]) - 3.0);
                 }
             }
             // y = C x + D u + w   (uses the pre-update state; model_simulation.py:94)
@@ -389,6 +390,11 @@ __global__ void k_closed_loop(KArgs a, LoopArgs la, int B, const int *__restrict
 // ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
+int closed_loop_fast_try(const ddmpc_set *set, const ddmpc_plant *plant, int B, const int *ctrl_idx, const double *x0,
+                         const double *u_past0, const double *y_past0, const double *u_s, const double *y_s,
+                         const double *w, uint64_t seed, uint64_t id0, double eps, int n_steps, double *u_sys,
+                         double *y_sys, int *status, int *iters, double *x_final, cudaStream_t st);
+
 static KArgs make_kargs(const ddmpc_set *set, double tol, int max_iter) {
     const Plan &pl = set->plan;
     const Dims &d = pl.d;
@@ -418,9 +424,10 @@ static int pick_tpb(size_t per_thread_doubles, size_t *smem_bytes) {
 int solve_batch_device(const ddmpc_set *set, int B, const int *ctrl_idx, const double *u_past, const double *y_past,
                        const double *u_s, const double *y_s, double tol, int max_iter, double *optimal_u, double *cost,
                        int *status, int *iters, double *t_out, cudaStream_t st) {
-    if (!set || B < 0 || !u_past || !y_past || !u_s || !y_s || !optimal_u)
-        return fail(DDMPC_ERR_INVALID_ARG, "solve_batch: null argument");
+    if (!set || B < 0) return fail(DDMPC_ERR_INVALID_ARG, "solve_batch: bad set / batch size");
     if (B == 0) return DDMPC_OK;
+    if (!u_past || !y_past || !u_s || !y_s || !optimal_u)
+        return fail(DDMPC_ERR_INVALID_ARG, "solve_batch: null argument");
     KArgs a = make_kargs(set, tol, max_iter);
     size_t smem = 0;
     const int tpb = pick_tpb((size_t)a.nth + 4 * (size_t)a.nb, &smem);
@@ -533,7 +540,9 @@ int ddmpc_closed_loop_batch(const ddmpc_set *set, const ddmpc_plant *plant, int 
                             const double *y_s, const double *w, uint64_t noise_seed, uint64_t scenario_id0,
                             double noise_eps, int n_steps, double tol, int max_iter, double *u_sys, double *y_sys,
                             int32_t *status, int32_t *iters, double *x_final, void *stream) {
-    if (!set || !plant || B < 0 || n_steps < 0 || !x0 || !u_past0 || !y_past0 || !u_s || !y_s || !u_sys || !y_sys)
+    if (!set || !plant || B < 0 || n_steps < 0) return fail(DDMPC_ERR_INVALID_ARG, "closed_loop_batch: bad argument");
+    if (B == 0 || n_steps == 0) return DDMPC_OK;
+    if (!x0 || !u_past0 || !y_past0 || !u_s || !y_s || !u_sys || !y_sys)
         return fail(DDMPC_ERR_INVALID_ARG, "closed_loop_batch: null argument");
     const Dims &d = set->plan.d;
     if (plant->m != d.m || plant->p != d.p || plant->n_x <= 0 || !plant->A || !plant->B || !plant->C || !plant->D)
@@ -543,6 +552,11 @@ int ddmpc_closed_loop_batch(const ddmpc_set *set, const ddmpc_plant *plant, int 
     if (B == 0 || n_steps == 0) return DDMPC_OK;
     cudaStream_t st = (cudaStream_t)stream;
     const int nxp = plant->n_x;
+    {   // register-resident specialisation (shared equality-only controller, small system)
+        const int rc = closed_loop_fast_try(set, plant, B, ctrl_idx, x0, u_past0, y_past0, u_s, y_s, w, noise_seed,
+                                            scenario_id0, noise_eps, n_steps, u_sys, y_sys, status, iters, x_final, st);
+        if (rc != -1) return rc;
+    }
     // plant matrices -> device (small; one staging buffer)
     const size_t nA = (size_t)nxp * nxp, nB = (size_t)nxp * d.m, nC = (size_t)d.p * nxp, nD = (size_t)d.p * d.m;
     std::vector<double> hp(nA + nB + nC + nD);
@@ -550,9 +564,14 @@ int ddmpc_closed_loop_batch(const ddmpc_set *set, const ddmpc_plant *plant, int 
     std::copy(plant->B, plant->B + nB, hp.begin() + nA);
     std::copy(plant->C, plant->C + nC, hp.begin() + nA + nB);
     std::copy(plant->D, plant->D + nD, hp.begin() + nA + nB + nC);
-    DevBuf dp;
-    DDMPC_CUDA(dp.alloc(sizeof(double) * hp.size()));
-    DDMPC_CUDA(cudaMemcpyAsync(dp.p, hp.data(), sizeof(double) * hp.size(), cudaMemcpyHostToDevice, st));
+    if (hp != set->plant_host) {
+        // a different plant: wait for loops still reading the old one, then replace it
+        DDMPC_CUDA(cudaDeviceSynchronize());
+        DDMPC_CUDA(set->plant_dev.alloc(sizeof(double) * hp.size()));
+        DDMPC_CUDA(cudaMemcpy(set->plant_dev.p, hp.data(), sizeof(double) * hp.size(), cudaMemcpyHostToDevice));
+        set->plant_host = hp;
+    }
+    const DevBuf &dp = set->plant_dev;
     KArgs a = make_kargs(set, tol, max_iter);
     LoopArgs la{};
     la.n_x = nxp; la.n_steps = n_steps; la.n_mpc = n_mpc;
@@ -566,7 +585,6 @@ int ddmpc_closed_loop_batch(const ddmpc_set *set, const ddmpc_plant *plant, int 
     k_closed_loop<<<ceil_div(B, tpb), tpb, smem, st>>>(a, la, B, ctrl_idx, x0, u_past0, y_past0, u_s, y_s, u_sys, y_sys,
                                                         status, iters, x_final);
     DDMPC_LAUNCH_CHECK();
-    DDMPC_CUDA(cudaStreamSynchronize(st));  // plant staging buffer lifetime
     return DDMPC_OK;
 }
 
@@ -595,6 +613,7 @@ int ddmpc_closed_loop_batch_host(const ddmpc_set *set, const ddmpc_plant *plant,
     DDMPC_TRY(s.out((size_t)B * plant->n_x, &dxf, x_final != nullptr));
     DDMPC_TRY(ddmpc_closed_loop_batch(set, plant, B, dc, dx0, dup, dyp, dus, dys, dw, noise_seed, scenario_id0,
                                       noise_eps, n_steps, tol, max_iter, dU, dY, dst, dit, dxf, nullptr));
+    DDMPC_CUDA(cudaStreamSynchronize(nullptr));
     DDMPC_CUDA(cudaMemcpy(u_sys, dU, sizeof(double) * B * n_steps * d.m, cudaMemcpyDeviceToHost));
     DDMPC_CUDA(cudaMemcpy(y_sys, dY, sizeof(double) * B * n_steps * d.p, cudaMemcpyDeviceToHost));
     if (status) DDMPC_CUDA(cudaMemcpy(status, dst, sizeof(int32_t) * B, cudaMemcpyDeviceToHost));

@@ -562,9 +562,9 @@ def philox4x32(ctr: np.ndarray, key: np.ndarray) -> np.ndarray:
 
 
 def philox_noise(seed: int, scenario_ids: np.ndarray, n_steps: int, p: int, eps_max: float) -> np.ndarray:
-    """w[b, k, j] = eps_max * (2*d - 1), d = 53-bit uniform built from the Philox
-    words of counter (k, j//2, id_lo, id_hi), key (seed_lo, seed_hi):
-    d = ((x[2*(j%2)] >> 5) * 2^26 + (x[2*(j%2)+1] >> 6)) * 2^-53."""
+    """w[b, k, j] = eps_max * (2*v - 3), v in [1, 2) the double whose 52 mantissa bits are the
+    top 52 bits of the 64-bit word (x[2*(j%2)] << 32 | x[2*(j%2)+1]) of the Philox output for
+    counter (k, j//2, id_lo, id_hi), key (seed_lo, seed_hi)."""
     ids = np.asarray(scenario_ids, dtype=np.uint64)
     B = ids.shape[0]
     nch = (p + 1) // 2
@@ -577,7 +577,8 @@ def philox_noise(seed: int, scenario_ids: np.ndarray, n_steps: int, p: int, eps_
     key[..., 0] = np.uint32(seed & 0xFFFFFFFF)
     key[..., 1] = np.uint32((seed >> 32) & 0xFFFFFFFF)
     x = philox4x32(ctr, key).astype(np.uint64)
-    d0 = ((x[..., 0] >> np.uint64(5)) * np.uint64(67108864) + (x[..., 1] >> np.uint64(6))).astype(np.float64) * (1.0 / 9007199254740992.0)
-    d1 = ((x[..., 2] >> np.uint64(5)) * np.uint64(67108864) + (x[..., 3] >> np.uint64(6))).astype(np.float64) * (1.0 / 9007199254740992.0)
-    d = np.stack([d0, d1], axis=-1).reshape(B, n_steps, 2 * nch)[..., :p]
-    return eps_max * (2.0 * d - 1.0)
+    one = np.uint64(0x3FF0000000000000)
+    v0 = ((((x[..., 0] << np.uint64(32)) | x[..., 1]) >> np.uint64(12)) | one).view(np.float64)
+    v1 = ((((x[..., 2] << np.uint64(32)) | x[..., 3]) >> np.uint64(12)) | one).view(np.float64)
+    d = np.stack([v0, v1], axis=-1).reshape(B, n_steps, 2 * nch)[..., :p]
+    return eps_max * (2.0 * d - 3.0)
