@@ -23,7 +23,7 @@ namespace ddmpc {
 
 template <int N, int M, int P, int NX, int NMPC>
 struct FastCoef {
-    double Kw[NMPC * M][N * (M + P)];  // rows of Ku acting on [u_past; y_past]
+    double Kt[N * (M + P)][NMPC * M];  // Kt[j][k] = Ku[k][j]: gain of window entry j on planned input k
     double A[NX][NX], B[NX][M], C[P][NX], D[P][M];
 };
 
@@ -48,50 +48,68 @@ __device__ __forceinline__ void philox_round(uint32_t &c0, uint32_t &c1, uint32_
     c2 = n2;
 }
 
-__device__ __forceinline__ double unit12_fast(uint32_t hi, uint32_t lo) {
-    return __hiloint2double((int)(0x3FF00000u | (hi >> 12)), (int)((hi << 20) | (lo >> 12)));
+__device__ __forceinline__ double unit32_fast(uint32_t x) {
+    return __hiloint2double((int)(0x3FF00000u | (x >> 12)), (int)(x << 20));
 }
 
 // One trajectory element (EL doubles) per step.  With EL == 2 an element is 16 B and the
-// elements f-1, f (f odd) fill one 32 B sector: `pend` carries the even element until its
-// partner arrives and the pair leaves as a single STG.256.
+// elements f-1, f (f odd) fill one 32 B sector, so they leave as a single STG.256; the even
+// element is not stored on its own - at the next step it is still the newest entry of the
+// measurement window (`prev`).
 template <int EL, bool PAIR>
-__device__ __forceinline__ void emit(double *__restrict__ base, size_t f, bool odd, bool first, double (&pend)[EL],
-                                     const double (&cur)[EL]) {
+__device__ __forceinline__ void emit(double *__restrict__ base, size_t f, bool odd, bool first,
+                                     const double (&prev)[EL], const double (&cur)[EL]) {
     if constexpr (EL == 2 && PAIR) {
         if (odd) {
             if (first) {
                 *reinterpret_cast<double2 *>(base + f * 2) = make_double2(cur[0], cur[1]);
             } else {
-                asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(base + (f - 1) * 2), "d"(pend[0]),
-                             "d"(pend[1]), "d"(cur[0]), "d"(cur[1])
+                asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(base + (f - 1) * 2), "d"(prev[0]),
+                             "d"(prev[1]), "d"(cur[0]), "d"(cur[1])
                              : "memory");
             }
         }
-        pend[0] = cur[0];
-        pend[1] = cur[1];
     } else {
 #pragma unroll
         for (int i = 0; i < EL; ++i) base[f * EL + i] = cur[i];
     }
 }
 
+constexpr int FAST_TPB = 64;
+
 template <int N, int M, int P, int NX, int NMPC, bool PHILOX, bool PAIR>
-__global__ void __maxnreg__(144)
-k_closed_loop_fast(const __grid_constant__ FastCoef<N, M, P, NX, NMPC> cf, const FastArgs a) {
+__global__ void __launch_bounds__(FAST_TPB, 8)
+k_closed_loop_fast(const __grid_constant__ FastCoef<N, M, P, NX, NMPC> cfp, const FastArgs a) {
+    // Coefficients: kernel parameter -> shared memory once per block.  (Feeding DFMA from the
+    // constant bank makes ptxas stage every coefficient through the 63-entry uniform register
+    // file on sm_100a, which thrashes; warp-broadcast LDS.128 is cheaper.)
+    using Coef = FastCoef<N, M, P, NX, NMPC>;
+    constexpr int R = NMPC * M;                  // planned-input rows per solve
+    constexpr bool ALIGNED = (NMPC % N) == 0;    // a block starts with the ring at slot 0
+    __shared__ __align__(16) Coef cf;
+    __shared__ double csp_s[R][FAST_TPB];        // per-loop set-point term of the planned inputs
+    __shared__ double up_s[R][FAST_TPB];         // planned inputs of the current n-step block
+    __shared__ double wu_s[N * M][FAST_TPB];     // measurement window, ring over N time slots
+    __shared__ double wy_s[N * P][FAST_TPB];
+    {
+        const double *src = reinterpret_cast<const double *>(&cfp);
+        double *dst = reinterpret_cast<double *>(&cf);
+        for (int i = threadIdx.x; i < (int)(sizeof(Coef) / sizeof(double)); i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
     // thread -> loop map: first half of the block takes even loops, second half odd loops, so
     // the sector parity of a step is uniform across a warp
     const int half = blockDim.x >> 1;
     const int tl = threadIdx.x;
     const int b = blockIdx.x * blockDim.x + 2 * (tl % half) + (tl / half);
     if (b >= a.B) return;
-    double x[NX], wu[N * M], wy[N * P], csp[NMPC * M];
+    double x[NX];
 #pragma unroll
     for (int i = 0; i < NX; ++i) x[i] = a.x0[(size_t)b * NX + i];
 #pragma unroll
-    for (int i = 0; i < N * M; ++i) wu[i] = a.u_past0[(size_t)b * N * M + i];
+    for (int i = 0; i < N * M; ++i) wu_s[i][tl] = a.u_past0[(size_t)b * N * M + i];
 #pragma unroll
-    for (int i = 0; i < N * P; ++i) wy[i] = a.y_past0[(size_t)b * N * P + i];
+    for (int i = 0; i < N * P; ++i) wy_s[i][tl] = a.y_past0[(size_t)b * N * P + i];
     {
         double sp[M + P];
 #pragma unroll
@@ -99,57 +117,100 @@ k_closed_loop_fast(const __grid_constant__ FastCoef<N, M, P, NX, NMPC> cf, const
 #pragma unroll
         for (int i = 0; i < P; ++i) sp[M + i] = a.y_s[(size_t)b * P + i];
 #pragma unroll
-        for (int k = 0; k < NMPC * M; ++k) {
+        for (int k = 0; k < R; ++k) {
             double acc = 0.0;
 #pragma unroll
             for (int j = 0; j < M + P; ++j) acc = fma(__ldg(a.Ksp + k * (M + P) + j), sp[j], acc);
-            csp[k] = acc;
+            csp_s[k][tl] = acc;
         }
     }
     const size_t f0 = (size_t)b * a.n_steps;
+    uint32_t nw[4] = {0u, 0u, 0u, 0u};   // words of the current Philox call
     const unsigned long long sid = a.id0 + (unsigned long long)b;
     const uint32_t sid_lo = (uint32_t)sid, sid_hi = (uint32_t)(sid >> 32);
-    double pu[M], py[P], up[NMPC * M];
-#pragma unroll
-    for (int i = 0; i < M; ++i) pu[i] = 0.0;
-#pragma unroll
-    for (int i = 0; i < P; ++i) py[i] = 0.0;
 
-    // ---- QP solve (equality-only => affine in the window): planned inputs
-    auto solve = [&]() {
+    // ---- QP solve (equality-only => affine in the window): planned inputs = csp + Kw * window.
+    // Window entry jj (0 = oldest) sits in ring slot (t0 + jj) % N.
+    // `cfz` is &cf plus an opaque zero refreshed every block: without it ptxas treats the
+    // coefficient loads as loop invariant, hoists all of them into registers and spills.
+    const Coef *cfz = &cf;
+    auto solve = [&](const int t0) {
+        {
+            int zoff;
+            asm volatile("mov.u32 %0, 0;" : "=r"(zoff));
+            cfz = &cf + zoff;
+        }
+        const double (*cspz)[FAST_TPB] = csp_s + (cfz - &cf);
+        constexpr int SPLIT = (R >= 8) ? 1 : (R >= 4 ? 2 : 4);   // more partial sums when rows are few
+        double acc[SPLIT][R];
 #pragma unroll
-        for (int k = 0; k < NMPC * M; ++k) {
-            double acc0 = csp[k], acc1 = 0.0;
+        for (int k = 0; k < R; ++k) {
+            acc[0][k] = cspz[k][tl];
 #pragma unroll
-            for (int j = 0; j < N * M; ++j) {
-                if (j & 1) acc1 = fma(cf.Kw[k][j], wu[j], acc1);
-                else acc0 = fma(cf.Kw[k][j], wu[j], acc0);
+            for (int q = 1; q < SPLIT; ++q) acc[q][k] = 0.0;
+        }
+        const int base = ALIGNED ? 0 : (t0 % N);
+#pragma unroll
+        for (int jj = 0; jj < N; ++jj) {
+            const int slot = ALIGNED ? jj : ((base + jj) % N);
+#pragma unroll
+            for (int i = 0; i < M; ++i) {
+                const double wj = wu_s[slot * M + i][tl];
+#pragma unroll
+                for (int k = 0; k < R; ++k) acc[jj % SPLIT][k] = fma(cfz->Kt[jj * M + i][k], wj, acc[jj % SPLIT][k]);
             }
 #pragma unroll
-            for (int j = 0; j < N * P; ++j) {
-                if (j & 1) acc1 = fma(cf.Kw[k][N * M + j], wy[j], acc1);
-                else acc0 = fma(cf.Kw[k][N * M + j], wy[j], acc0);
+            for (int i = 0; i < P; ++i) {
+                const double wj = wy_s[slot * P + i][tl];
+#pragma unroll
+                for (int k = 0; k < R; ++k)
+                    acc[jj % SPLIT][k] = fma(cfz->Kt[N * M + jj * P + i][k], wj, acc[jj % SPLIT][k]);
             }
-            up[k] = acc0 + acc1;
+        }
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            double v = acc[0][k];
+#pragma unroll
+            for (int q = 1; q < SPLIT; ++q) v += acc[q][k];
+            up_s[k][tl] = v;
         }
     };
-    // ---- one plant step with the s-th planned input: noise, y, x, record, window shift
+    // ---- one plant step with the s-th planned input: noise, y, x, record, window update
     auto step = [&](const int s, const int k) {
         double u[M], y[P];
 #pragma unroll
-        for (int i = 0; i < M; ++i) u[i] = up[s * M + i];
+        for (int i = 0; i < M; ++i) u[i] = up_s[s * M + i][tl];
         if constexpr (!PHILOX) {
 #pragma unroll
             for (int i = 0; i < P; ++i) y[i] = __ldg(a.w + (f0 + k) * P + i);
+        } else if constexpr ((NMPC * P) % 4 == 0) {
+            // noise word q = k*P + i is word (q & 3) of Philox call (q >> 2); a block starts on a
+            // call boundary, so call index and word are compile-time offsets from the block base
+#pragma unroll
+            for (int i = 0; i < P; ++i) {
+                const int qs = s * P + i;
+                if ((qs & 3) == 0) {
+                    uint32_t c0 = (uint32_t)(((unsigned)(k - s) * (unsigned)P) >> 2) + (uint32_t)(qs >> 2), c1 = 0u,
+                             c2 = sid_lo, c3 = sid_hi;
+#pragma unroll
+                    for (int r = 0; r < 10; ++r) philox_round(c0, c1, c2, c3, a.rk[2 * r], a.rk[2 * r + 1]);
+                    nw[0] = c0; nw[1] = c1; nw[2] = c2; nw[3] = c3;
+                }
+                y[i] = a.eps * (2.0 * unit32_fast(nw[qs & 3]) - 3.0);
+            }
         } else {
 #pragma unroll
-            for (int ch = 0; ch < (P + 1) / 2; ++ch) {
-                uint32_t c0 = (uint32_t)k, c1 = (uint32_t)ch, c2 = sid_lo, c3 = sid_hi;
+            for (int i = 0; i < P; ++i) {
+                const unsigned q = (unsigned)k * (unsigned)P + (unsigned)i;
+                if (i == 0 || (q & 3u) == 0u) {
+                    uint32_t c0 = q >> 2, c1 = 0u, c2 = sid_lo, c3 = sid_hi;
 #pragma unroll
-                for (int r = 0; r < 10; ++r) philox_round(c0, c1, c2, c3, a.rk[2 * r], a.rk[2 * r + 1]);
-                // same order of operations as the oracle: eps * (2 v - 3)
-                y[2 * ch] = a.eps * (2.0 * unit12_fast(c0, c1) - 3.0);
-                if (2 * ch + 1 < P) y[2 * ch + 1] = a.eps * (2.0 * unit12_fast(c2, c3) - 3.0);
+                    for (int r = 0; r < 10; ++r) philox_round(c0, c1, c2, c3, a.rk[2 * r], a.rk[2 * r + 1]);
+                    nw[0] = c0; nw[1] = c1; nw[2] = c2; nw[3] = c3;
+                }
+                const unsigned l = q & 3u;
+                const uint32_t word = l == 0 ? nw[0] : (l == 1 ? nw[1] : (l == 2 ? nw[2] : nw[3]));
+                y[i] = a.eps * (2.0 * unit32_fast(word) - 3.0);
             }
         }
         // y = C x + D u + w   (pre-update state; model_simulation.py:94)
@@ -157,9 +218,9 @@ k_closed_loop_fast(const __grid_constant__ FastCoef<N, M, P, NX, NMPC> cf, const
         for (int i = 0; i < P; ++i) {
             double acc = 0.0, acd = 0.0;
 #pragma unroll
-            for (int j = 0; j < NX; ++j) acc = fma(cf.C[i][j], x[j], acc);
+            for (int j = 0; j < NX; ++j) acc = fma(cfz->C[i][j], x[j], acc);
 #pragma unroll
-            for (int j = 0; j < M; ++j) acd = fma(cf.D[i][j], u[j], acd);
+            for (int j = 0; j < M; ++j) acd = fma(cfz->D[i][j], u[j], acd);
             y[i] = (acc + acd) + y[i];
         }
         // x <- A x + B u      (model_simulation.py:96)
@@ -168,57 +229,68 @@ k_closed_loop_fast(const __grid_constant__ FastCoef<N, M, P, NX, NMPC> cf, const
         for (int i = 0; i < NX; ++i) {
             double acc = 0.0, acb = 0.0;
 #pragma unroll
-            for (int j = 0; j < NX; ++j) acc = fma(cf.A[i][j], x[j], acc);
+            for (int j = 0; j < NX; ++j) acc = fma(cfz->A[i][j], x[j], acc);
 #pragma unroll
-            for (int j = 0; j < M; ++j) acb = fma(cf.B[i][j], u[j], acb);
+            for (int j = 0; j < M; ++j) acb = fma(cfz->B[i][j], u[j], acb);
             xn[i] = acc + acb;
         }
 #pragma unroll
         for (int i = 0; i < NX; ++i) x[i] = xn[i];
-        // record (full-sector stores)
+        // record (full-sector stores); the previous element is the newest window entry
+        const int slot = ALIGNED ? (s % N) : (k % N);            // oldest slot: overwritten below
+        const int pslot = ALIGNED ? ((s + N - 1) % N) : ((k + N - 1) % N);
         const size_t f = f0 + k;
         const bool odd = (f & 1) != 0;
-        emit<M, PAIR>(a.u_sys, f, odd, k == 0, pu, u);
-        emit<P, PAIR>(a.y_sys, f, odd, k == 0, py, y);
-        // window shift (controller.py:893-895)
+        if constexpr (PAIR) {
+            if (odd) {   // warp-uniform
+                double pvu[M], pvy[P];
 #pragma unroll
-        for (int i = 0; i < N * M - M; ++i) wu[i] = wu[i + M];
+                for (int i = 0; i < M; ++i) pvu[i] = wu_s[pslot * M + i][tl];
 #pragma unroll
-        for (int i = 0; i < M; ++i) wu[N * M - M + i] = u[i];
+                for (int i = 0; i < P; ++i) pvy[i] = wy_s[pslot * P + i][tl];
+                emit<M, true>(a.u_sys, f, true, k == 0, pvu, u);
+                emit<P, true>(a.y_sys, f, true, k == 0, pvy, y);
+            }
+        } else {
+            emit<M, false>(a.u_sys, f, odd, k == 0, u, u);
+            emit<P, false>(a.y_sys, f, odd, k == 0, y, y);
+        }
+        // window update (controller.py:893-895): the oldest slot receives (u, y)
 #pragma unroll
-        for (int i = 0; i < N * P - P; ++i) wy[i] = wy[i + P];
+        for (int i = 0; i < M; ++i) wu_s[slot * M + i][tl] = u[i];
 #pragma unroll
-        for (int i = 0; i < P; ++i) wy[N * P - P + i] = y[i];
+        for (int i = 0; i < P; ++i) wy_s[slot * P + i][tl] = y[i];
     };
 
-    int solves = 0, t0 = 0;
+    int t0 = 0;
     for (; t0 + NMPC <= a.n_steps; t0 += NMPC) {   // full n-step blocks: no guards
-        solve();
-        ++solves;
+        solve(t0);
 #pragma unroll
         for (int s = 0; s < NMPC; ++s) step(s, t0 + s);
     }
     if (t0 < a.n_steps) {                          // last, partial block (controller_operation.py:278)
-        solve();
-        ++solves;
+        solve(t0);
 #pragma unroll
         for (int s = 0; s < NMPC; ++s)
             if (t0 + s < a.n_steps) step(s, t0 + s);
     }
-    if constexpr (PAIR) {   // an unpaired final element still sits in pend
+    const int lslot = (a.n_steps + N - 1) % N;     // newest window entry
+    if constexpr (PAIR) {   // an unpaired final element is still the newest window entry
         const size_t fl = f0 + a.n_steps - 1;
         if ((fl & 1) == 0) {
-            if constexpr (M == 2) *reinterpret_cast<double2 *>(a.u_sys + fl * 2) = make_double2(pu[0], pu[1]);
-            if constexpr (P == 2) *reinterpret_cast<double2 *>(a.y_sys + fl * 2) = make_double2(py[0], py[1]);
+            if constexpr (M == 2)
+                *reinterpret_cast<double2 *>(a.u_sys + fl * 2) = make_double2(wu_s[lslot * M][tl], wu_s[lslot * M + 1][tl]);
+            if constexpr (P == 2)
+                *reinterpret_cast<double2 *>(a.y_sys + fl * 2) = make_double2(wy_s[lslot * P][tl], wy_s[lslot * P + 1][tl]);
         }
     }
     bool finite = true;
 #pragma unroll
     for (int i = 0; i < NX; ++i) finite = finite && isfinite(x[i]);
 #pragma unroll
-    for (int i = 0; i < N * P; ++i) finite = finite && isfinite(wy[i]);
+    for (int i = 0; i < N * P; ++i) finite = finite && isfinite(wy_s[i][tl]);
     if (a.status) a.status[b] = finite ? DDMPC_SOLVE_OPTIMAL : DDMPC_SOLVE_NONFINITE;
-    if (a.iters) a.iters[b] = solves;
+    if (a.iters) a.iters[b] = (a.n_steps + NMPC - 1) / NMPC;
     if (a.x_final) {
 #pragma unroll
         for (int i = 0; i < NX; ++i) a.x_final[(size_t)b * NX + i] = x[i];
@@ -251,7 +323,7 @@ static int launch_fast(const ddmpc_set *set, const ddmpc_plant *plant, const Fas
     }
     Coef cf;
     for (int k = 0; k < NMPC * M; ++k)
-        for (int j = 0; j < NW; ++j) cf.Kw[k][j] = cache[(size_t)k * d.nth + j];
+        for (int j = 0; j < NW; ++j) cf.Kt[j][k] = cache[(size_t)k * d.nth + j];
     for (int i = 0; i < NX; ++i) {
         for (int j = 0; j < NX; ++j) cf.A[i][j] = plant->A[i * NX + j];
         for (int j = 0; j < M; ++j) cf.B[i][j] = plant->B[i * M + j];
@@ -266,7 +338,7 @@ static int launch_fast(const ddmpc_set *set, const ddmpc_plant *plant, const Fas
         a.rk[2 * r] = (uint32_t)a.seed + (uint32_t)r * 0x9E3779B9u;
         a.rk[2 * r + 1] = (uint32_t)(a.seed >> 32) + (uint32_t)r * 0xBB67AE85u;
     }
-    const int tpb = 64;
+    const int tpb = FAST_TPB;
     const dim3 grid(ceil_div(a.B, tpb));
     // 32-byte pairing needs 16-byte elements (M == 2 and P == 2) and 32-byte aligned outputs
     const bool pair = (M == 2 && P == 2) && ((reinterpret_cast<uintptr_t>(a.u_sys) & 31) == 0) &&

@@ -255,9 +255,9 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
     }
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
-// 52 random mantissa bits -> v in [1, 2); the noise sample is eps * (2 v - 3) in [-eps, eps)
-__device__ __forceinline__ double unit12(uint32_t hi, uint32_t lo) {
-    return __hiloint2double((int)(0x3FF00000u | (hi >> 12)), (int)((hi << 20) | (lo >> 12)));
+// 32 random mantissa bits -> v in [1, 2); the noise sample is eps * (2 v - 3) in [-eps, eps)
+__device__ __forceinline__ double unit32(uint32_t x) {
+    return __hiloint2double((int)(0x3FF00000u | (x >> 12)), (int)(x << 20));
 }
 
 struct LoopArgs {
@@ -340,12 +340,17 @@ __global__ void k_closed_loop(KArgs a, LoopArgs la, int B, const int *__restrict
             if (la.w) {
                 for (int i = 0; i < p; ++i) SMV(yk, i) = la.w[((size_t)b * la.n_steps + k) * p + i];
             } else {
-                for (int ch = 0; ch < (p + 1) / 2; ++ch) {
-                    uint32_t o[4];
-                    philox4x32_10((uint32_t)k, (uint32_t)ch, (uint32_t)(sid & 0xffffffffu), (uint32_t)(sid >> 32),
-                                  (uint32_t)(la.seed & 0xffffffffu), (uint32_t)(la.seed >> 32), o);
-                    SMV(yk, 2 * ch) = la.eps * (2.0 * unit12(o[0], o[1]) - 3.0);
-                    if (2 * ch + 1 < p) SMV(yk, 2 * ch + 1) = la.eps * (2.0 * unit12(o[2], o[3]) - 3.0);
+                // noise word q = k*p + i is word (q & 3) of Philox call (q >> 2)
+                uint32_t o[4];
+                unsigned last = 0xffffffffu;
+                for (int i = 0; i < p; ++i) {
+                    const unsigned q = (unsigned)k * (unsigned)p + (unsigned)i;
+                    if ((q >> 2) != last) {
+                        last = q >> 2;
+                        philox4x32_10(last, 0u, (uint32_t)(sid & 0xffffffffu), (uint32_t)(sid >> 32),
+                                      (uint32_t)(la.seed & 0xffffffffu), (uint32_t)(la.seed >> 32), o);
+                    }
+                    SMV(yk, i) = la.eps * (2.0 * unit32(o[q & 3]) - 3.0);
                 }
             }
             // y = C x + D u + w   (uses the pre-update state; model_simulation.py:94)

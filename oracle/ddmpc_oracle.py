@@ -562,23 +562,20 @@ def philox4x32(ctr: np.ndarray, key: np.ndarray) -> np.ndarray:
 
 
 def philox_noise(seed: int, scenario_ids: np.ndarray, n_steps: int, p: int, eps_max: float) -> np.ndarray:
-    """w[b, k, j] = eps_max * (2*v - 3), v in [1, 2) the double whose 52 mantissa bits are the
-    top 52 bits of the 64-bit word (x[2*(j%2)] << 32 | x[2*(j%2)+1]) of the Philox output for
-    counter (k, j//2, id_lo, id_hi), key (seed_lo, seed_hi)."""
+    """w[b, k, j] = eps_max * (2*v - 3) where, with q = k*p + j, v in [1, 2) is the double whose
+    top 32 mantissa bits are word (q & 3) of Philox4x32-10(counter = (q >> 2, 0, id_lo, id_hi),
+    key = (seed_lo, seed_hi)) and whose low 20 mantissa bits are zero."""
     ids = np.asarray(scenario_ids, dtype=np.uint64)
     B = ids.shape[0]
-    nch = (p + 1) // 2
-    ctr = np.zeros((B, n_steps, nch, 4), dtype=np.uint32)
-    ctr[..., 0] = np.arange(n_steps, dtype=np.uint32)[None, :, None]
-    ctr[..., 1] = np.arange(nch, dtype=np.uint32)[None, None, :]
-    ctr[..., 2] = (ids & np.uint64(0xFFFFFFFF)).astype(np.uint32)[:, None, None]
-    ctr[..., 3] = (ids >> np.uint64(32)).astype(np.uint32)[:, None, None]
-    key = np.zeros((B, n_steps, nch, 2), dtype=np.uint32)
+    nq = n_steps * p
+    ncall = (nq + 3) // 4
+    ctr = np.zeros((B, ncall, 4), dtype=np.uint32)
+    ctr[..., 0] = np.arange(ncall, dtype=np.uint32)[None, :]
+    ctr[..., 2] = (ids & np.uint64(0xFFFFFFFF)).astype(np.uint32)[:, None]
+    ctr[..., 3] = (ids >> np.uint64(32)).astype(np.uint32)[:, None]
+    key = np.zeros((B, ncall, 2), dtype=np.uint32)
     key[..., 0] = np.uint32(seed & 0xFFFFFFFF)
     key[..., 1] = np.uint32((seed >> 32) & 0xFFFFFFFF)
-    x = philox4x32(ctr, key).astype(np.uint64)
-    one = np.uint64(0x3FF0000000000000)
-    v0 = ((((x[..., 0] << np.uint64(32)) | x[..., 1]) >> np.uint64(12)) | one).view(np.float64)
-    v1 = ((((x[..., 2] << np.uint64(32)) | x[..., 3]) >> np.uint64(12)) | one).view(np.float64)
-    d = np.stack([v0, v1], axis=-1).reshape(B, n_steps, 2 * nch)[..., :p]
-    return eps_max * (2.0 * d - 3.0)
+    x = philox4x32(ctr, key).astype(np.uint64).reshape(B, ncall * 4)[:, :nq]
+    v = ((x << np.uint64(20)) | np.uint64(0x3FF0000000000000)).view(np.float64)
+    return (eps_max * (2.0 * v - 3.0)).reshape(B, n_steps, p)
