@@ -37,13 +37,13 @@ SOLVES_PER_LOOP = 101          # ceil(401 / 4)
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--loops", type=int, default=65536, help="closed loops per GPU")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--e2e-steps", type=int, default=10)
     return ap.parse_args()
 
 
@@ -169,7 +169,7 @@ class Clocks:
                                           int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))))
                     except Exception:
                         pass
-                    time.sleep(0.01)
+                    time.sleep(0.05)
             self.thread = threading.Thread(target=poll, daemon=True)
             self.thread.start()
         except Exception:
@@ -188,7 +188,7 @@ class Clocks:
                     reasons.add(name)
         sm = [r[1] for r in inside]
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.smax, "reasons": sorted(reasons),
-                "samples": len(inside), "source": "NVML nvmlDeviceGetClockInfo / CurrentClocksEventReasons, 10 ms period"}
+                "samples": len(inside), "source": "NVML nvmlDeviceGetClockInfo / CurrentClocksEventReasons, 50 ms period"}
 
 
 def measured_peaks():
@@ -298,10 +298,10 @@ def main():
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get("k_closed_loop_dram_bytes_per_launch")
+            traffic = json.load(open(tpath)).get("k_closed_loop_fast_dram_bytes_per_launch")
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": "k_closed_loop", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "k_closed_loop_fast", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": k_ms,
                 "flops_per_solve_executed": 2 * (8 * 20) + 4 * 2 * (4 * 4 + 4 * 2 + 2 * 4 + 2 * 2)}
