@@ -43,6 +43,7 @@ def parse_args():
     ap.add_argument("--loops", type=int, default=65536, help="closed loops per GPU")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="time direct launches instead of CUDA-graph replays")
     ap.add_argument("--e2e-steps", type=int, default=10)
     return ap.parse_args()
 
@@ -139,7 +140,8 @@ def workload_config(loops, world):
             "noise": "device Philox4x32-10, seed 0, stream = global scenario id",
             "l2": "each step writes 841 MB of trajectories per GPU (> 126 MB L2); no flush needed",
             "parallelism": f"scenario-sharded x{world}, no data-path collective; one NCCL all_gather of per-loop "
-                           "metrics after the timed steps"}
+                           "metrics after the timed steps",
+            "launch": "each step is one k_closed_loop_fast launch replayed from a CUDA graph"}
 
 
 # --------------------------------------------------------------------------
@@ -256,15 +258,40 @@ def main():
     assert int(status.max()) == 0, "non-optimal solve status in the bench workload"
     solves_per_step = int(iters.sum().item())
     assert solves_per_step == B * SOLVES_PER_LOOP
+    # One step = one kernel launch; the Python call around it costs 0.1-0.4 ms on a busy host, more than the
+    # kernel.  Capture the step once in a CUDA graph and replay it (launch-bound inner loop -> graph).
+    graph, launches_per_step = None, 1
+    if not args.no_graph:
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                step()
+            torch.cuda.current_stream().wait_stream(side)
+            l0 = _lib.kernel_launches()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                _, _, status, iters = step()
+            launches_per_step = _lib.kernel_launches() - l0
+        except Exception as exc:  # pragma: no cover
+            print(f"CUDA graph capture failed ({exc}); timing direct launches", file=sys.stderr)
+            graph = None
+    run_step = graph.replay if graph is not None else step
     for _ in range(max(args.warmup, 3)):       # W untimed warm-up steps, no idle gap before the timed region
-        step()
+        run_step()
     barrier()
     launches0 = _lib.kernel_launches()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     ev0.record()
+    dbg = os.environ.get("BENCH_DEBUG_EVENTS") == "1"
+    dbg_ev = []
     for _ in range(args.steps):
-        _, _, status, iters = step()
+        run_step()
+        if dbg:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            dbg_ev.append(e)
     # the only collective of the job: per-loop metrics (final tracking error + status) to every rank
     track = (y_sys[:, -1, :] - ys).abs().amax(dim=1)
     if world > 1:
@@ -273,7 +300,11 @@ def main():
     ev1.record()
     barrier()
     t1 = time.perf_counter()
-    launches = _lib.kernel_launches() - launches0
+    launches = (_lib.kernel_launches() - launches0) if graph is None else launches_per_step * args.steps
+    if dbg and rank == 0:
+        ts = np.array([dbg_ev[i].elapsed_time(dbg_ev[i + 1]) for i in range(len(dbg_ev) - 1)])
+        print("per-step ms: first", np.round(ts[:8], 3), "median", np.median(ts), "p90", np.percentile(ts, 90), "max",
+              ts.max(), "host loop s", t1 - t0, file=sys.stderr)
     ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -287,7 +318,7 @@ def main():
            for _ in range(min(args.steps, 50))]
     for a, b_ in kev:
         a.record()
-        step()
+        run_step()
         b_.record()
     torch.cuda.synchronize()
     k_ms = float(np.mean([a.elapsed_time(b_) for a, b_ in kev]))

@@ -78,10 +78,11 @@ __device__ __forceinline__ void emit(double *__restrict__ base, size_t f, bool o
     }
 }
 
-constexpr int FAST_TPB = 64;
-
-template <int N, int M, int P, int NX, int NMPC, bool PHILOX, bool PAIR>
-__global__ void __launch_bounds__(FAST_TPB, 8)
+// LPT = closed loops per thread.  Every coefficient fetched from the constant bank feeds LPT
+// DFMAs (one per loop), so LPT = 2 halves the pressure on the indexed-constant (ADU/IDC) path and
+// doubles the independent work between dependent instructions, at the price of half the warps.
+template <int N, int M, int P, int NX, int NMPC, int LPT, bool PHILOX, bool PAIR>
+__global__ void __launch_bounds__(LPT == 1 ? 64 : 32, 8)
 k_closed_loop_fast(const __grid_constant__ FastCoef<N, M, P, NX, NMPC> cfp, const FastArgs a) {
     // Coefficients stay in the kernel-parameter constant bank and are fetched with indexed LDC
     // (address = parameter base + a run-time zero).  Two alternatives were measured and lost:
@@ -91,41 +92,57 @@ k_closed_loop_fast(const __grid_constant__ FastCoef<N, M, P, NX, NMPC> cfp, cons
     using Coef = FastCoef<N, M, P, NX, NMPC>;
     constexpr int R = NMPC * M;                  // planned-input rows per solve
     constexpr bool ALIGNED = (NMPC % N) == 0;    // a block starts with the ring at slot 0
-    __shared__ double csp_s[R][FAST_TPB];        // per-loop set-point term of the planned inputs
-    __shared__ double up_s[R][FAST_TPB];         // planned inputs of the current n-step block
-    __shared__ double wu_s[N * M][FAST_TPB];     // measurement window, ring over N time slots
-    __shared__ double wy_s[N * P][FAST_TPB];
-    // thread -> loop map: first half of the block takes even loops, second half odd loops, so
-    // the sector parity of a step is uniform across a warp
-    const int half = blockDim.x >> 1;
+    constexpr int FAST_TPB = LPT == 1 ? 64 : 32; // one warp per block when a thread carries two loops
+    __shared__ double csp_s[R][LPT][FAST_TPB];        // per-loop set-point term of the planned inputs
+    __shared__ double up_s[R][LPT][FAST_TPB];         // planned inputs of the current n-step block
+    __shared__ double wu_s[N * M][LPT][FAST_TPB];     // measurement window, ring over N time slots
+    __shared__ double wy_s[N * P][LPT][FAST_TPB];
+    // thread -> loop map (64 loops per block): LPT = 1: the first warp takes the even loops and the
+    // second warp the odd ones; LPT = 2: thread t carries loops 2t (l = 0) and 2t + 1 (l = 1).
+    // Either way the sector parity of a step is uniform across a warp for a given l.
     const int tl = threadIdx.x;
-    const int b = blockIdx.x * blockDim.x + 2 * (tl % half) + (tl / half);
-    if (b >= a.B) return;
-    double x[NX];
+    int b[LPT];
+    bool live[LPT];
+    size_t f0[LPT];
+    uint32_t sid_lo[LPT], sid_hi[LPT];
 #pragma unroll
-    for (int i = 0; i < NX; ++i) x[i] = a.x0[(size_t)b * NX + i];
+    for (int l = 0; l < LPT; ++l) {
+        b[l] = LPT == 1 ? blockIdx.x * 64 + 2 * (tl % 32) + (tl / 32) : blockIdx.x * 64 + 2 * tl + l;
+        live[l] = b[l] < a.B;
+        if (!live[l]) b[l] = 0;                  // dead slots replay loop 0 and never store
+        f0[l] = (size_t)b[l] * a.n_steps;
+        const unsigned long long sid = a.id0 + (unsigned long long)b[l];
+        sid_lo[l] = (uint32_t)sid;
+        sid_hi[l] = (uint32_t)(sid >> 32);
+    }
+    if (!live[0]) return;
+    double x[LPT][NX];
 #pragma unroll
-    for (int i = 0; i < N * M; ++i) wu_s[i][tl] = a.u_past0[(size_t)b * N * M + i];
+    for (int l = 0; l < LPT; ++l) {
 #pragma unroll
-    for (int i = 0; i < N * P; ++i) wy_s[i][tl] = a.y_past0[(size_t)b * N * P + i];
-    {
+        for (int i = 0; i < NX; ++i) x[l][i] = a.x0[(size_t)b[l] * NX + i];
+#pragma unroll
+        for (int i = 0; i < N * M; ++i) wu_s[i][l][tl] = a.u_past0[(size_t)b[l] * N * M + i];
+#pragma unroll
+        for (int i = 0; i < N * P; ++i) wy_s[i][l][tl] = a.y_past0[(size_t)b[l] * N * P + i];
         double sp[M + P];
 #pragma unroll
-        for (int i = 0; i < M; ++i) sp[i] = a.u_s[(size_t)b * M + i];
+        for (int i = 0; i < M; ++i) sp[i] = a.u_s[(size_t)b[l] * M + i];
 #pragma unroll
-        for (int i = 0; i < P; ++i) sp[M + i] = a.y_s[(size_t)b * P + i];
+        for (int i = 0; i < P; ++i) sp[M + i] = a.y_s[(size_t)b[l] * P + i];
 #pragma unroll
         for (int k = 0; k < R; ++k) {
             double acc = 0.0;
 #pragma unroll
             for (int j = 0; j < M + P; ++j) acc = fma(__ldg(a.Ksp + k * (M + P) + j), sp[j], acc);
-            csp_s[k][tl] = acc;
+            csp_s[k][l][tl] = acc;
         }
     }
-    const size_t f0 = (size_t)b * a.n_steps;
-    uint32_t nw[4] = {0u, 0u, 0u, 0u};   // words of the current Philox call
-    const unsigned long long sid = a.id0 + (unsigned long long)b;
-    const uint32_t sid_lo = (uint32_t)sid, sid_hi = (uint32_t)(sid >> 32);
+    uint32_t nw[LPT][4];                         // words of the current Philox call
+#pragma unroll
+    for (int l = 0; l < LPT; ++l)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) nw[l][i] = 0u;
 
     // ---- QP solve (equality-only => affine in the window): planned inputs = csp + Kw * window.
     // Window entry jj (0 = oldest) sits in ring slot (t0 + jj) % N.
@@ -133,129 +150,162 @@ k_closed_loop_fast(const __grid_constant__ FastCoef<N, M, P, NX, NMPC> cfp, cons
     // treats the coefficient loads as loop invariant, hoists all of them and spills.
     const Coef *cfz = &cfp;
     auto solve = [&](const int t0) {
-        // a.zmask is 0 at run time: a uniform, loop-variant zero that ptxas cannot fold
-        const int zuni = t0 & a.zmask;
+        const int zuni = t0 & a.zmask;           // a.zmask is 0 at run time
         cfz = &cfp + zuni;
-        const double (*cspz)[FAST_TPB] = csp_s + zuni;
-        constexpr int SPLIT = (R >= 8) ? 1 : (R >= 4 ? 2 : 4);   // more partial sums when rows are few
-        double acc[SPLIT][R];
+        constexpr int SPLIT = (R * LPT >= 8) ? 1 : (R * LPT >= 4 ? 2 : 4);   // partial sums when rows are few
+        double acc[SPLIT][LPT][R];
 #pragma unroll
-        for (int k = 0; k < R; ++k) {
-            acc[0][k] = cspz[k][tl];
+        for (int l = 0; l < LPT; ++l)
 #pragma unroll
-            for (int q = 1; q < SPLIT; ++q) acc[q][k] = 0.0;
-        }
+            for (int k = 0; k < R; ++k) {
+                acc[0][l][k] = csp_s[k + zuni][l][tl];
+#pragma unroll
+                for (int q = 1; q < SPLIT; ++q) acc[q][l][k] = 0.0;
+            }
         const int base = ALIGNED ? 0 : (t0 % N);
 #pragma unroll
         for (int jj = 0; jj < N; ++jj) {
             const int slot = ALIGNED ? jj : ((base + jj) % N);
 #pragma unroll
-            for (int i = 0; i < M; ++i) {
-                const double wj = wu_s[slot * M + i][tl];
+            for (int i = 0; i < M + P; ++i) {
+                double wj[LPT];
 #pragma unroll
-                for (int k = 0; k < R; ++k) acc[jj % SPLIT][k] = fma(cfz->Kt[jj * M + i][k], wj, acc[jj % SPLIT][k]);
-            }
+                for (int l = 0; l < LPT; ++l)
+                    wj[l] = (i < M) ? wu_s[slot * M + (i < M ? i : 0)][l][tl] : wy_s[slot * P + (i >= M ? i - M : 0)][l][tl];
+                const int col = (i < M) ? (jj * M + i) : (N * M + jj * P + (i - M));
 #pragma unroll
-            for (int i = 0; i < P; ++i) {
-                const double wj = wy_s[slot * P + i][tl];
+                for (int k = 0; k < R; ++k) {
+                    const double c = cfz->Kt[col][k];
 #pragma unroll
-                for (int k = 0; k < R; ++k)
-                    acc[jj % SPLIT][k] = fma(cfz->Kt[N * M + jj * P + i][k], wj, acc[jj % SPLIT][k]);
+                    for (int l = 0; l < LPT; ++l) acc[jj % SPLIT][l][k] = fma(c, wj[l], acc[jj % SPLIT][l][k]);
+                }
             }
         }
 #pragma unroll
-        for (int k = 0; k < R; ++k) {
-            double v = acc[0][k];
+        for (int l = 0; l < LPT; ++l)
 #pragma unroll
-            for (int q = 1; q < SPLIT; ++q) v += acc[q][k];
-            up_s[k][tl] = v;
-        }
+            for (int k = 0; k < R; ++k) {
+                double v = acc[0][l][k];
+#pragma unroll
+                for (int q = 1; q < SPLIT; ++q) v += acc[q][l][k];
+                up_s[k][l][tl] = v;
+            }
     };
     // ---- one plant step with the s-th planned input: noise, y, x, record, window update
     auto step = [&](const int s, const int k) {
-        double u[M], y[P];
+        double u[LPT][M], y[LPT][P];
 #pragma unroll
-        for (int i = 0; i < M; ++i) u[i] = up_s[s * M + i][tl];
-        if constexpr (!PHILOX) {
+        for (int l = 0; l < LPT; ++l) {
 #pragma unroll
-            for (int i = 0; i < P; ++i) y[i] = __ldg(a.w + (f0 + k) * P + i);
-        } else if constexpr ((NMPC * P) % 4 == 0) {
-            // noise word q = k*P + i is word (q & 3) of Philox call (q >> 2); a block starts on a
-            // call boundary, so call index and word are compile-time offsets from the block base
+            for (int i = 0; i < M; ++i) u[l][i] = up_s[s * M + i][l][tl];
+            if constexpr (!PHILOX) {
 #pragma unroll
-            for (int i = 0; i < P; ++i) {
-                const int qs = s * P + i;
-                if ((qs & 3) == 0) {
-                    uint32_t c0 = (uint32_t)(((unsigned)(k - s) * (unsigned)P) >> 2) + (uint32_t)(qs >> 2), c1 = 0u,
-                             c2 = sid_lo, c3 = sid_hi;
+                for (int i = 0; i < P; ++i) y[l][i] = __ldg(a.w + (f0[l] + k) * P + i);
+            } else if constexpr ((NMPC * P) % 4 == 0) {
+                // noise word q = k*P + i is word (q & 3) of Philox call (q >> 2); a block starts on a
+                // call boundary, so call index and word are compile-time offsets from the block base
 #pragma unroll
-                    for (int r = 0; r < 10; ++r) philox_round(c0, c1, c2, c3, a.rk[2 * r], a.rk[2 * r + 1]);
-                    nw[0] = c0; nw[1] = c1; nw[2] = c2; nw[3] = c3;
+                for (int i = 0; i < P; ++i) {
+                    const int qs = s * P + i;
+                    if ((qs & 3) == 0) {
+                        uint32_t c0 = (uint32_t)(((unsigned)(k - s) * (unsigned)P) >> 2) + (uint32_t)(qs >> 2),
+                                 c1 = 0u, c2 = sid_lo[l], c3 = sid_hi[l];
+#pragma unroll
+                        for (int r = 0; r < 10; ++r) philox_round(c0, c1, c2, c3, a.rk[2 * r], a.rk[2 * r + 1]);
+                        nw[l][0] = c0; nw[l][1] = c1; nw[l][2] = c2; nw[l][3] = c3;
+                    }
+                    y[l][i] = a.eps * (2.0 * unit32_fast(nw[l][qs & 3]) - 3.0);
                 }
-                y[i] = a.eps * (2.0 * unit32_fast(nw[qs & 3]) - 3.0);
-            }
-        } else {
+            } else {
 #pragma unroll
-            for (int i = 0; i < P; ++i) {
-                const unsigned q = (unsigned)k * (unsigned)P + (unsigned)i;
-                if (i == 0 || (q & 3u) == 0u) {
-                    uint32_t c0 = q >> 2, c1 = 0u, c2 = sid_lo, c3 = sid_hi;
+                for (int i = 0; i < P; ++i) {
+                    const unsigned q = (unsigned)k * (unsigned)P + (unsigned)i;
+                    if (i == 0 || (q & 3u) == 0u) {
+                        uint32_t c0 = q >> 2, c1 = 0u, c2 = sid_lo[l], c3 = sid_hi[l];
 #pragma unroll
-                    for (int r = 0; r < 10; ++r) philox_round(c0, c1, c2, c3, a.rk[2 * r], a.rk[2 * r + 1]);
-                    nw[0] = c0; nw[1] = c1; nw[2] = c2; nw[3] = c3;
+                        for (int r = 0; r < 10; ++r) philox_round(c0, c1, c2, c3, a.rk[2 * r], a.rk[2 * r + 1]);
+                        nw[l][0] = c0; nw[l][1] = c1; nw[l][2] = c2; nw[l][3] = c3;
+                    }
+                    const unsigned w4 = q & 3u;
+                    const uint32_t word = w4 == 0 ? nw[l][0] : (w4 == 1 ? nw[l][1] : (w4 == 2 ? nw[l][2] : nw[l][3]));
+                    y[l][i] = a.eps * (2.0 * unit32_fast(word) - 3.0);
                 }
-                const unsigned l = q & 3u;
-                const uint32_t word = l == 0 ? nw[0] : (l == 1 ? nw[1] : (l == 2 ? nw[2] : nw[3]));
-                y[i] = a.eps * (2.0 * unit32_fast(word) - 3.0);
             }
         }
         // y = C x + D u + w   (pre-update state; model_simulation.py:94)
 #pragma unroll
         for (int i = 0; i < P; ++i) {
-            double acc = 0.0, acd = 0.0;
+            double acc[LPT], acd[LPT];
 #pragma unroll
-            for (int j = 0; j < NX; ++j) acc = fma(cfz->C[i][j], x[j], acc);
+            for (int l = 0; l < LPT; ++l) acc[l] = acd[l] = 0.0;
 #pragma unroll
-            for (int j = 0; j < M; ++j) acd = fma(cfz->D[i][j], u[j], acd);
-            y[i] = (acc + acd) + y[i];
+            for (int j = 0; j < NX; ++j) {
+                const double c = cfz->C[i][j];
+#pragma unroll
+                for (int l = 0; l < LPT; ++l) acc[l] = fma(c, x[l][j], acc[l]);
+            }
+#pragma unroll
+            for (int j = 0; j < M; ++j) {
+                const double c = cfz->D[i][j];
+#pragma unroll
+                for (int l = 0; l < LPT; ++l) acd[l] = fma(c, u[l][j], acd[l]);
+            }
+#pragma unroll
+            for (int l = 0; l < LPT; ++l) y[l][i] = (acc[l] + acd[l]) + y[l][i];
         }
         // x <- A x + B u      (model_simulation.py:96)
-        double xn[NX];
+        double xn[LPT][NX];
 #pragma unroll
         for (int i = 0; i < NX; ++i) {
-            double acc = 0.0, acb = 0.0;
+            double acc[LPT], acb[LPT];
 #pragma unroll
-            for (int j = 0; j < NX; ++j) acc = fma(cfz->A[i][j], x[j], acc);
+            for (int l = 0; l < LPT; ++l) acc[l] = acb[l] = 0.0;
 #pragma unroll
-            for (int j = 0; j < M; ++j) acb = fma(cfz->B[i][j], u[j], acb);
-            xn[i] = acc + acb;
+            for (int j = 0; j < NX; ++j) {
+                const double c = cfz->A[i][j];
+#pragma unroll
+                for (int l = 0; l < LPT; ++l) acc[l] = fma(c, x[l][j], acc[l]);
+            }
+#pragma unroll
+            for (int j = 0; j < M; ++j) {
+                const double c = cfz->B[i][j];
+#pragma unroll
+                for (int l = 0; l < LPT; ++l) acb[l] = fma(c, u[l][j], acb[l]);
+            }
+#pragma unroll
+            for (int l = 0; l < LPT; ++l) xn[l][i] = acc[l] + acb[l];
         }
-#pragma unroll
-        for (int i = 0; i < NX; ++i) x[i] = xn[i];
-        // record (full-sector stores); the previous element is the newest window entry
         const int slot = ALIGNED ? (s % N) : (k % N);            // oldest slot: overwritten below
         const int pslot = ALIGNED ? ((s + N - 1) % N) : ((k + N - 1) % N);
-        const size_t f = f0 + k;
-        const bool odd = (f & 1) != 0;
-        if constexpr (PAIR) {
-            if (odd) {   // warp-uniform
-                double pvu[M], pvy[P];
 #pragma unroll
-                for (int i = 0; i < M; ++i) pvu[i] = wu_s[pslot * M + i][tl];
+        for (int l = 0; l < LPT; ++l) {
 #pragma unroll
-                for (int i = 0; i < P; ++i) pvy[i] = wy_s[pslot * P + i][tl];
-                emit<M, true>(a.u_sys, f, true, k == 0, pvu, u);
-                emit<P, true>(a.y_sys, f, true, k == 0, pvy, y);
+            for (int i = 0; i < NX; ++i) x[l][i] = xn[l][i];
+            // record (full-sector stores); the previous element is the newest window entry
+            const size_t f = f0[l] + k;
+            const bool odd = (f & 1) != 0;
+            if (live[l]) {
+                if constexpr (PAIR) {
+                    if (odd) {   // warp-uniform
+                        double pvu[M], pvy[P];
+#pragma unroll
+                        for (int i = 0; i < M; ++i) pvu[i] = wu_s[pslot * M + i][l][tl];
+#pragma unroll
+                        for (int i = 0; i < P; ++i) pvy[i] = wy_s[pslot * P + i][l][tl];
+                        emit<M, true>(a.u_sys, f, true, k == 0, pvu, u[l]);
+                        emit<P, true>(a.y_sys, f, true, k == 0, pvy, y[l]);
+                    }
+                } else {
+                    emit<M, false>(a.u_sys, f, odd, k == 0, u[l], u[l]);
+                    emit<P, false>(a.y_sys, f, odd, k == 0, y[l], y[l]);
+                }
             }
-        } else {
-            emit<M, false>(a.u_sys, f, odd, k == 0, u, u);
-            emit<P, false>(a.y_sys, f, odd, k == 0, y, y);
+            // window update (controller.py:893-895): the oldest slot receives (u, y)
+#pragma unroll
+            for (int i = 0; i < M; ++i) wu_s[slot * M + i][l][tl] = u[l][i];
+#pragma unroll
+            for (int i = 0; i < P; ++i) wy_s[slot * P + i][l][tl] = y[l][i];
         }
-        // window update (controller.py:893-895): the oldest slot receives (u, y)
-#pragma unroll
-        for (int i = 0; i < M; ++i) wu_s[slot * M + i][tl] = u[i];
-#pragma unroll
-        for (int i = 0; i < P; ++i) wy_s[slot * P + i][tl] = y[i];
     };
 
     int t0 = 0;
@@ -271,25 +321,31 @@ k_closed_loop_fast(const __grid_constant__ FastCoef<N, M, P, NX, NMPC> cfp, cons
             if (t0 + s < a.n_steps) step(s, t0 + s);
     }
     const int lslot = (a.n_steps + N - 1) % N;     // newest window entry
-    if constexpr (PAIR) {   // an unpaired final element is still the newest window entry
-        const size_t fl = f0 + a.n_steps - 1;
-        if ((fl & 1) == 0) {
-            if constexpr (M == 2)
-                *reinterpret_cast<double2 *>(a.u_sys + fl * 2) = make_double2(wu_s[lslot * M][tl], wu_s[lslot * M + 1][tl]);
-            if constexpr (P == 2)
-                *reinterpret_cast<double2 *>(a.y_sys + fl * 2) = make_double2(wy_s[lslot * P][tl], wy_s[lslot * P + 1][tl]);
+#pragma unroll
+    for (int l = 0; l < LPT; ++l) {
+        if (!live[l]) continue;
+        if constexpr (PAIR) {   // an unpaired final element is still the newest window entry
+            const size_t fl = f0[l] + a.n_steps - 1;
+            if ((fl & 1) == 0) {
+                if constexpr (M == 2)
+                    *reinterpret_cast<double2 *>(a.u_sys + fl * 2) =
+                        make_double2(wu_s[lslot * M][l][tl], wu_s[lslot * M + 1][l][tl]);
+                if constexpr (P == 2)
+                    *reinterpret_cast<double2 *>(a.y_sys + fl * 2) =
+                        make_double2(wy_s[lslot * P][l][tl], wy_s[lslot * P + 1][l][tl]);
+            }
         }
-    }
-    bool finite = true;
+        bool finite = true;
 #pragma unroll
-    for (int i = 0; i < NX; ++i) finite = finite && isfinite(x[i]);
+        for (int i = 0; i < NX; ++i) finite = finite && isfinite(x[l][i]);
 #pragma unroll
-    for (int i = 0; i < N * P; ++i) finite = finite && isfinite(wy_s[i][tl]);
-    if (a.status) a.status[b] = finite ? DDMPC_SOLVE_OPTIMAL : DDMPC_SOLVE_NONFINITE;
-    if (a.iters) a.iters[b] = (a.n_steps + NMPC - 1) / NMPC;
-    if (a.x_final) {
+        for (int i = 0; i < N * P; ++i) finite = finite && isfinite(wy_s[i][l][tl]);
+        if (a.status) a.status[b[l]] = finite ? DDMPC_SOLVE_OPTIMAL : DDMPC_SOLVE_NONFINITE;
+        if (a.iters) a.iters[b[l]] = (a.n_steps + NMPC - 1) / NMPC;
+        if (a.x_final) {
 #pragma unroll
-        for (int i = 0; i < NX; ++i) a.x_final[(size_t)b * NX + i] = x[i];
+            for (int i = 0; i < NX; ++i) a.x_final[(size_t)b[l] * NX + i] = x[l][i];
+        }
     }
 }
 
@@ -596,18 +652,27 @@ static int launch_fast(const ddmpc_set *set, const ddmpc_plant *plant, const Fas
         a.rk[2 * r] = (uint32_t)a.seed + (uint32_t)r * 0x9E3779B9u;
         a.rk[2 * r + 1] = (uint32_t)(a.seed >> 32) + (uint32_t)r * 0xBB67AE85u;
     }
-    const int tpb = FAST_TPB;
-    const dim3 grid(ceil_div(a.B, tpb));
     // 32-byte pairing needs 16-byte elements (M == 2 and P == 2) and 32-byte aligned outputs
     const bool pair = (M == 2 && P == 2) && ((reinterpret_cast<uintptr_t>(a.u_sys) & 31) == 0) &&
                       ((reinterpret_cast<uintptr_t>(a.y_sys) & 31) == 0);
-    if (a.w) {
-        if (pair) k_closed_loop_fast<N, M, P, NX, NMPC, false, true><<<grid, tpb, 0, st>>>(cf, a);
-        else k_closed_loop_fast<N, M, P, NX, NMPC, false, false><<<grid, tpb, 0, st>>>(cf, a);
-    } else {
-        if (pair) k_closed_loop_fast<N, M, P, NX, NMPC, true, true><<<grid, tpb, 0, st>>>(cf, a);
-        else k_closed_loop_fast<N, M, P, NX, NMPC, true, false><<<grid, tpb, 0, st>>>(cf, a);
-    }
+    // loops per thread: 2 once the batch is large enough to keep every SM busy with half the warps
+    int lpt = a.B >= 16384 ? 2 : 1;
+    if (const char *e = getenv("DDMPC_LPT")) lpt = (e[0] == '2') ? 2 : 1;
+    const int tpb = lpt == 1 ? 64 : 32;
+    const dim3 grid(ceil_div(a.B, 64));
+#define DDMPC_LAUNCH_FAST(LPT_)                                                                              \
+    do {                                                                                                     \
+        if (a.w) {                                                                                           \
+            if (pair) k_closed_loop_fast<N, M, P, NX, NMPC, LPT_, false, true><<<grid, tpb, 0, st>>>(cf, a);   \
+            else k_closed_loop_fast<N, M, P, NX, NMPC, LPT_, false, false><<<grid, tpb, 0, st>>>(cf, a);       \
+        } else {                                                                                             \
+            if (pair) k_closed_loop_fast<N, M, P, NX, NMPC, LPT_, true, true><<<grid, tpb, 0, st>>>(cf, a);    \
+            else k_closed_loop_fast<N, M, P, NX, NMPC, LPT_, true, false><<<grid, tpb, 0, st>>>(cf, a);        \
+        }                                                                                                    \
+    } while (0)
+    if (lpt == 2) DDMPC_LAUNCH_FAST(2);
+    else DDMPC_LAUNCH_FAST(1);
+#undef DDMPC_LAUNCH_FAST
     DDMPC_LAUNCH_CHECK();
     return DDMPC_OK;
 }
