@@ -361,7 +361,8 @@ def main():
         dist.all_reduce(ems, op=dist.ReduceOp.MAX)
     e2e_value = world * solves_per_step * args.e2e_steps / (float(ems.item()) * 1e-3)
     assert int(hst.max()) == 0
-    assert torch.equal(hu[:64], u_sys[:64].cpu()), "host-API result differs from the device-resident run"
+    # (chunks of the host path may take a different kernel specialisation: same maths, different FP64 summation order)
+    assert torch.allclose(hu[:64], u_sys[:64].cpu(), rtol=1e-9, atol=1e-9), "host-API result differs from the device-resident run"
     h2d = sum(t.numel() * t.element_size() for t in (hx0, hup, hyp, hus, hys))
     d2h = hu.numel() * 8 + hy.numel() * 8 + B * 4
     e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -93,10 +93,17 @@ k_closed_loop_fast(const __grid_constant__ FastCoef<N, M, P, NX, NMPC> cfp, cons
     constexpr int R = NMPC * M;                  // planned-input rows per solve
     constexpr bool ALIGNED = (NMPC % N) == 0;    // a block starts with the ring at slot 0
     constexpr int FAST_TPB = LPT == 1 ? 64 : 32; // one warp per block when a thread carries two loops
-    __shared__ double csp_s[R][LPT][FAST_TPB];        // per-loop set-point term of the planned inputs
-    __shared__ double up_s[R][LPT][FAST_TPB];         // planned inputs of the current n-step block
-    __shared__ double wu_s[N * M][LPT][FAST_TPB];     // measurement window, ring over N time slots
-    __shared__ double wy_s[N * P][LPT][FAST_TPB];
+    // Tensor-core solve: with 8 planned-input rows the gain application U(8 x loops) = Ku(8 x 16) W(16 x loops)
+    // is exactly an m8n8k4 FP64 MMA shape: the warp's 64 loops are 8 n-tiles, the window is read from
+    // shared memory in B-fragment order and Ku lives in registers as A fragments.  This moves 128 of the
+    // 272 FMAs per loop and n-step block from the FP64 pipe to the (otherwise idle) tensor pipe.
+    constexpr bool USE_MMA = (R == 8) && (LPT == 2) && ((N * M) % 4 == 0) && ((N * P) % 4 == 0) && ALIGNED;
+    constexpr int TP = FAST_TPB + (USE_MMA ? 2 : 0);  // +2 doubles: row stride 68 = 4 (mod 16) -> B-fragment
+                                                      // loads of 4 rows x 8 loops spread over all banks
+    __shared__ __align__(16) double csp_s[R][LPT][TP];     // per-loop set-point term of the planned inputs
+    __shared__ __align__(16) double up_s[R][LPT][TP];      // planned inputs of the current n-step block
+    __shared__ __align__(16) double wu_s[N * M][LPT][TP];  // measurement window, ring over N time slots
+    __shared__ __align__(16) double wy_s[N * P][LPT][TP];
     // thread -> loop map (64 loops per block): LPT = 1: the first warp takes the even loops and the
     // second warp the odd ones; LPT = 2: thread t carries loops 2t (l = 0) and 2t + 1 (l = 1).
     // Either way the sector parity of a step is uniform across a warp for a given l.
@@ -115,7 +122,7 @@ k_closed_loop_fast(const __grid_constant__ FastCoef<N, M, P, NX, NMPC> cfp, cons
         sid_lo[l] = (uint32_t)sid;
         sid_hi[l] = (uint32_t)(sid >> 32);
     }
-    if (!live[0]) return;
+    if (!USE_MMA && !live[0]) return;             // (mma.sync needs the whole warp)
     double x[LPT][NX];
 #pragma unroll
     for (int l = 0; l < LPT; ++l) {
@@ -149,9 +156,52 @@ k_closed_loop_fast(const __grid_constant__ FastCoef<N, M, P, NX, NMPC> cfp, cons
     // `cfz` is &cfp plus a run-time zero that changes (formally) every block: without it ptxas
     // treats the coefficient loads as loop invariant, hoists all of them and spills.
     const Coef *cfz = &cfp;
+    double afrag[USE_MMA ? (N * (M + P)) / 4 : 1];   // A fragments: Ku[lane/4][4*ks + lane%4]
+    if constexpr (USE_MMA) {
+#pragma unroll
+        for (int ks = 0; ks < (N * (M + P)) / 4; ++ks) afrag[ks] = cfp.Kt[4 * ks + (tl & 3)][tl >> 2];
+        __syncwarp();                            // window / csp written above by their owner lanes
+    }
     auto solve = [&](const int t0) {
         const int zuni = t0 & a.zmask;           // a.zmask is 0 at run time
         cfz = &cfp + zuni;
+        if constexpr (USE_MMA) {
+            __syncwarp();                        // window entries of the previous block are visible
+            const int g = tl >> 2, q = tl & 3;   // fragment coordinates of this lane
+            constexpr int NT = FAST_TPB / 8;     // n-tiles (8 loops each) per l
+            // C fragments: rows g, loops 8*t8 + 2q, +1  <- set-point term.  k-steps outermost so that
+            // consecutive MMAs belong to different n-tiles (independent accumulators).
+            double2 c[LPT][NT];
+#pragma unroll
+            for (int l = 0; l < LPT; ++l)
+#pragma unroll
+                for (int t8 = 0; t8 < NT; ++t8) c[l][t8] = *reinterpret_cast<const double2 *>(&csp_s[g][l][8 * t8 + 2 * q]);
+#pragma unroll
+            for (int ks = 0; ks < (N * (M + P)) / 4; ++ks) {
+                // B fragment: window entry 4*ks + q of loop 8*t8 + g (entries 0..N*M-1 are u, then y)
+                const int e = 4 * ks + q;
+                double bv[LPT][NT];
+#pragma unroll
+                for (int l = 0; l < LPT; ++l)
+#pragma unroll
+                    for (int t8 = 0; t8 < NT; ++t8)
+                        bv[l][t8] = (4 * ks < N * M) ? wu_s[e < N * M ? e : 0][l][8 * t8 + g]
+                                                     : wy_s[e >= N * M ? e - N * M : 0][l][8 * t8 + g];
+#pragma unroll
+                for (int l = 0; l < LPT; ++l)
+#pragma unroll
+                    for (int t8 = 0; t8 < NT; ++t8)
+                        asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                            : "+d"(c[l][t8].x), "+d"(c[l][t8].y)
+                            : "d"(afrag[ks]), "d"(bv[l][t8]));
+            }
+#pragma unroll
+            for (int l = 0; l < LPT; ++l)
+#pragma unroll
+                for (int t8 = 0; t8 < NT; ++t8) *reinterpret_cast<double2 *>(&up_s[g][l][8 * t8 + 2 * q]) = c[l][t8];
+            __syncwarp();                        // planned inputs visible to their owner lanes
+            return;
+        }
         constexpr int SPLIT = (R * LPT >= 8) ? 1 : (R * LPT >= 4 ? 2 : 4);   // partial sums when rows are few
         double acc[SPLIT][LPT][R];
 #pragma unroll
