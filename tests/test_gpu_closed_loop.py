@@ -176,3 +176,66 @@ def test_many_loops_linearity_property():
     uc = cs.closed_loop(_plant(), comb(x), comb(up), comb(yp), comb(us), comb(ys), n_steps, w=comb(w))[0]
     lhs = outs[0] + outs[1] - outs[2]
     assert (torch.abs(lhs - uc).max() / torch.abs(uc).max()).item() < 1e-9
+
+
+@pytest.mark.parametrize("n_mpc", [1, 20])
+def test_config4_synthetic_system_vs_oracle(n_mpc):
+    """BASELINE config 4 (n=20, m=p=4, N=2000, L=40) on a small batch: generic kernel vs the literal-KKT oracle."""
+    from direct_data_driven_mpc_b200 import ControllerSet, scenarios as S
+    B, n_steps = 3, 41 if n_mpc == 20 else 6
+    sc = S.config4_batch(B, n_mpc_step=n_mpc)
+    prm, pl = sc["params"], sc["plant"]
+    cs = ControllerSet(prm["n"], 4, 4, sc["u_d"], sc["y_d"], prm["L"], prm["Q"], prm["R"], prm["eps_max"],
+                       prm["lamb_alpha"], prm["lamb_sigma"], prm["c"], 0, 1, n_mpc, True)
+    assert cs.info(0) == (320, 0)                                  # PE of order L + 2n = 80: rank 4 * 80
+    r = np.random.default_rng(0)
+    x0 = sc["x0"] + 0.1 * r.normal(size=sc["x0"].shape)
+    u_s = sc["u_s"] * r.uniform(0.8, 1.2, (B, 1))
+    y_s = u_s @ pl.equilibrium_gain().T
+    w = pl.eps_max * r.uniform(-1, 1, (B, n_steps, 4))
+    u, y, status, iters = cs.closed_loop(pl, x0, sc["u_past0"], sc["y_past0"], u_s, y_s, n_steps, w=w)
+    u, y = u.cpu().numpy(), y.cpu().numpy()
+    assert (status.cpu().numpy() == 0).all()
+    qp = O.OracleController(20, 4, 4, sc["u_d"], sc["y_d"], 40, prm["Q"], prm["R"], prm["u_s"], prm["y_s"],
+                            prm["eps_max"], prm["lamb_alpha"], prm["lamb_sigma"], prm["c"], O.SLACK_NONE, O.ROBUST,
+                            n_mpc, True, check_pe=False)
+    for b in range(B):
+        plant_o = O.Plant(pl.A, pl.B, pl.C, pl.D, pl.eps_max)
+        plant_o.x = x0[b].copy()
+        qp.u_s, qp.y_s = u_s[b].reshape(-1, 1), y_s[b].reshape(-1, 1)
+        qp.set_past_input_output_data(sc["u_past0"][b].reshape(-1, 1), sc["y_past0"][b].reshape(-1, 1))
+        u_ref, y_ref = O.closed_loop(plant_o, qp, n_steps, w[b])
+        assert _rel(u[b], u_ref) < 1e-5 and _rel(y[b], y_ref) < 1e-5, (b, _rel(u[b], u_ref))
+
+
+def test_config3_full_size_properties():
+    """65,536 loops (BASELINE config 3 size): every loop converges to its set-point, the batch equals the
+    concatenation of two half-batch shards (sharding invariance), and a sample matches the oracle."""
+    import torch
+    from direct_data_driven_mpc_b200 import ControllerSet, scenarios as S
+    B = 65536
+    sc = S.config3_batch(B)
+    prm, pl = sc["params"], sc["plant"]
+    cs = ControllerSet(4, 2, 2, sc["u_d"], sc["y_d"], 30, prm["Q"], prm["R"], prm["eps_max"], prm["lamb_alpha"],
+                       prm["lamb_sigma"], prm["c"], 0, 1, 4, True)
+    args = lambda lo, hi: (pl, sc["x0"][lo:hi], sc["u_past0"][lo:hi], sc["y_past0"][lo:hi], sc["u_s"][lo:hi],
+                           sc["y_s"][lo:hi], 401)
+    u, y, status, iters = cs.closed_loop(*args(0, B), noise_seed=0, scenario_id0=0, noise_eps=0.002)
+    assert int(status.max()) == 0 and int(iters.min()) == 101 and int(iters.max()) == 101
+    ys = torch.from_numpy(sc["y_s"]).to(y.device)
+    assert float((y[:, -1] - ys).abs().max()) < 0.02                 # settled near every set-point, no divergence
+    half = B // 2
+    ua, ya, _, _ = cs.closed_loop(*args(0, half), noise_seed=0, scenario_id0=0, noise_eps=0.002)
+    ub, yb, _, _ = cs.closed_loop(*args(half, B), noise_seed=0, scenario_id0=half, noise_eps=0.002)
+    # shards may run a different kernel specialisation (one vs two loops per thread): same numbers to ~1e-12
+    assert float((torch.cat([ua, ub]) - u).abs().max()) < 1e-9 and float((torch.cat([ya, yb]) - y).abs().max()) < 1e-9
+    ids = [0, 1, 255, 256, 40000, 65535]
+    w = O.philox_noise(0, np.array(ids), 401, 2, 0.002)
+    ctrl = O.make_controller(O.four_tank_params(), sc["u_d"], sc["y_d"])
+    for j, b in enumerate(ids):
+        plant_o = O.four_tank_plant()
+        plant_o.x = sc["x0"][b].copy()
+        ctrl.u_s, ctrl.y_s = sc["u_s"][b].reshape(-1, 1), sc["y_s"][b].reshape(-1, 1)
+        ctrl.set_past_input_output_data(sc["u_past0"][b].reshape(-1, 1), sc["y_past0"][b].reshape(-1, 1))
+        u_ref, y_ref = O.closed_loop(plant_o, ctrl, 401, w[j])
+        assert _rel(u[b].cpu().numpy(), u_ref) < 1e-5 and _rel(y[b].cpu().numpy(), y_ref) < 1e-5, b
