@@ -9,36 +9,43 @@ namespace ddmpc {
 // ---------------------------------------------------------------------------
 // C(MxN) = alpha * A(MxK) * diag(d) * B(KxN) + beta * C     (d optional)
 // element (i,j) of X lives at X[i*rsX + j*csX]; batch b adds b*bsX.
-// 64x64 tile, 256 threads, 4x4 per thread, K-tile 16.
+//
+// FP64 tensor-core GEMM: 64x64 CTA tile, 4 warps (2x2), each warp a 32x32 block of 4x4
+// mma.sync.m8n8k4.f64 tiles (DMMA), K staged through shared memory 16 at a time.
+// Fragment layout of m8n8k4 (g = lane/4, q = lane%4):  A[g][q], B[q][g], C[g][2q], C[g][2q+1].
+// Shared row strides are 4 (mod 16) doubles so the 4x4 (row, k) patch a half-warp reads hits
+// 16 distinct 8-byte bank pairs.
 // ---------------------------------------------------------------------------
 constexpr int GT = 64, GK = 16;
+constexpr int G_LDA = GK + 4;   // As[m][k]
+constexpr int G_LDB = GT + 4;   // Bs[k][n]
 
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(128)
 k_gemm(int M, int N, int K, double alpha,
        const double *__restrict__ A, long rsA, long csA, long bsA,
        const double *__restrict__ Bm, long rsB, long csB, long bsB,
        const double *__restrict__ dvec, long bsd,
        double beta, double *__restrict__ C, long rsC, long csC, long bsC) {
-    __shared__ double As[GK][GT + 1];
-    __shared__ double Bs[GK][GT + 1];
+    __shared__ double As[GT][G_LDA];
+    __shared__ double Bs[GK][G_LDB];
     const int b = blockIdx.z;
     A += (long)b * bsA;
     Bm += (long)b * bsB;
     C += (long)b * bsC;
     if (dvec) dvec += (long)b * bsd;
-    const int tid = threadIdx.x;
-    const int tx = tid & 15, ty = tid >> 4;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
+    const int g = lane >> 2, q = lane & 3;
     const int i0 = blockIdx.y * GT, j0 = blockIdx.x * GT;
-    double acc[4][4];
+    double acc[4][4][2];
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) acc[a][c] = 0.0;
+        for (int c = 0; c < 4; ++c) acc[a][c][0] = acc[a][c][1] = 0.0;
 
     for (int k0 = 0; k0 < K; k0 += GK) {
-        // stage A tile (GT x GK) and B tile (GK x GT)
-#pragma unroll
-        for (int e = tid; e < GT * GK; e += 256) {
+        // stage A tile (GT x GK) and B tile (GK x GT); consecutive threads follow the unit stride
+        for (int e = tid; e < GT * GK; e += 128) {
             int i, k;
             if (csA == 1) { i = e / GK; k = e % GK; } else { k = e / GT; i = e % GT; }
             double v = 0.0;
@@ -46,10 +53,9 @@ k_gemm(int M, int N, int K, double alpha,
                 v = A[(long)(i0 + i) * rsA + (long)(k0 + k) * csA];
                 if (dvec) v *= dvec[k0 + k];
             }
-            As[k][i] = v;
+            As[i][k] = v;
         }
-#pragma unroll
-        for (int e = tid; e < GT * GK; e += 256) {
+        for (int e = tid; e < GT * GK; e += 128) {
             int j, k;
             if (csB == 1) { k = e / GT; j = e % GT; } else { j = e / GK; k = e % GK; }
             double v = 0.0;
@@ -58,31 +64,37 @@ k_gemm(int M, int N, int K, double alpha,
         }
         __syncthreads();
 #pragma unroll
-        for (int k = 0; k < GK; ++k) {
-            double av[4], bv[4];
+        for (int ks = 0; ks < GK / 4; ++ks) {
+            double af[4], bf[4];
 #pragma unroll
-            for (int a = 0; a < 4; ++a) av[a] = As[k][ty + 16 * a];
+            for (int a = 0; a < 4; ++a) af[a] = As[wm + 8 * a + g][4 * ks + q];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) bv[c] = Bs[k][tx + 16 * c];
+            for (int c = 0; c < 4; ++c) bf[c] = Bs[4 * ks + q][wn + 8 * c + g];
 #pragma unroll
             for (int a = 0; a < 4; ++a)
 #pragma unroll
-                for (int c = 0; c < 4; ++c) acc[a][c] = fma(av[a], bv[c], acc[a][c]);
+                for (int c = 0; c < 4; ++c)
+                    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                        : "+d"(acc[a][c][0]), "+d"(acc[a][c][1])
+                        : "d"(af[a]), "d"(bf[c]));
         }
         __syncthreads();
     }
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
-        const int i = i0 + ty + 16 * a;
+        const int i = i0 + wm + 8 * a + g;
         if (i >= M) continue;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-            const int j = j0 + tx + 16 * c;
-            if (j >= N) continue;
-            double *cp = C + (long)i * rsC + (long)j * csC;
-            double v = alpha * acc[a][c];
-            if (beta != 0.0) v += beta * (*cp);
-            *cp = v;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int j = j0 + wn + 8 * c + 2 * q + h;
+                if (j >= N) continue;
+                double *cp = C + (long)i * rsC + (long)j * csC;
+                double v = alpha * acc[a][c][h];
+                if (beta != 0.0) v += beta * (*cp);
+                *cp = v;
+            }
         }
     }
 }
@@ -99,7 +111,7 @@ inline int gemm(cudaStream_t st, int batch, int M, int N, int K, double alpha, M
                 const double *dvec = nullptr, long bsd = 0) {
     if (M <= 0 || N <= 0 || batch <= 0) return DDMPC_OK;
     dim3 grid(ceil_div(N, GT), ceil_div(M, GT), batch);
-    k_gemm<<<grid, 256, 0, st>>>(M, N, K, alpha, A.p, A.rs, A.cs, A.bs, B.p, B.rs, B.cs, B.bs,
+    k_gemm<<<grid, 128, 0, st>>>(M, N, K, alpha, A.p, A.rs, A.cs, A.bs, B.p, B.rs, B.cs, B.bs,
                                  dvec, bsd, beta, C, rsC, csC, bsC);
     DDMPC_LAUNCH_CHECK();
     return DDMPC_OK;
@@ -109,7 +121,7 @@ inline int gemm(cudaStream_t st, int batch, int M, int N, int K, double alpha, M
 // In-place lower Cholesky of a row-major n x n matrix (ld), one CTA per batch
 // entry.  info[b] = 0 or (1 + index of the first non-positive pivot).
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024)
+static __global__ void __launch_bounds__(1024)
 k_potrf(int n, double *__restrict__ A, long ld, long bs, int *__restrict__ info) {
     A += (long)blockIdx.x * bs;
     const int tid = threadIdx.x, T = blockDim.x;
@@ -156,7 +168,7 @@ inline int potrf(cudaStream_t st, int batch, int n, double *A, long ld, long bs,
 //   trans == 0:  L   X = B        trans == 1:  L^T X = B
 // B (n x nrhs, row-major, ldb) is overwritten by X.  One thread per RHS column.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
+static __global__ void __launch_bounds__(128)
 k_trsm(int n, int nrhs, int trans, const double *__restrict__ Lm, long ldl, long bsl,
        double *__restrict__ Bm, long ldb, long bsb) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -220,7 +232,7 @@ __device__ __forceinline__ void jacobi_pair(int n2, int r, int k, int &p, int &q
     q = a < b ? b : a;
 }
 
-__global__ void __launch_bounds__(1024)
+static __global__ void __launch_bounds__(1024)
 k_jacobi(int n, double *__restrict__ A, long ld, long bsA, double *__restrict__ V, long ldv, long bsV,
          double *__restrict__ lam, long bsl, int max_sweeps) {
     extern __shared__ double sh[];  // c[n2/2], s[n2/2], red[32]

@@ -54,4 +54,7 @@ struct ddmpc_set {
     // fast_loop.cu: host copy of the applied gain rows + device copy of their set-point block
     mutable std::vector<double> fast_host;
     mutable ddmpc::DevBuf fast_ksp;
+    // gemm_loop.cu: workspace (block maps of the plant + value-major loop state) and its host key
+    mutable ddmpc::DevBuf gemm_ws;
+    mutable std::vector<double> gemm_host;
 };

@@ -239,3 +239,44 @@ def test_config3_full_size_properties():
         ctrl.set_past_input_output_data(sc["u_past0"][b].reshape(-1, 1), sc["y_past0"][b].reshape(-1, 1))
         u_ref, y_ref = O.closed_loop(plant_o, ctrl, 401, w[j])
         assert _rel(u[b].cpu().numpy(), u_ref) < 1e-5 and _rel(y[b].cpu().numpy(), y_ref) < 1e-5, b
+
+
+@pytest.mark.parametrize("n_mpc,n_steps", [(20, 47), (8, 20), (10, 10)])
+def test_config4_gemm_path_vs_generic_and_oracle(n_mpc, n_steps, monkeypatch):
+    """Large-system path (batch as the N dimension of DMMA GEMMs, block-stepped plant) vs the generic
+    thread-per-loop kernel on 512 loops, and vs the oracle on a sample; Philox and uploaded noise."""
+    from direct_data_driven_mpc_b200 import ControllerSet, scenarios as S
+    B = 512
+    sc = S.config4_batch(B, n_mpc_step=n_mpc)
+    prm, pl = sc["params"], sc["plant"]
+    cs = ControllerSet(prm["n"], 4, 4, sc["u_d"], sc["y_d"], prm["L"], prm["Q"], prm["R"], prm["eps_max"],
+                       prm["lamb_alpha"], prm["lamb_sigma"], prm["c"], 0, 1, n_mpc, True)
+    r = np.random.default_rng(1)
+    x0 = sc["x0"] + 0.1 * r.normal(size=sc["x0"].shape)
+    u_s = sc["u_s"] * r.uniform(0.8, 1.2, (B, 1))
+    y_s = u_s @ pl.equilibrium_gain().T
+    w = pl.eps_max * r.uniform(-1, 1, (B, n_steps, 4))
+    for noise in ("philox", "uploaded"):
+        kw = dict(w=w) if noise == "uploaded" else dict(noise_seed=5, scenario_id0=1000, noise_eps=0.002)
+        monkeypatch.delenv("DDMPC_FORCE_GENERIC", raising=False)
+        u1, y1, s1, i1, xf1 = cs.closed_loop(pl, x0, sc["u_past0"], sc["y_past0"], u_s, y_s, n_steps,
+                                             want_x_final=True, **kw)
+        monkeypatch.setenv("DDMPC_FORCE_GENERIC", "1")
+        u2, y2, s2, i2, xf2 = cs.closed_loop(pl, x0, sc["u_past0"], sc["y_past0"], u_s, y_s, n_steps,
+                                             want_x_final=True, **kw)
+        monkeypatch.delenv("DDMPC_FORCE_GENERIC", raising=False)
+        assert int(s1.max()) == 0 and int(s2.max()) == 0
+        assert (i1 == i2).all()
+        assert _rel(u1.cpu().numpy(), u2.cpu().numpy()) < 1e-9 and _rel(y1.cpu().numpy(), y2.cpu().numpy()) < 1e-9
+        assert _rel(xf1.cpu().numpy(), xf2.cpu().numpy()) < 1e-9
+    qp = O.OracleController(20, 4, 4, sc["u_d"], sc["y_d"], 40, prm["Q"], prm["R"], prm["u_s"], prm["y_s"],
+                            prm["eps_max"], prm["lamb_alpha"], prm["lamb_sigma"], prm["c"], O.SLACK_NONE, O.ROBUST,
+                            n_mpc, True, check_pe=False)
+    u1, y1 = u1.cpu().numpy(), y1.cpu().numpy()
+    for b in (0, 511):
+        plant_o = O.Plant(pl.A, pl.B, pl.C, pl.D, pl.eps_max)
+        plant_o.x = x0[b].copy()
+        qp.u_s, qp.y_s = u_s[b].reshape(-1, 1), y_s[b].reshape(-1, 1)
+        qp.set_past_input_output_data(sc["u_past0"][b].reshape(-1, 1), sc["y_past0"][b].reshape(-1, 1))
+        u_ref, y_ref = O.closed_loop(plant_o, qp, n_steps, w[b])
+        assert _rel(u1[b], u_ref) < 1e-5 and _rel(y1[b], y_ref) < 1e-5
