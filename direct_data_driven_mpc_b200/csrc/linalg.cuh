@@ -16,16 +16,21 @@ namespace ddmpc {
 // Shared row strides are 4 (mod 16) doubles so the 4x4 (row, k) patch a half-warp reads hits
 // 16 distinct 8-byte bank pairs.
 // ---------------------------------------------------------------------------
-constexpr int GT = 64, GK = 16;
+constexpr int GK = 16;
 constexpr int G_LDA = GK + 4;   // As[m][k]
-constexpr int G_LDB = GT + 4;   // Bs[k][n]
 
+// GT = CTA tile edge: 64 (warp tile 32x32) or 32 (warp tile 16x16, for products too small to fill
+// 148 SMs with 64x64 tiles)
+template <int GT>
 static __global__ void __launch_bounds__(128)
 k_gemm(int M, int N, int K, double alpha,
        const double *__restrict__ A, long rsA, long csA, long bsA,
        const double *__restrict__ Bm, long rsB, long csB, long bsB,
        const double *__restrict__ dvec, long bsd,
        double beta, double *__restrict__ C, long rsC, long csC, long bsC) {
+    constexpr int G_LDB = GT + 4;   // Bs[k][n]
+    constexpr int WT = GT / 2;      // warp tile edge
+    constexpr int NF = WT / 8;      // m8n8 fragments per warp tile edge
     __shared__ double As[GT][G_LDA];
     __shared__ double Bs[GK][G_LDB];
     const int b = blockIdx.z;
@@ -34,14 +39,14 @@ k_gemm(int M, int N, int K, double alpha,
     C += (long)b * bsC;
     if (dvec) dvec += (long)b * bsd;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
+    const int wm = (warp >> 1) * WT, wn = (warp & 1) * WT;
     const int g = lane >> 2, q = lane & 3;
     const int i0 = blockIdx.y * GT, j0 = blockIdx.x * GT;
-    double acc[4][4][2];
+    double acc[NF][NF][2];
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
+    for (int a = 0; a < NF; ++a)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) acc[a][c][0] = acc[a][c][1] = 0.0;
+        for (int c = 0; c < NF; ++c) acc[a][c][0] = acc[a][c][1] = 0.0;
 
     for (int k0 = 0; k0 < K; k0 += GK) {
         // stage A tile (GT x GK) and B tile (GK x GT); consecutive threads follow the unit stride
@@ -65,15 +70,15 @@ k_gemm(int M, int N, int K, double alpha,
         __syncthreads();
 #pragma unroll
         for (int ks = 0; ks < GK / 4; ++ks) {
-            double af[4], bf[4];
+            double af[NF], bf[NF];
 #pragma unroll
-            for (int a = 0; a < 4; ++a) af[a] = As[wm + 8 * a + g][4 * ks + q];
+            for (int a = 0; a < NF; ++a) af[a] = As[wm + 8 * a + g][4 * ks + q];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) bf[c] = Bs[4 * ks + q][wn + 8 * c + g];
+            for (int c = 0; c < NF; ++c) bf[c] = Bs[4 * ks + q][wn + 8 * c + g];
 #pragma unroll
-            for (int a = 0; a < 4; ++a)
+            for (int a = 0; a < NF; ++a)
 #pragma unroll
-                for (int c = 0; c < 4; ++c)
+                for (int c = 0; c < NF; ++c)
                     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                         : "+d"(acc[a][c][0]), "+d"(acc[a][c][1])
                         : "d"(af[a]), "d"(bf[c]));
@@ -81,11 +86,11 @@ k_gemm(int M, int N, int K, double alpha,
         __syncthreads();
     }
 #pragma unroll
-    for (int a = 0; a < 4; ++a) {
+    for (int a = 0; a < NF; ++a) {
         const int i = i0 + wm + 8 * a + g;
         if (i >= M) continue;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < NF; ++c) {
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int j = j0 + wn + 8 * c + 2 * q + h;
@@ -110,9 +115,16 @@ inline int gemm(cudaStream_t st, int batch, int M, int N, int K, double alpha, M
                 double beta, double *C, long rsC, long csC, long bsC,
                 const double *dvec = nullptr, long bsd = 0) {
     if (M <= 0 || N <= 0 || batch <= 0) return DDMPC_OK;
-    dim3 grid(ceil_div(N, GT), ceil_div(M, GT), batch);
-    k_gemm<<<grid, 128, 0, st>>>(M, N, K, alpha, A.p, A.rs, A.cs, A.bs, B.p, B.rs, B.cs, B.bs,
-                                 dvec, bsd, beta, C, rsC, csC, bsC);
+    const long tiles64 = (long)ceil_div(N, 64) * ceil_div(M, 64) * batch;
+    if (tiles64 >= 148) {
+        dim3 grid(ceil_div(N, 64), ceil_div(M, 64), batch);
+        k_gemm<64><<<grid, 128, 0, st>>>(M, N, K, alpha, A.p, A.rs, A.cs, A.bs, B.p, B.rs, B.cs, B.bs, dvec, bsd, beta,
+                                         C, rsC, csC, bsC);
+    } else {   // not enough 64x64 tiles for one wave: quarter-size tiles
+        dim3 grid(ceil_div(N, 32), ceil_div(M, 32), batch);
+        k_gemm<32><<<grid, 128, 0, st>>>(M, N, K, alpha, A.p, A.rs, A.cs, A.bs, B.p, B.rs, B.cs, B.bs, dvec, bsd, beta,
+                                         C, rsC, csC, bsC);
+    }
     DDMPC_LAUNCH_CHECK();
     return DDMPC_OK;
 }
@@ -219,6 +231,78 @@ inline int potrs(cudaStream_t st, int batch, int n, int nrhs, const double *L, l
 }
 
 // ---------------------------------------------------------------------------
+// Numerical rank of a symmetric PSD matrix by elimination with diagonal pivoting (the pivots
+// of a rank-revealing Cholesky / LDL^T).  One CTA per batch entry; A (n x n, ld) is destroyed.
+// rank[b] = number of pivots > rel * (first pivot).  Rows/columns are never swapped: an `alive`
+// flag marks what is left, and each step is one rank-1 update of the alive block.
+// ---------------------------------------------------------------------------
+static __global__ void __launch_bounds__(1024)
+k_pivot_rank(int n, double *__restrict__ A, long ld, long bs, double rel, int *__restrict__ rank) {
+    extern __shared__ double sh[];          // colp[n], alive[n] (as double), red[64]
+    A += (long)blockIdx.x * bs;
+    const int tid = threadIdx.x, T = blockDim.x;
+    double *colp = sh, *alive = sh + n, *red = sh + 2 * n;
+    int *redi = reinterpret_cast<int *>(red + 32);
+    __shared__ double s_piv, s_first;
+    __shared__ int s_idx, s_stop;
+    for (int i = tid; i < n; i += T) alive[i] = 1.0;
+    if (tid == 0) { s_stop = 0; s_first = 0.0; }
+    __syncthreads();
+    int r = 0;
+    for (; r < n; ++r) {
+        // pivot = largest alive diagonal entry
+        double best = -1.0;
+        int bi = -1;
+        for (int i = tid; i < n; i += T)
+            if (alive[i] != 0.0) {
+                const double d = A[(long)i * ld + i];
+                if (d > best) { best = d; bi = i; }
+            }
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ob > best || (ob == best && oi >= 0 && (bi < 0 || oi < bi))) { best = ob; bi = oi; }
+        }
+        if ((tid & 31) == 0) { red[tid >> 5] = best; redi[tid >> 5] = bi; }
+        __syncthreads();
+        if (tid == 0) {
+            double b = -1.0;
+            int ix = -1;
+            for (int w = 0; w < (T + 31) / 32; ++w)
+                if (red[w] > b || (red[w] == b && redi[w] >= 0 && (ix < 0 || redi[w] < ix))) { b = red[w]; ix = redi[w]; }
+            if (r == 0) s_first = b;
+            s_piv = b;
+            s_idx = ix;
+            s_stop = (ix < 0 || !(b > rel * s_first) || !(b > 0.0)) ? 1 : 0;
+        }
+        __syncthreads();
+        if (s_stop) break;
+        const int pv = s_idx;
+        const double inv = 1.0 / s_piv;
+        for (int i = tid; i < n; i += T) colp[i] = (alive[i] != 0.0 && i != pv) ? A[(long)i * ld + pv] : 0.0;
+        __syncthreads();
+        if (tid == 0) alive[pv] = 0.0;
+        // rank-1 update of the alive block: A[i][j] -= A[i][pv] A[pv][j] / A[pv][pv]
+        for (long e = tid; e < (long)n * n; e += T) {
+            const int i = (int)(e / n), j = (int)(e % n);
+            const double ci = colp[i], cj = colp[j];
+            if (ci != 0.0 && cj != 0.0) A[(long)i * ld + j] = fma(-ci * inv, cj, A[(long)i * ld + j]);
+        }
+        __syncthreads();
+    }
+    if (tid == 0) rank[blockIdx.x] = r;
+}
+
+inline int pivot_rank(cudaStream_t st, int batch, int n, double *A, long ld, long bs, double rel, int *rank) {
+    if (n <= 0 || batch <= 0) return DDMPC_OK;
+    const size_t sh = (size_t)(2 * n + 64) * sizeof(double);
+    const int threads = n >= 128 ? 1024 : (n >= 48 ? 512 : 256);
+    k_pivot_rank<<<batch, threads, sh, st>>>(n, A, ld, bs, rel, rank);
+    DDMPC_LAUNCH_CHECK();
+    return DDMPC_OK;
+}
+
+// ---------------------------------------------------------------------------
 // Symmetric eigen-decomposition by parallel-ordered cyclic Jacobi.  One CTA per
 // batch entry; A (n x n, ld) is destroyed (its diagonal ends as the spectrum),
 // V (n x n, ldv; may be NULL) receives the eigenvectors as columns, lam (n) the
@@ -288,7 +372,9 @@ k_jacobi(int n, double *__restrict__ A, long ld, long bsA, double *__restrict__ 
             __syncthreads();
             // column rotations  A <- A J,  V <- V J
             for (long e = tid; e < (long)np2 * n; e += T) {
-                const int k = (int)(e / n), i = (int)(e % n);
+                // a warp works on ONE row and 32 different pairs: its loads stay inside a few cache lines
+                // (one row per lane would touch 32 different lines per load)
+                const int i = (int)(e / np2), k = (int)(e % np2);
                 int p, q;
                 jacobi_pair(n2, r, k, p, q);
                 if (q >= n) continue;

@@ -329,19 +329,18 @@ static int validate(const ddmpc_params &q) {
 int pe_rank_device(cudaStream_t st, int batch, const double *X, long bsX, int N, int nch, int order,
                    int *rank_dev /* device, batch ints */) {
     const int rows = order * nch, cols = N - order + 1;
-    DevBuf Hpe, G, lam;
+    DevBuf Hpe, G;
     DDMPC_CUDA(Hpe.alloc(sizeof(double) * (size_t)batch * rows * cols));
     DDMPC_CUDA(G.alloc(sizeof(double) * (size_t)batch * rows * rows));
-    DDMPC_CUDA(lam.alloc(sizeof(double) * (size_t)batch * rows));
     DDMPC_TRY(launch_hankel(st, batch, X, bsX, N, nch, order, 0, nullptr, Hpe.d(), cols, (long)rows * cols));
     Mat Hm = mat(Hpe.d(), cols, 1, (long)rows * cols);
     DDMPC_TRY(gemm(st, batch, rows, rows, cols, 1.0, Hm, tr(Hm), 0.0, G.d(), rows, 1, (long)rows * rows));
     DDMPC_TRY(symmetrize(st, batch, rows, G.d(), rows, (long)rows * rows));
-    DDMPC_TRY(jacobi_eig(st, batch, rows, G.d(), rows, (long)rows * rows, nullptr, 0, 0, lam.d(), rows));
-    // lambda = sigma^2.  A Gram spectrum resolves sigma only down to ~sqrt(eps)*sigma_max,
-    // so the cut is 1e-12*lambda_max (sigma/sigma_max > 1e-6); see DESIGN.md "PE rank test".
-    k_spectrum<<<batch, 32, 0, st>>>(rows, lam.d(), rows, 1e-12, 0, nullptr, 0, rank_dev);
-    DDMPC_LAUNCH_CHECK();
+    // Rank = number of pivots of a diagonally pivoted elimination of the Gram matrix above
+    // 1e-12 x the largest.  The Gram matrix squares the singular values (lambda = sigma^2) and
+    // resolves sigma only down to ~sqrt(eps)*sigma_max, hence this cut (sigma/sigma_max > 1e-6)
+    // instead of matrix_rank's max(M,N)*eps; see DESIGN.md "PE rank test".
+    DDMPC_TRY(pivot_rank(st, batch, rows, G.d(), rows, (long)rows * rows, 1e-12, rank_dev));
     DDMPC_CUDA(cudaStreamSynchronize(st));
     return DDMPC_OK;
 }
