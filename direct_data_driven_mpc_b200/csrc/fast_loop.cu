@@ -39,7 +39,104 @@ struct FastArgs {
     int *status, *iters;
     uint32_t rk[20];     // Philox round keys (key + r * Weyl), filled on the host
     int zmask;           // always 0: defeats loop-invariant hoisting of coefficient loads
+    // CONVEX slack bound (device operators of controller 0, see plan.cuh)
+    const double *Ks, *Phi, *Psi;   // (nb, nth), (nb, nb), (L*m, nb)
+    double bound, tol;
+    int nb, nth, max_iter;
 };
+
+// Warp-cooperative ADMM on the box rows of ONE loop, called only for the rare solves
+// whose unconstrained slack violates the bound.  Lane i owns rows i and i + 32 (nb <= 64).
+//   th(e)  : theta entry e of the loop (window then set-points)        up(k) : planned input k (corrected in place)
+//   scr    : 2 x 64 doubles of shared scratch (d, t)
+// Returns the number of iterations; *inaccurate is set when max_iter was reached.
+template <typename ThetaF, typename UpF>
+__device__ __noinline__ int admm_box_warp(const FastArgs &a, int R, ThetaF th, UpF up, double *scr, bool *inaccurate) {
+    const int lane = threadIdx.x & 31, nb = a.nb, nth = a.nth;
+    double *dsh = scr, *tsh = scr + 64;
+    double sun[2], z[2], w[2];
+    double smax = 0.0;
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+        const int i = lane + 32 * rr;
+        double acc = 0.0;
+        if (i < nb)
+            for (int e = 0; e < nth; ++e) acc = fma(__ldg(a.Ks + (size_t)i * nth + e), th(e), acc);
+        sun[rr] = acc;
+        z[rr] = fmin(fmax(acc, -a.bound), a.bound);
+        w[rr] = 0.0;
+        smax = fmax(smax, fabs(acc));
+    }
+    for (int o = 16; o > 0; o >>= 1) smax = fmax(smax, __shfl_xor_sync(0xffffffffu, smax, o));
+    const double thr = a.tol * fmax(a.bound, smax);
+    int it = 0;
+    bool conv = false;
+    while (it < a.max_iter && !conv) {
+        ++it;
+        __syncwarp();
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+            const int i = lane + 32 * rr;
+            if (i < nb) dsh[i] = sun[rr] - z[rr] + w[rr];
+        }
+        __syncwarp();
+        double res = 0.0;
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+            const int i = lane + 32 * rr;
+            if (i < nb) {
+                // Phi is symmetric: read column i (= row i) with the lanes along the unit stride
+                double acc0 = 0.0, acc1 = 0.0;
+                const double *col = a.Phi + i;
+                int j = 0;
+                for (; j + 7 < nb; j += 8) {       // 8 independent loads in flight (the loop is latency-bound)
+                    double pv[8];
+#pragma unroll
+                    for (int u8 = 0; u8 < 8; ++u8) pv[u8] = __ldg(col + (size_t)(j + u8) * nb);
+#pragma unroll
+                    for (int u8 = 0; u8 < 8; u8 += 2) {
+                        acc0 = fma(pv[u8], dsh[j + u8], acc0);
+                        acc1 = fma(pv[u8 + 1], dsh[j + u8 + 1], acc1);
+                    }
+                }
+                for (; j < nb; ++j) acc0 = fma(__ldg(col + (size_t)j * nb), dsh[j], acc0);
+                const double si = (z[rr] - w[rr]) + (acc0 + acc1);
+                const double zn = fmin(fmax(si + w[rr], -a.bound), a.bound);
+                res = fmax(res, fmax(fabs(si - zn), fabs(zn - z[rr])));
+                w[rr] = w[rr] + si - zn;
+                z[rr] = zn;
+            }
+        }
+        for (int o = 16; o > 0; o >>= 1) res = fmax(res, __shfl_xor_sync(0xffffffffu, res, o));
+        conv = res <= thr;
+    }
+    *inaccurate = !conv;
+    __syncwarp();
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+        const int i = lane + 32 * rr;
+        if (i < nb) dsh[i] = sun[rr] - z[rr] + w[rr];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+        const int i = lane + 32 * rr;
+        if (i < nb) {
+            double acc = 0.0;
+            for (int j = 0; j < nb; ++j) acc = fma(__ldg(a.Phi + (size_t)j * nb + i), dsh[j], acc);
+            tsh[i] = acc;                      // t = Phi d
+        }
+    }
+    __syncwarp();
+    if (lane < R) {                            // u = u0 - Psi t on the applied rows
+        double acc = 0.0;
+        const double *row = a.Psi + (size_t)lane * nb;
+        for (int j = 0; j < nb; ++j) acc = fma(__ldg(row + j), tsh[j], acc);
+        up(lane, acc);
+    }
+    __syncwarp();
+    return it;
+}
 
 __device__ __forceinline__ void philox_round(uint32_t &c0, uint32_t &c1, uint32_t &c2, uint32_t &c3, uint32_t k0,
                                              uint32_t k1) {
@@ -81,7 +178,7 @@ __device__ __forceinline__ void emit(double *__restrict__ base, size_t f, bool o
 // LPT = closed loops per thread.  Every coefficient fetched from the constant bank feeds LPT
 // DFMAs (one per loop), so LPT = 2 halves the pressure on the indexed-constant (ADU/IDC) path and
 // doubles the independent work between dependent instructions, at the price of half the warps.
-template <int N, int M, int P, int NX, int NMPC, int LPT, bool PHILOX, bool PAIR>
+template <int N, int M, int P, int NX, int NMPC, int LPT, bool PHILOX, bool PAIR, bool CVX = false>
 __global__ void __launch_bounds__(LPT == 1 ? 64 : 32, 8)
 k_closed_loop_fast(const __grid_constant__ FastCoef<N, M, P, NX, NMPC> cfp, const FastArgs a) {
     // Coefficients stay in the kernel-parameter constant bank and are fetched with indexed LDC
@@ -104,6 +201,11 @@ k_closed_loop_fast(const __grid_constant__ FastCoef<N, M, P, NX, NMPC> cfp, cons
     __shared__ __align__(16) double up_s[R][LPT][TP];      // planned inputs of the current n-step block
     __shared__ __align__(16) double wu_s[N * M][LPT][TP];  // measurement window, ring over N time slots
     __shared__ __align__(16) double wy_s[N * P][LPT][TP];
+    static_assert(!CVX || USE_MMA, "the fused CONVEX path needs the tensor-core solve (LPT = 2, 8 planned-input rows)");
+    __shared__ double sp_s[CVX ? M + P : 1][LPT][TP];      // set-points (theta tail) for the slack rows
+    __shared__ int extra_s[CVX ? LPT : 1][TP];             // extra ADMM iterations per loop
+    __shared__ int stat_s[CVX ? LPT : 1][TP];              // worst ADMM status per loop
+    __shared__ double adm_s[CVX ? 128 : 1];                // scratch of the warp-cooperative ADMM
     // thread -> loop map (64 loops per block): LPT = 1: the first warp takes the even loops and the
     // second warp the odd ones; LPT = 2: thread t carries loops 2t (l = 0) and 2t + 1 (l = 1).
     // Either way the sector parity of a step is uniform across a warp for a given l.
@@ -143,6 +245,12 @@ k_closed_loop_fast(const __grid_constant__ FastCoef<N, M, P, NX, NMPC> cfp, cons
 #pragma unroll
             for (int j = 0; j < M + P; ++j) acc = fma(__ldg(a.Ksp + k * (M + P) + j), sp[j], acc);
             csp_s[k][l][tl] = acc;
+        }
+        if constexpr (CVX) {
+#pragma unroll
+            for (int j = 0; j < M + P; ++j) sp_s[j][l][tl] = sp[j];
+            extra_s[l][tl] = 0;
+            stat_s[l][tl] = DDMPC_SOLVE_OPTIMAL;
         }
     }
     uint32_t nw[LPT][4];                         // words of the current Philox call
@@ -200,6 +308,101 @@ k_closed_loop_fast(const __grid_constant__ FastCoef<N, M, P, NX, NMPC> cfp, cons
 #pragma unroll
                 for (int t8 = 0; t8 < NT; ++t8) *reinterpret_cast<double2 *>(&up_s[g][l][8 * t8 + 2 * q]) = c[l][t8];
             __syncwarp();                        // planned inputs visible to their owner lanes
+            if constexpr (CVX) {
+                // ---- CONVEX slack bound: s_unc (nb x loops) = Ks (nb x n_theta) [window; set-points], again as
+                // m8n8k4 MMAs, two row tiles at a time; only max |s_unc| per loop is kept.
+                constexpr int NKS = (N * (M + P) + M + P) / 4;
+                static_assert((M + P) % 4 == 0, "set-point block must fill whole k-steps");
+                const int nrt = (a.nb + 7) / 8;
+                double2 smax[LPT][NT];
+#pragma unroll
+                for (int l = 0; l < LPT; ++l)
+#pragma unroll
+                    for (int t8 = 0; t8 < NT; ++t8) smax[l][t8] = make_double2(0.0, 0.0);
+                for (int rt = 0; rt < nrt; rt += 2) {
+                    double2 cc[2][LPT][NT];
+#pragma unroll
+                    for (int r2 = 0; r2 < 2; ++r2)
+#pragma unroll
+                        for (int l = 0; l < LPT; ++l)
+#pragma unroll
+                            for (int t8 = 0; t8 < NT; ++t8) cc[r2][l][t8] = make_double2(0.0, 0.0);
+#pragma unroll
+                    for (int ks = 0; ks < NKS; ++ks) {
+                        const int e = 4 * ks + q;
+                        double bv[LPT][NT];
+#pragma unroll
+                        for (int l = 0; l < LPT; ++l)
+#pragma unroll
+                            for (int t8 = 0; t8 < NT; ++t8)
+                                bv[l][t8] = (4 * ks < N * M)        ? wu_s[e < N * M ? e : 0][l][8 * t8 + g]
+                                            : (4 * ks < N * (M + P)) ? wy_s[(e >= N * M && e < N * (M + P)) ? e - N * M : 0][l][8 * t8 + g]
+                                                                     : sp_s[e >= N * (M + P) ? e - N * (M + P) : 0][l][8 * t8 + g];
+#pragma unroll
+                        for (int r2 = 0; r2 < 2; ++r2) {
+                            const int row = 8 * (rt + r2) + g;
+                            const double av = row < a.nb ? __ldg(a.Ks + (size_t)row * a.nth + e) : 0.0;
+#pragma unroll
+                            for (int l = 0; l < LPT; ++l)
+#pragma unroll
+                                for (int t8 = 0; t8 < NT; ++t8)
+                                    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                                        : "+d"(cc[r2][l][t8].x), "+d"(cc[r2][l][t8].y)
+                                        : "d"(av), "d"(bv[l][t8]));
+                        }
+                    }
+#pragma unroll
+                    for (int r2 = 0; r2 < 2; ++r2)
+#pragma unroll
+                        for (int l = 0; l < LPT; ++l)
+#pragma unroll
+                            for (int t8 = 0; t8 < NT; ++t8) {
+                                smax[l][t8].x = fmax(smax[l][t8].x, fabs(cc[r2][l][t8].x));
+                                smax[l][t8].y = fmax(smax[l][t8].y, fabs(cc[r2][l][t8].y));
+                            }
+                }
+                // max over the 8 rows of a tile (lanes with equal q); bit (l, t8, hh) of vmask = "loop
+                // slot 8*t8 + 2q + hh of group l violates the bound" (static indices only: smax stays in registers)
+                unsigned vmask = 0u;
+#pragma unroll
+                for (int l = 0; l < LPT; ++l)
+#pragma unroll
+                    for (int t8 = 0; t8 < NT; ++t8) {
+#pragma unroll
+                        for (int o = 4; o < 32; o <<= 1) {
+                            smax[l][t8].x = fmax(smax[l][t8].x, __shfl_xor_sync(0xffffffffu, smax[l][t8].x, o));
+                            smax[l][t8].y = fmax(smax[l][t8].y, __shfl_xor_sync(0xffffffffu, smax[l][t8].y, o));
+                        }
+                        if (smax[l][t8].x > a.bound) vmask |= 1u << (2 * (l * NT + t8));
+                        if (smax[l][t8].y > a.bound) vmask |= 1u << (2 * (l * NT + t8) + 1);
+                    }
+                if (g != 0) vmask = 0u;          // lanes 0..3 (g = 0, q = lane) speak for their loops
+                if (__any_sync(0xffffffffu, vmask != 0u)) {
+                    // rare: run the ADMM for each violating loop, the whole warp on one loop at a time
+#pragma unroll 1
+                    for (int src = 0; src < 4; ++src) {
+                        unsigned mbits = __shfl_sync(0xffffffffu, vmask, src);
+                        while (mbits) {
+                            const int bit = __ffs(mbits) - 1;
+                            mbits &= mbits - 1;
+                            const int l = bit / (2 * NT), t8 = (bit >> 1) % NT, hh = bit & 1;
+                            const int slot = 8 * t8 + 2 * src + hh;    // loop slot (l, slot)
+                            auto th = [&](int e) -> double {
+                                return e < N * M ? wu_s[e][l][slot]
+                                                 : (e < N * (M + P) ? wy_s[e - N * M][l][slot] : sp_s[e - N * (M + P)][l][slot]);
+                            };
+                            auto upf = [&](int k, double corr) { up_s[k][l][slot] -= corr; };
+                            bool inacc = false;
+                            const int it = admm_box_warp(a, R, th, upf, adm_s, &inacc);
+                            if (tl == 0) {
+                                extra_s[l][slot] += it - 1;
+                                if (inacc) stat_s[l][slot] = DDMPC_SOLVE_OPTIMAL_INACCURATE;
+                            }
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
             return;
         }
         constexpr int SPLIT = (R * LPT >= 8) ? 1 : (R * LPT >= 4 ? 2 : 4);   // partial sums when rows are few
@@ -390,8 +593,13 @@ k_closed_loop_fast(const __grid_constant__ FastCoef<N, M, P, NX, NMPC> cfp, cons
         for (int i = 0; i < NX; ++i) finite = finite && isfinite(x[l][i]);
 #pragma unroll
         for (int i = 0; i < N * P; ++i) finite = finite && isfinite(wy_s[i][l][tl]);
-        if (a.status) a.status[b[l]] = finite ? DDMPC_SOLVE_OPTIMAL : DDMPC_SOLVE_NONFINITE;
-        if (a.iters) a.iters[b[l]] = (a.n_steps + NMPC - 1) / NMPC;
+        int st_out = finite ? DDMPC_SOLVE_OPTIMAL : DDMPC_SOLVE_NONFINITE, it_out = (a.n_steps + NMPC - 1) / NMPC;
+        if constexpr (CVX) {
+            st_out = max(st_out, stat_s[l][tl]);
+            it_out += extra_s[l][tl];
+        }
+        if (a.status) a.status[b[l]] = st_out;
+        if (a.iters) a.iters[b[l]] = it_out;
         if (a.x_final) {
 #pragma unroll
             for (int i = 0; i < NX; ++i) a.x_final[(size_t)b[l] * NX + i] = x[l][i];
@@ -708,6 +916,28 @@ static int launch_fast(const ddmpc_set *set, const ddmpc_plant *plant, const Fas
     // loops per thread: 2 once the batch is large enough to keep every SM busy with half the warps
     int lpt = a.B >= 16384 ? 2 : 1;
     if (const char *e = getenv("DDMPC_LPT")) lpt = (e[0] == '2') ? 2 : 1;
+    if (d.convex) {
+        // fused CONVEX path: slack rows through the tensor-core solve (needs LPT = 2 and 8 planned-input rows)
+        constexpr bool CVX_OK = (NMPC * M == 8) && (NMPC % N == 0) && ((N * M) % 4 == 0) && ((N * P) % 4 == 0) &&
+                                ((M + P) % 4 == 0);
+        if constexpr (CVX_OK) {
+            if (d.nb > 64) return -1;
+            a.Ks = set->plan.Ks.d(); a.Phi = set->plan.Phi.d(); a.Psi = set->plan.Psi.d();
+            a.bound = set->plan.bound; a.nb = d.nb; a.nth = d.nth;
+            const dim3 grid(ceil_div(a.B, 64));
+            if (a.w) {
+                if (pair) k_closed_loop_fast<N, M, P, NX, NMPC, 2, false, true, true><<<grid, 32, 0, st>>>(cf, a);
+                else k_closed_loop_fast<N, M, P, NX, NMPC, 2, false, false, true><<<grid, 32, 0, st>>>(cf, a);
+            } else {
+                if (pair) k_closed_loop_fast<N, M, P, NX, NMPC, 2, true, true, true><<<grid, 32, 0, st>>>(cf, a);
+                else k_closed_loop_fast<N, M, P, NX, NMPC, 2, true, false, true><<<grid, 32, 0, st>>>(cf, a);
+            }
+            DDMPC_LAUNCH_CHECK();
+            return DDMPC_OK;
+        } else {
+            return -1;
+        }
+    }
     const int tpb = lpt == 1 ? 64 : 32;
     const dim3 grid(ceil_div(a.B, 64));
 #define DDMPC_LAUNCH_FAST(LPT_)                                                                              \
@@ -785,12 +1015,15 @@ static int launch_pair(const ddmpc_set *set, const ddmpc_plant *plant, const Fas
 int closed_loop_fast_try(const ddmpc_set *set, const ddmpc_plant *plant, int B, const int *ctrl_idx, const double *x0,
                          const double *u_past0, const double *y_past0, const double *u_s, const double *y_s,
                          const double *w, uint64_t seed, uint64_t id0, double eps, int n_steps, double *u_sys,
-                         double *y_sys, int *status, int *iters, double *x_final, cudaStream_t st) {
+                         double *y_sys, int *status, int *iters, double *x_final, double tol, int max_iter,
+                         cudaStream_t st) {
     const Dims &d = set->plan.d;
-    if (ctrl_idx || set->plan.count != 1 || d.convex || !d.robust) return -1;
+    if (ctrl_idx || set->plan.count != 1 || !d.robust) return -1;
     const char *force = getenv("DDMPC_FORCE_GENERIC");
     if (force && force[0] == '1') return -1;
     FastArgs fa{};
+    fa.tol = tol > 0.0 ? tol : 1e-8;
+    fa.max_iter = max_iter > 0 ? max_iter : 1000;
     fa.B = B; fa.n_steps = n_steps;
     fa.x0 = x0; fa.u_past0 = u_past0; fa.y_past0 = y_past0; fa.u_s = u_s; fa.y_s = y_s; fa.w = w;
     fa.seed = seed; fa.id0 = id0; fa.eps = eps;
@@ -803,7 +1036,7 @@ int closed_loop_fast_try(const ddmpc_set *set, const ddmpc_plant *plant, int B, 
     // the warps per SM but also doubles the shared-memory instructions per loop and ends up
     // MIO-throttled (0.49 ms vs 0.34 ms on config 3).  Opt in with DDMPC_TWO_LANES=1.
     const char *two = getenv("DDMPC_TWO_LANES");
-    if (two && two[0] == '1') {
+    if (two && two[0] == '1' && !d.convex) {
 #define DDMPC_PAIR_CASE(N_, M_, P_, NX_, NMPC_)                                                    \
     if (d.n == N_ && d.m == M_ && d.p == P_ && plant->n_x == NX_ && nmpc == NMPC_)                 \
         return launch_pair<N_, M_, P_, NX_, NMPC_>(set, plant, fa, st);

@@ -398,7 +398,8 @@ __global__ void k_closed_loop(KArgs a, LoopArgs la, int B, const int *__restrict
 int closed_loop_fast_try(const ddmpc_set *set, const ddmpc_plant *plant, int B, const int *ctrl_idx, const double *x0,
                          const double *u_past0, const double *y_past0, const double *u_s, const double *y_s,
                          const double *w, uint64_t seed, uint64_t id0, double eps, int n_steps, double *u_sys,
-                         double *y_sys, int *status, int *iters, double *x_final, cudaStream_t st);
+                         double *y_sys, int *status, int *iters, double *x_final, double tol, int max_iter,
+                         cudaStream_t st);
 
 int closed_loop_gemm_try(const ddmpc_set *set, const ddmpc_plant *plant, int B, const int *ctrl_idx, const double *x0,
                          const double *u_past0, const double *y_past0, const double *u_s, const double *y_s,
@@ -564,7 +565,8 @@ int ddmpc_closed_loop_batch(const ddmpc_set *set, const ddmpc_plant *plant, int 
     const int nxp = plant->n_x;
     {   // register-resident specialisation (shared equality-only controller, small system)
         const int rc = closed_loop_fast_try(set, plant, B, ctrl_idx, x0, u_past0, y_past0, u_s, y_s, w, noise_seed,
-                                            scenario_id0, noise_eps, n_steps, u_sys, y_sys, status, iters, x_final, st);
+                                            scenario_id0, noise_eps, n_steps, u_sys, y_sys, status, iters, x_final, tol,
+                                            max_iter, st);
         if (rc != -1) return rc;
     }
     {   // large systems: the batch as the N dimension of FP64 tensor-core GEMMs

@@ -280,3 +280,47 @@ def test_config4_gemm_path_vs_generic_and_oracle(n_mpc, n_steps, monkeypatch):
         qp.set_past_input_output_data(sc["u_past0"][b].reshape(-1, 1), sc["y_past0"][b].reshape(-1, 1))
         u_ref, y_ref = O.closed_loop(plant_o, qp, n_steps, w[b])
         assert _rel(u1[b], u_ref) < 1e-5 and _rel(y1[b], y_ref) < 1e-5
+
+
+@pytest.mark.parametrize("c", [1.0, 0.3])
+def test_convex_fused_path_vs_generic_and_oracle(c, monkeypatch):
+    """CONVEX slack bound inside the fused kernel (slack rows on the tensor cores, warp-cooperative ADMM for
+    the violating loops) vs the generic thread-per-loop kernel (70 loops: several blocks, dead lanes) and vs
+    the oracle's active-set solution on a sample."""
+    plant_o, prm, rng, x0, u_d, y_d = O.example_scenario(0)
+    B, n_steps = 70, 37
+    cs, _ = _set(u_d, y_d, 1, True, 4, c=c)
+    r = np.random.default_rng(3)
+    xs = np.tile(plant_o.x, (B, 1)) + 0.05 * r.normal(size=(B, 4))
+    us = np.tile(prm["u_s"].T, (B, 1)) * r.uniform(0.7, 1.3, (B, 1))
+    ys = us @ _plant().equilibrium_gain().T
+    up0, yp0 = np.tile(u_d[-4:].reshape(1, -1), (B, 1)), np.tile(y_d[-4:].reshape(1, -1), (B, 1))
+    w = 0.002 * r.uniform(-1, 1, (B, n_steps, 2))
+    monkeypatch.delenv("DDMPC_FORCE_GENERIC", raising=False)
+    u1, y1, s1, i1 = cs.closed_loop(_plant(), xs, up0, yp0, us, ys, n_steps, w=w)
+    monkeypatch.setenv("DDMPC_FORCE_GENERIC", "1")
+    u2, y2, s2, i2 = cs.closed_loop(_plant(), xs, up0, yp0, us, ys, n_steps, w=w)
+    monkeypatch.delenv("DDMPC_FORCE_GENERIC", raising=False)
+    assert int(s1.max()) == 0 and int(s2.max()) == 0
+    assert int(i1.max()) > 10                                  # the box really binds somewhere
+    assert (i1 == i2).all(), (i1 - i2).abs().max()
+    assert _rel(u1.cpu().numpy(), u2.cpu().numpy()) < 1e-8 and _rel(y1.cpu().numpy(), y2.cpu().numpy()) < 1e-8
+    u1, y1 = u1.cpu().numpy(), y1.cpu().numpy()
+    for b in (0, 33, 69):
+        po = O.four_tank_plant()
+        po.x = xs[b].copy()
+        ctrl = O.make_controller(prm, u_d, y_d, n_mpc_step=4, slack_type=O.SLACK_CONVEX, c=c)
+        ctrl.u_s, ctrl.y_s = us[b].reshape(-1, 1), ys[b].reshape(-1, 1)
+        u_ref, y_ref = O.closed_loop(po, ctrl, n_steps, w[b])
+        assert _rel(u1[b], u_ref) < 1e-5 and _rel(y1[b], y_ref) < 1e-5, b
+    # Philox noise through the fused path, large batch: equals the generic kernel on a slice
+    Bb = 16384 + 40
+    sc_x = np.tile(plant_o.x, (Bb, 1))
+    args = (np.tile(u_d[-4:].reshape(1, -1), (Bb, 1)), np.tile(y_d[-4:].reshape(1, -1), (Bb, 1)),
+            np.tile(prm["u_s"].T, (Bb, 1)), np.tile(prm["y_s"].T, (Bb, 1)))
+    u3, y3, s3, i3 = cs.closed_loop(_plant(), sc_x, *args, 21, noise_seed=9, scenario_id0=5, noise_eps=0.002)
+    monkeypatch.setenv("DDMPC_FORCE_GENERIC", "1")
+    u4, y4, s4, i4 = cs.closed_loop(_plant(), sc_x[:64], *(a[:64] for a in args), 21, noise_seed=9, scenario_id0=5,
+                                    noise_eps=0.002)
+    monkeypatch.delenv("DDMPC_FORCE_GENERIC", raising=False)
+    assert _rel(u3[:64].cpu().numpy(), u4.cpu().numpy()) < 1e-8 and (i3[:64] == i4).all()
