@@ -67,6 +67,8 @@ def _load() -> C.CDLL:
         "ddmpc_solve_full_batch": (i32, [vp, i32, vp, vp, vp, vp, vp, f64, i32, vp, vp, vp, vp, vp]),
         "ddmpc_closed_loop_batch": (i32, [vp, C.POINTER(Plant), i32, vp, vp, vp, vp, vp, vp, vp, u64, u64, f64,
                                           i32, f64, i32, vp, vp, vp, vp, vp, vp]),
+        "ddmpc_generate_example_data": (i32, [C.POINTER(Plant), vp, vp, i32, vp, i32, f64, f64, f64, vp, vp, vp, vp, vp, vp]),
+        "ddmpc_pcg64_uniform": (i32, [vp, i32, i32, f64, f64, f64, vp, vp]),
         "ddmpc_closed_loop_batch_host": (i32, [vp, C.POINTER(Plant), i32, vp, vp, vp, vp, vp, vp, vp, u64, u64, f64,
                                                i32, f64, i32, vp, vp, vp, vp, vp]),
     }
@@ -81,7 +83,7 @@ EXPORTED = ["ddmpc_version", "ddmpc_strerror", "ddmpc_last_error", "ddmpc_kernel
             "ddmpc_hankel_host", "ddmpc_pe_rank_host", "ddmpc_set_create", "ddmpc_set_create_host",
             "ddmpc_set_destroy", "ddmpc_set_count", "ddmpc_set_info", "ddmpc_set_get", "ddmpc_solve_batch",
             "ddmpc_solve_batch_host", "ddmpc_solve_full_batch", "ddmpc_closed_loop_batch",
-            "ddmpc_closed_loop_batch_host"]
+            "ddmpc_closed_loop_batch_host", "ddmpc_generate_example_data", "ddmpc_pcg64_uniform"]
 
 
 def last_error() -> str:

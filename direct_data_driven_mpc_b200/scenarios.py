@@ -125,3 +125,47 @@ def config4_batch(B: int = 16384, seed: int = 0, N: int = 2000, L: int = 40, n_m
     return dict(plant=pl, params=prm, u_d=u_d, y_d=y_d, x0=np.tile(x_end, (B, 1)),
                 u_past0=np.tile(u_d[-n:].reshape(1, -1), (B, 1)), y_past0=np.tile(y_d[-n:].reshape(1, -1), (B, 1)),
                 u_s=np.tile(u_s, (B, 1)), y_s=np.tile(y_s, (B, 1)))
+
+
+class DeviceScenarios:
+    """S example-script scenarios generated on the GPU with the reference's NumPy streams
+    (``ddmpc_generate_example_data``): tensors ``x0 (S, n_x)``, ``u_d (S, N, m)``, ``y_d (S, N, p)``,
+    ``x_end (S, n_x)`` and the generator states, from which further draws continue in the
+    reference's order (``uniform``)."""
+
+    def __init__(self, seeds, plant: LTIPlant = None, N: int = 400, u_range=(-1.0, 1.0), device=None):
+        import ctypes as C
+        import torch
+        from . import _lib
+        self.plant = plant or four_tank_plant()
+        pl = self.plant
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.seeds = np.ascontiguousarray(np.asarray(seeds, dtype=np.uint64).reshape(-1))
+        S = self.S = self.seeds.size
+        self.N = N
+        Ot, Tt = _observer_matrices(pl)
+        pinv = np.ascontiguousarray(np.linalg.pinv(Ot))
+        Tt = np.ascontiguousarray(Tt)
+        f64 = dict(dtype=torch.float64, device=self.device)
+        self.x0 = torch.empty(S, pl.n_x, **f64)
+        self.u_d = torch.empty(S, N, pl.m, **f64)
+        self.y_d = torch.empty(S, N, pl.p, **f64)
+        self.x_end = torch.empty(S, pl.n_x, **f64)
+        self.rng_state = torch.empty(S, 4, dtype=torch.int64, device=self.device)   # raw uint64 words
+        ps = pl.c_struct()
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib.ddmpc_generate_example_data(
+                C.byref(ps), pinv.ctypes.data, Tt.ctypes.data, S, self.seeds.ctypes.data, N, float(u_range[0]),
+                float(u_range[1]), float(pl.eps_max), self.x0.data_ptr(), self.u_d.data_ptr(), self.y_d.data_ptr(),
+                self.x_end.data_ptr(), self.rng_state.data_ptr(), torch.cuda.current_stream().cuda_stream))
+
+    def uniform(self, count: int, lo: float = -1.0, hi: float = 1.0, scale: float = 1.0):
+        """Next ``count`` draws of every stream: (S, count) = scale * Generator.uniform(lo, hi, count)."""
+        import torch
+        from . import _lib
+        out = torch.empty(self.S, count, dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib.ddmpc_pcg64_uniform(self.rng_state.data_ptr(), self.S, count, float(lo), float(hi),
+                                                    float(scale), out.data_ptr(),
+                                                    torch.cuda.current_stream().cuda_stream))
+        return out

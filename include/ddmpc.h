@@ -92,8 +92,8 @@ int ddmpc_hankel(const double *X, int N, int n_ch, int L, double *H, void *strea
 int ddmpc_hankel_host(const double *X, int N, int n_ch, int L, double *H);
 
 /* ---- evaluate_persistent_excitation(X, order)  (hankel_matrix.py:55-87)
- * rank of H_order(X) from the eigenvalues of its Gram matrix; *rank is a HOST
- * int; synchronises. */
+ * numerical rank of H_order(X) (pivots of a rank-revealing elimination of its
+ * Gram matrix, see DESIGN.md "Numerics"); *rank is a HOST int; synchronises. */
 int ddmpc_pe_rank_host(const double *X, int N, int n_ch, int order, int *rank);
 
 /* ---- DirectDataDrivenMPCController.__init__ + initialize_data_driven_mpc
@@ -184,6 +184,24 @@ int ddmpc_closed_loop_batch_host(const ddmpc_set *set, const ddmpc_plant *plant,
                                  int n_steps, double tol, int max_iter,
                                  double *u_sys, double *y_sys, int32_t *status, int32_t *iters,
                                  double *x_final);
+
+/* ---- On-device scenario generation with NumPy-compatible streams (next-tier row):
+ * stages 1-3 of examples/direct_data_driven_mpc_example.py:263-300 for S seeds at once =
+ * randomize_initial_system_state (utilities/controller/controller_operation.py:59-75) then
+ * generate_initial_input_output_data (:126-133).  Stream s is np.random.default_rng(seeds[s])
+ * (SeedSequence -> PCG64 -> Generator.uniform, restated bit-for-bit), draws in the reference's
+ * order.  plant matrices, pinv_Ot (n_x, p*n_x), Tt (p*n_x, m*n_x) and seeds are HOST arrays;
+ * outputs are DEVICE arrays x0 (S, n_x), u_d (S, N, m), y_d (S, N, p), x_end (S, n_x) (plant
+ * state after the data run) and rng_state (S, 4) uint64 (generator state to continue from).
+ * Synchronises. */
+int ddmpc_generate_example_data(const ddmpc_plant *plant, const double *pinv_Ot, const double *Tt, int S,
+                                const uint64_t *seeds, int N, double u_lo, double u_hi, double eps,
+                                double *x0, double *u_d, double *y_d, double *x_end, uint64_t *rng_state,
+                                void *stream);
+/* Continue the S streams: out (S, count) = scale * Generator.uniform(lo, hi, count), e.g. the loop noise
+ * w_sys = eps_max * U(-1, 1, (n_steps, p)) of controller_operation.py:263.  Device arrays. */
+int ddmpc_pcg64_uniform(uint64_t *rng_state, int S, int count, double lo, double hi, double scale, double *out,
+                        void *stream);
 
 /* Number of kernels this library has launched since load (bench bookkeeping). */
 uint64_t ddmpc_kernel_launches(void);

@@ -324,3 +324,21 @@ def test_convex_fused_path_vs_generic_and_oracle(c, monkeypatch):
                                     noise_eps=0.002)
     monkeypatch.delenv("DDMPC_FORCE_GENERIC", raising=False)
     assert _rel(u3[:64].cpu().numpy(), u4.cpu().numpy()) < 1e-8 and (i3[:64] == i4).all()
+
+
+def test_batched_reproduction_matches_reference_semantics(golden_repro):
+    """reproduction.run_reproduction_batch (device data generation, shared generator order across the three
+    schemes) vs the fixture produced by the reference's own functions for seed 4, plus figure-level facts."""
+    from direct_data_driven_mpc_b200.reproduction import run_reproduction_batch
+    g = golden_repro
+    res = run_reproduction_batch([4, 0, 7, 11], t_sim=600)
+    assert np.array_equal(res["u_d"][0].cpu().numpy(), g["u_d"])
+    assert np.allclose(res["Y_n"][0], g["Y_n"], rtol=0, atol=1e-12) and np.allclose(res["x_start"][0], g["x_start"], atol=1e-12)
+    for name in ("TEC", "TEC_N_STEP"):
+        sc = res["schemes"][name]
+        assert _rel(sc["u_sys"][0].cpu().numpy(), g[f"u_{name}"]) < 1e-5 and _rel(sc["y_sys"][0].cpu().numpy(), g[f"y_{name}"]) < 1e-5
+        assert not bool(sc["diverged"].any()) and float(sc["final_error"].max()) < 0.03
+        assert abs(float(sc["u_peak"][0]) - 8.66) < 0.01
+    uc = res["schemes"]["UCON"]
+    assert _rel(uc["u_sys"][0, :150].cpu().numpy(), g["u_UCON"][:150]) < 1e-5
+    assert bool(uc["diverged"][0])                               # UCON diverges by design (reproduction.py:21-28)

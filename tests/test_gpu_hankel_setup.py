@@ -169,3 +169,41 @@ def test_constructor_errors_on_device_path():
         DirectDataDrivenMPCController(**{**kw, "L": 6, "Q": 3 * np.eye(12), "R": 1e-4 * np.eye(12)})
     with pytest.raises(ValueError, match="Q should be"):
         DirectDataDrivenMPCController(**{**kw, "Q": np.eye(3)})
+
+
+def test_on_device_scenario_generation_matches_numpy_streams(golden_example):
+    """ddmpc_generate_example_data: thread s replays np.random.default_rng(seed_s) through the example
+    script's stages 1-3.  Uniform draws are bit-exact; simulated outputs agree to rounding."""
+    from direct_data_driven_mpc_b200 import scenarios as S
+    seeds = [0, 1, 4, 12345, 2 ** 40 + 7, 2 ** 63 + 11]
+    ds = S.DeviceScenarios(seeds)
+    u_d, y_d, x0, x_end = (t.cpu().numpy() for t in (ds.u_d, ds.y_d, ds.x0, ds.x_end))
+    w = ds.uniform(401 * 2, -1.0, 1.0, 0.002).cpu().numpy().reshape(len(seeds), 401, 2)
+    for i, seed in enumerate(seeds):
+        rng, x0_h, ud_h, yd_h, xe_h = S.example_data(seed)
+        assert np.array_equal(u_d[i], ud_h), seed                       # PCG64 draws: bit-exact
+        assert np.allclose(y_d[i], yd_h, rtol=0, atol=1e-13)
+        assert np.allclose(x0[i], x0_h, rtol=0, atol=1e-12) and np.allclose(x_end[i], xe_h, rtol=0, atol=1e-12)
+        assert np.array_equal(w[i], 0.002 * rng.uniform(-1.0, 1.0, (401, 2)))   # draw 7 continues the stream
+    g = golden_example                                                   # ... and equals the live reference (seed 0)
+    assert np.array_equal(u_d[0], g["u_d"]) and np.allclose(y_d[0], g["y_d"], rtol=0, atol=1e-13)
+    assert np.array_equal(w[0], g["w_sys"])
+
+
+def test_per_seed_controllers_from_device_data():
+    """config-2 pipeline without host loops: generate S data sets on the device, build S controllers, run S loops."""
+    from direct_data_driven_mpc_b200 import ControllerSet, scenarios as S
+    n_seeds, n_steps = 48, 29
+    ds = S.DeviceScenarios(np.arange(n_seeds))
+    prm = S.four_tank_controller_params()
+    cs = ControllerSet(4, 2, 2, ds.u_d, ds.y_d, 30, prm["Q"], prm["R"], prm["eps_max"], prm["lamb_alpha"],
+                       prm["lamb_sigma"], 1.0, 0, 1, 4, True)
+    assert list(cs.statuses()) == [0] * n_seeds
+    w = ds.uniform(n_steps * 2, -1.0, 1.0, 0.002).reshape(n_seeds, n_steps, 2)
+    u, y, st, it = cs.closed_loop(ds.plant, ds.x_end, ds.u_d[:, -4:].reshape(n_seeds, -1), ds.y_d[:, -4:].reshape(n_seeds, -1),
+                                  np.tile(prm["u_s"].T, (n_seeds, 1)), np.tile(prm["y_s"].T, (n_seeds, 1)), n_steps,
+                                  w=w, ctrl_idx=np.arange(n_seeds))
+    u, y = u.cpu().numpy(), y.cpu().numpy()
+    for seed in (0, 17, 47):                                             # == `--seed <seed>` of the example script
+        u_ref, y_ref, _, _ = O.run_example(seed, n_steps - 1)
+        assert _relerr(u[seed], u_ref) < 1e-6 and _relerr(y[seed], y_ref) < 1e-6
