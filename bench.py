@@ -105,6 +105,40 @@ def cpu_baseline(budget_s: float):
     }
 
 
+def single_loop_latency(make_ctrl, plant_factory, w_sys, n_steps=401):
+    """BASELINE metric part (ii): p50 single-loop step latency - config 1 (seed 0, t_sim 400) driven through the
+    per-step controller API exactly as the reference's loop does (controller_operation.py:269-305); one sample per MPC
+    iteration = solve + its n_mpc_step plant steps + window updates."""
+    ctrl, plant = make_ctrl(), plant_factory()
+    ts = []
+    for rep in range(3):                       # rep 0 warms everything up
+        ctrl_r, plant_r = (ctrl, plant) if rep == 0 else (make_ctrl(), plant_factory())
+        ts = []
+        for t in range(0, n_steps, ctrl_r.n_mpc_step):
+            t0 = time.perf_counter()
+            ctrl_r.update_and_solve_data_driven_mpc()
+            for k in range(t, min(t + ctrl_r.n_mpc_step, n_steps)):
+                u = ctrl_r.get_optimal_control_input_at_step(n_step=k - t)
+                y = plant_r.simulate_step(u, w_sys[k])
+                ctrl_r.store_input_output_measurement(u.reshape(-1, 1), y.reshape(-1, 1))
+            ts.append((time.perf_counter() - t0) * 1e6)
+    ts = np.array(ts)
+    return {"p50_us": float(np.percentile(ts, 50)), "p90_us": float(np.percentile(ts, 90)), "iterations": int(ts.size),
+            "what": "config 1 (four-tank, seed 0, t_sim 400, n_mpc_step 4): one MPC iteration = solve + 4 plant steps"}
+
+
+class _HostPlant:
+    """utilities/model_simulation.py:93-98 on the host (the plant stays on the host in the per-step API)."""
+
+    def __init__(self, pl, x):
+        self.A, self.B, self.C, self.D, self.x = pl.A, pl.B, pl.C, pl.D, np.array(x, dtype=float)
+
+    def simulate_step(self, u, w):
+        y = self.C @ self.x + self.D @ u + w
+        self.x = self.A @ self.x + self.B @ u
+        return y
+
+
 def run_reference(args, rank, world):
     """--impl reference: the CPU implementation of the path on the host cores.  cvxpy is not installed in this
     image (no wheel, no network) so the unmodified reference class cannot run; the oracle port runs instead."""
@@ -279,8 +313,10 @@ def main():
     run_step = graph.replay if graph is not None else step
     for _ in range(max(args.warmup, 3)):       # W untimed warm-up steps, no idle gap before the timed region
         run_step()
-    if world > 1:                              # warm the collective too (communicator set-up is not part of a step)
-        wtrack = (y_sys[:, -1, :] - ys).abs().amax(dim=1)
+    # warm the per-loop metric kernels (first use loads their CUDA modules) and the collective
+    # (communicator set-up): neither is part of a step
+    wtrack = (y_sys[:, -1, :] - ys).abs().amax(dim=1)
+    if world > 1:
         dist.all_gather([torch.empty_like(wtrack) for _ in range(world)], wtrack)
     barrier()
     launches0 = _lib.kernel_launches()
@@ -372,9 +408,26 @@ def main():
            "ms_per_step": float(ems.item()) / args.e2e_steps,
            "api": "ControllerSet.closed_loop_host (pinned host in, full trajectories out, 8 chunks on 2 streams)"}
 
-    cb = None
+    cb, latency = None, None
+    if rank == 0:
+        from direct_data_driven_mpc_b200 import (DataDrivenMPCType, DirectDataDrivenMPCController,
+                                                 SlackVarConstraintTypes)
+        rng1, x0_1, ud1, yd1, xe1 = S.example_data(0)
+        w1 = 0.002 * rng1.uniform(-1.0, 1.0, (N_STEPS, 2))
+
+        def make_gpu_ctrl():
+            return DirectDataDrivenMPCController(
+                n=4, m=2, p=2, u_d=ud1, y_d=yd1, L=30, Q=prm["Q"], R=prm["R"], u_s=prm["u_s"], y_s=prm["y_s"],
+                eps_max=prm["eps_max"], lamb_alpha=prm["lamb_alpha"], lamb_sigma=prm["lamb_sigma"], c=prm["c"],
+                slack_var_constraint_type=SlackVarConstraintTypes.NONE, controller_type=DataDrivenMPCType.ROBUST,
+                n_mpc_step=4, use_terminal_constraint=True)
+        latency = single_loop_latency(make_gpu_ctrl, lambda: _HostPlant(plant, xe1), w1)
+        latency["api"] = "DirectDataDrivenMPCController.update_and_solve_data_driven_mpc (B = 1, host buffers)"
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cb = cpu_baseline(args.cpu_seconds)
+        from oracle import ddmpc_oracle as O
+        cb["single_loop_latency"] = single_loop_latency(
+            lambda: O.make_controller(O.four_tank_params(), ud1, yd1), lambda: _HostPlant(plant, xe1), w1)
 
     if rank == 0:
         line = {
@@ -382,6 +435,7 @@ def main():
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(B, world),
             "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cb,
+            "single_loop_latency": latency,
             "setup_ms": setup_ms, "solves_per_step_per_gpu": solves_per_step,
             "final_tracking_error_max": float(track.max().item()),
         }

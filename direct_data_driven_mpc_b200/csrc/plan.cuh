@@ -57,4 +57,12 @@ struct ddmpc_set {
     // gemm_loop.cu: workspace (block maps of the plant + value-major loop state) and its host key
     mutable ddmpc::DevBuf gemm_ws;
     mutable std::vector<double> gemm_host;
+    // solve.cu: staging of the B = 1 host path (pinned host, device, private stream)
+    mutable void *stage_host = nullptr;
+    mutable ddmpc::DevBuf stage_dev;
+    mutable cudaStream_t stage_stream = nullptr;
+    ~ddmpc_set() {
+        if (stage_host) cudaFreeHost(stage_host);
+        if (stage_stream) cudaStreamDestroy(stage_stream);
+    }
 };

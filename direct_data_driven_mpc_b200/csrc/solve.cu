@@ -174,6 +174,144 @@ __global__ void k_solve_batch(KArgs a, int B, const int *__restrict__ ctrl_idx, 
     if (iters_out) iters_out[b] = iters;
 }
 
+// ---------------------------------------------------------------------------
+// Small batches (the B = 1 controller object of the reference API, up to a few dozen solves):
+// one CTA per solve, rows of every operator spread over the threads, block-cooperative ADMM.
+// Same arithmetic as k_solve_batch; exists for latency (p50 single-loop step latency metric).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double block_max(double v, double *red) {
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double r = red[0];
+    for (int w = 1; w < (blockDim.x + 31) / 32; ++w) r = fmax(r, red[w]);
+    return r;
+}
+__device__ __forceinline__ double block_sum(double v, double *red) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double r = 0.0;
+    for (int w = 0; w < (blockDim.x + 31) / 32; ++w) r += red[w];
+    return r;
+}
+__device__ __forceinline__ double dot_row(const double *__restrict__ row, const double *v, int n) {
+    double a0 = 0.0, a1 = 0.0;
+    int j = 0;
+    for (; j + 1 < n; j += 2) {
+        a0 = fma(__ldg(row + j), v[j], a0);
+        a1 = fma(__ldg(row + j + 1), v[j + 1], a1);
+    }
+    if (j < n) a0 = fma(__ldg(row + j), v[j], a0);
+    return a0 + a1;
+}
+
+__global__ void __launch_bounds__(128)
+k_solve_small(KArgs a, int B, const int *__restrict__ ctrl_idx, const double *__restrict__ u_past,
+              const double *__restrict__ y_past, const double *__restrict__ u_s, const double *__restrict__ y_s,
+              double *__restrict__ optimal_u, double *__restrict__ cost, int *__restrict__ status_out,
+              int *__restrict__ iters_out, double *__restrict__ t_out) {
+    extern __shared__ double sm[];
+    const int b = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
+    double *th = sm, *su = th + a.nth, *z = su + a.nb, *w = z + a.nb, *dd = w + a.nb, *red = dd + a.nb;
+    const int c = ctrl_idx ? ctrl_idx[b] : 0;
+    const int nm = a.n * a.m, npp = a.n * a.p;
+    double tmax = 0.0, bad = 0.0;
+    for (int i = tid; i < a.nth; i += T) {
+        double v;
+        if (i < nm) v = u_past[(size_t)b * nm + i];
+        else if (i < nm + npp) v = y_past[(size_t)b * npp + (i - nm)];
+        else if (i < nm + npp + a.m) v = u_s[(size_t)b * a.m + (i - nm - npp)];
+        else v = y_s[(size_t)b * a.p + (i - nm - npp - a.m)];
+        th[i] = v;
+        tmax = fmax(tmax, fabs(v));
+        if (!isfinite(v)) bad = 1.0;
+    }
+    const double thmax = block_max(tmax, red);
+    const bool finite = block_max(bad, red) == 0.0;
+    int status = finite ? DDMPC_SOLVE_OPTIMAL : DDMPC_SOLVE_NONFINITE;
+    int iters = 1;
+    if (a.F) {
+        const double *F = a.F + (size_t)c * a.nfix * a.nth;
+        double fe = 0.0;
+        for (int i = tid; i < a.nfix; i += T) fe = fmax(fe, fabs(dot_row(F + (size_t)i * a.nth, th, a.nth)));
+        fe = block_max(fe, red);
+        if (fe > 1e-6 * (1.0 + thmax)) status = max(status, (int)DDMPC_SOLVE_INFEASIBLE);
+    }
+    const double *Ku = a.Ku + (size_t)c * a.Lm * a.nth;
+    for (int k = tid; k < a.Lm; k += T) optimal_u[(size_t)b * a.Lm + k] = dot_row(Ku + (size_t)k * a.nth, th, a.nth);
+    double J = 0.0;
+    if (cost) {
+        const double *Z = a.Z + (size_t)c * a.nth * a.nth;
+        double part = 0.0;
+        for (int i = tid; i < a.nth; i += T) part = fma(th[i], dot_row(Z + (size_t)i * a.nth, th, a.nth), part);
+        J = block_sum(part, red);
+    }
+    bool active = false;
+    if (a.convex) {
+        const double *Ks = a.Ks + (size_t)c * a.nb * a.nth;
+        double sm_l = 0.0;
+        for (int j = tid; j < a.nb; j += T) {
+            const double s = dot_row(Ks + (size_t)j * a.nth, th, a.nth);
+            su[j] = s;
+            sm_l = fmax(sm_l, fabs(s));
+        }
+        const double smax = block_max(sm_l, red);
+        if (smax > a.bound && finite) {
+            active = true;
+            const double *Phi = a.Phi + (size_t)c * a.nb * a.nb;
+            const double bnd = a.bound, thr = a.tol * fmax(bnd, smax);
+            for (int j = tid; j < a.nb; j += T) {
+                z[j] = fmin(fmax(su[j], -bnd), bnd);
+                w[j] = 0.0;
+            }
+            int it = 0;
+            bool conv = false;
+            while (it < a.max_iter && !conv) {
+                ++it;
+                __syncthreads();
+                for (int j = tid; j < a.nb; j += T) dd[j] = su[j] - z[j] + w[j];
+                __syncthreads();
+                double res = 0.0;
+                for (int j = tid; j < a.nb; j += T) {
+                    const double acc = dot_row(Phi + (size_t)j * a.nb, dd, a.nb);
+                    const double si = (z[j] - w[j]) + acc;
+                    const double zn = fmin(fmax(si + w[j], -bnd), bnd);
+                    res = fmax(res, fmax(fabs(si - zn), fabs(zn - z[j])));
+                    w[j] = w[j] + si - zn;
+                    z[j] = zn;
+                }
+                conv = block_max(res, red) <= thr;
+            }
+            if (!conv) status = max(status, (int)DDMPC_SOLVE_OPTIMAL_INACCURATE);
+            iters = it;
+            __syncthreads();
+            for (int j = tid; j < a.nb; j += T) dd[j] = su[j] - z[j] + w[j];
+            __syncthreads();
+            for (int j = tid; j < a.nb; j += T) su[j] = dot_row(Phi + (size_t)j * a.nb, dd, a.nb);   // t = Phi d
+            __syncthreads();
+            const double *Psi = a.Psi + (size_t)c * a.Lm * a.nb;
+            for (int k = tid; k < a.Lm; k += T) optimal_u[(size_t)b * a.Lm + k] -= dot_row(Psi + (size_t)k * a.nb, su, a.nb);
+            if (cost) {
+                const double *Lam = a.Lam + (size_t)c * a.nb * a.nb;
+                const double rho = a.rho2[c];
+                double part = 0.0;
+                for (int i = tid; i < a.nb; i += T) part = fma(su[i], dot_row(Lam + (size_t)i * a.nb, su, a.nb), part);
+                J += rho * rho * block_sum(part, red);
+            }
+        }
+    }
+    if (t_out)
+        for (int j = tid; j < a.nb; j += T) t_out[(size_t)b * a.nb + j] = active ? su[j] : 0.0;
+    if (tid == 0) {
+        if (cost) cost[b] = J;
+        if (status_out) status_out[b] = status;
+        if (iters_out) iters_out[b] = iters;
+    }
+}
+
 // full primal: x = X0 theta - Yf t      (one thread per (b, i))
 __global__ void k_full_x(KArgs a, int B, const int *__restrict__ ctrl_idx, const double *__restrict__ u_past,
                          const double *__restrict__ y_past, const double *__restrict__ u_s,
@@ -440,6 +578,17 @@ int solve_batch_device(const ddmpc_set *set, int B, const int *ctrl_idx, const d
     if (!u_past || !y_past || !u_s || !y_s || !optimal_u)
         return fail(DDMPC_ERR_INVALID_ARG, "solve_batch: null argument");
     KArgs a = make_kargs(set, tol, max_iter);
+    if (B <= 64) {   // latency path: one CTA per solve
+        const size_t sh = sizeof(double) * ((size_t)a.nth + 4 * (size_t)a.nb + 64);
+        if (sh <= 200 * 1024) {
+            if (sh > 48 * 1024)
+                DDMPC_CUDA(cudaFuncSetAttribute(k_solve_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
+            k_solve_small<<<B, 128, sh, st>>>(a, B, ctrl_idx, u_past, y_past, u_s, y_s, optimal_u, cost, status, iters,
+                                              t_out);
+            DDMPC_LAUNCH_CHECK();
+            return DDMPC_OK;
+        }
+    }
     size_t smem = 0;
     const int tpb = pick_tpb((size_t)a.nth + 4 * (size_t)a.nb, &smem);
     if (!tpb) return fail(DDMPC_ERR_INVALID_ARG, "solve_batch: problem too large for the generic kernel");
@@ -490,11 +639,50 @@ int ddmpc_solve_batch(const ddmpc_set *set, int B, const int32_t *ctrl_idx, cons
                               nullptr, (cudaStream_t)stream);
 }
 
+// B == 1 (the controller object of the reference API): persistent pinned + device staging buffers,
+// two async copies and one kernel on a private stream - no allocation on the per-step path.
+static int solve_one_host_staged(const ddmpc_set *set, const int32_t *ctrl_idx, const double *u_past,
+                                 const double *y_past, const double *u_s, const double *y_s, double tol, int max_iter,
+                                 double *optimal_u, double *cost, int32_t *status, int32_t *iters) {
+    const Dims &d = set->plan.d;
+    const int nm = d.n * d.m, npp = d.n * d.p;
+    const size_t n_in = (size_t)d.nth + 1, n_out = (size_t)d.Lm + 3;   // doubles (+ ctrl / cost, status, iters)
+    if (!set->stage_host) {
+        DDMPC_CUDA(cudaHostAlloc(&set->stage_host, sizeof(double) * (n_in + n_out), cudaHostAllocDefault));
+        DDMPC_CUDA(set->stage_dev.alloc(sizeof(double) * (n_in + n_out)));
+        DDMPC_CUDA(cudaStreamCreateWithFlags(&set->stage_stream, cudaStreamNonBlocking));
+    }
+    double *h = (double *)set->stage_host, *dv = set->stage_dev.d();
+    std::copy(u_past, u_past + nm, h);
+    std::copy(y_past, y_past + npp, h + nm);
+    std::copy(u_s, u_s + d.m, h + nm + npp);
+    std::copy(y_s, y_s + d.p, h + nm + npp + d.m);
+    int32_t *hci = reinterpret_cast<int32_t *>(h + d.nth);
+    hci[0] = ctrl_idx ? ctrl_idx[0] : 0;
+    cudaStream_t st = set->stage_stream;
+    DDMPC_CUDA(cudaMemcpyAsync(dv, h, sizeof(double) * n_in, cudaMemcpyHostToDevice, st));
+    double *dout = dv + n_in;
+    int32_t *dints = reinterpret_cast<int32_t *>(dout + d.Lm + 1);
+    DDMPC_TRY(solve_batch_device(set, 1, reinterpret_cast<const int *>(dv + d.nth), dv, dv + nm, dv + nm + npp,
+                                 dv + nm + npp + d.m, tol, max_iter, dout, dout + d.Lm, dints, dints + 1, nullptr, st));
+    double *hout = h + n_in;
+    DDMPC_CUDA(cudaMemcpyAsync(hout, dout, sizeof(double) * n_out, cudaMemcpyDeviceToHost, st));
+    DDMPC_CUDA(cudaStreamSynchronize(st));
+    std::copy(hout, hout + d.Lm, optimal_u);
+    if (cost) *cost = hout[d.Lm];
+    const int32_t *hints = reinterpret_cast<const int32_t *>(hout + d.Lm + 1);
+    if (status) *status = hints[0];
+    if (iters) *iters = hints[1];
+    return DDMPC_OK;
+}
+
 int ddmpc_solve_batch_host(const ddmpc_set *set, int B, const int32_t *ctrl_idx, const double *u_past,
                            const double *y_past, const double *u_s, const double *y_s, double tol, int max_iter,
                            double *optimal_u, double *cost, int32_t *status, int32_t *iters) {
     if (!set || B <= 0 || !optimal_u) return fail(DDMPC_ERR_INVALID_ARG, "solve_batch_host: bad argument");
     const Dims &d = set->plan.d;
+    if (B == 1 && u_past && y_past && u_s && y_s)
+        return solve_one_host_staged(set, ctrl_idx, u_past, y_past, u_s, y_s, tol, max_iter, optimal_u, cost, status, iters);
     Stage s;
     int32_t *dc, *dst, *dit;
     double *dup, *dyp, *dus, *dys, *dou, *dco;
@@ -508,6 +696,7 @@ int ddmpc_solve_batch_host(const ddmpc_set *set, int B, const int32_t *ctrl_idx,
     DDMPC_TRY(s.out((size_t)B, &dst, status != nullptr));
     DDMPC_TRY(s.out((size_t)B, &dit, iters != nullptr));
     DDMPC_TRY(solve_batch_device(set, B, dc, dup, dyp, dus, dys, tol, max_iter, dou, dco, dst, dit, nullptr, nullptr));
+    DDMPC_CUDA(cudaStreamSynchronize(nullptr));
     DDMPC_CUDA(cudaMemcpy(optimal_u, dou, sizeof(double) * B * d.Lm, cudaMemcpyDeviceToHost));
     if (cost) DDMPC_CUDA(cudaMemcpy(cost, dco, sizeof(double) * B, cudaMemcpyDeviceToHost));
     if (status) DDMPC_CUDA(cudaMemcpy(status, dst, sizeof(int32_t) * B, cudaMemcpyDeviceToHost));
