@@ -869,6 +869,274 @@ k_closed_loop_pair(const __grid_constant__ PairCoef<N, M, P, NX, NMPC> cfp, cons
     }
 }
 
+// ===========================================================================
+// All-tensor-core variant (four-tank n-step shape: 8 planned-input rows, NMPC a multiple of N, M = P = 2).
+// Per n-step block and warp (64 loops = 8 n-tiles of the m8n8k4 FP64 MMA):
+//   solve :  U (8 x loops)         = Ku (8 x 16) [window_u; window_y] + csp          4 k-steps, 32 DMMA
+//   plant :  [Y (8); x+ (4)] x loops = Mblk (12 x 12) [x (4); U (8)]                 3 k-steps x 2 row tiles, 48 DMMA
+// where Mblk is the NMPC-step block map of the LTI plant (rows y_0..y_{NMPC-1}, x_NMPC; columns x_0, u_0..):
+// model_simulation.py:93-98 unrolled NMPC times (measurement noise only enters y and is added afterwards).
+// Everything lives in shared memory [value][loop]; the planned inputs of a block ARE the input half of the next
+// measurement window (NMPC = N), so `up_s` doubles as the window.  What is left for the owner thread of a loop is
+// the noise draw, y = Y + w, the sector-paired trajectory stores and the output half of the window.
+// ===========================================================================
+template <int N, int M, int P, int NX, int NMPC>
+struct MmaCoef {
+    double Ku[NMPC * M][N * (M + P)];               // gain rows on [u_past; y_past]
+    double Mb[NMPC * P + NX][NX + NMPC * M];        // block map, full block
+    double Mt[NMPC * P + NX][NX + NMPC * M];        // block map of the last, partial block (n_tail steps), zero padded
+};
+
+template <int N, int M, int P, int NX, int NMPC, bool PHILOX>
+__global__ void __launch_bounds__(32, 8)
+k_closed_loop_mma(const __grid_constant__ MmaCoef<N, M, P, NX, NMPC> cfp, const FastArgs a, const int n_tail) {
+    constexpr int R = NMPC * M, NW = N * (M + P), LPT = 2, TPB = 32, TP = TPB + 2, NT = TPB / 8;
+    constexpr int KB = NX + R, RB = NMPC * P + NX;
+    static_assert(M == 2 && P == 2 && R == 8 && (NMPC % N) == 0 && NMPC == N, "shape not supported by the MMA kernel");
+    static_assert(NW % 4 == 0 && (N * M) % 4 == 0 && KB % 4 == 0 && RB <= 16 && NMPC * P == 8, "fragment tiling");
+    __shared__ __align__(16) double csp_s[R][LPT][TP];
+    __shared__ __align__(16) double up_s[R][LPT][TP];          // planned inputs = input half of the window
+    __shared__ __align__(16) double wy_s[N * P][LPT][TP];      // output half of the window
+    __shared__ __align__(16) double x_s[NX][LPT][TP];          // plant state
+    __shared__ __align__(16) double Y_s[NMPC * P][LPT][TP];    // noise-free outputs of the block
+    const int tl = threadIdx.x, g = tl >> 2, q = tl & 3;
+    int b[LPT];
+    bool live[LPT];
+    size_t f0[LPT];
+    uint32_t sid_lo[LPT], sid_hi[LPT];
+#pragma unroll
+    for (int l = 0; l < LPT; ++l) {
+        b[l] = blockIdx.x * 64 + 2 * tl + l;
+        live[l] = b[l] < a.B;
+        if (!live[l]) b[l] = 0;
+        f0[l] = (size_t)b[l] * a.n_steps;
+        const unsigned long long sid = a.id0 + (unsigned long long)b[l];
+        sid_lo[l] = (uint32_t)sid;
+        sid_hi[l] = (uint32_t)(sid >> 32);
+#pragma unroll
+        for (int i = 0; i < NX; ++i) x_s[i][l][tl] = a.x0[(size_t)b[l] * NX + i];
+#pragma unroll
+        for (int i = 0; i < N * M; ++i) up_s[i][l][tl] = a.u_past0[(size_t)b[l] * N * M + i];
+#pragma unroll
+        for (int i = 0; i < N * P; ++i) wy_s[i][l][tl] = a.y_past0[(size_t)b[l] * N * P + i];
+        double sp[M + P];
+#pragma unroll
+        for (int i = 0; i < M; ++i) sp[i] = a.u_s[(size_t)b[l] * M + i];
+#pragma unroll
+        for (int i = 0; i < P; ++i) sp[M + i] = a.y_s[(size_t)b[l] * P + i];
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            double acc = 0.0;
+#pragma unroll
+            for (int j = 0; j < M + P; ++j) acc = fma(__ldg(a.Ksp + k * (M + P) + j), sp[j], acc);
+            csp_s[k][l][tl] = acc;
+        }
+    }
+    // A fragments (row g, column 4*ks + q of each k-step) stay in registers for the whole run
+    double aK[NW / 4], aP[2][KB / 4];
+#pragma unroll
+    for (int ks = 0; ks < NW / 4; ++ks) aK[ks] = cfp.Ku[g][4 * ks + q];
+#pragma unroll
+    for (int rt = 0; rt < 2; ++rt)
+#pragma unroll
+        for (int ks = 0; ks < KB / 4; ++ks) aP[rt][ks] = (8 * rt + g < RB) ? cfp.Mb[(8 * rt + g) % RB][4 * ks + q] : 0.0;
+    double pu[LPT][M], py[LPT][P];               // previous trajectory element (sector pairing)
+    uint32_t nw[LPT][4];
+#pragma unroll
+    for (int l = 0; l < LPT; ++l) {
+        pu[l][0] = pu[l][1] = py[l][0] = py[l][1] = 0.0;
+        nw[l][0] = nw[l][1] = nw[l][2] = nw[l][3] = 0u;
+    }
+    __syncwarp();
+
+    auto mma = [](double2 &c, double av, double bv) {
+        asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+            : "+d"(c.x), "+d"(c.y)
+            : "d"(av), "d"(bv));
+    };
+    auto block = [&](const int t0, const int steps) {
+        // ---- solve: planned inputs (C fragments start from the set-point term)
+        double2 c[LPT][NT];
+#pragma unroll
+        for (int l = 0; l < LPT; ++l)
+#pragma unroll
+            for (int t8 = 0; t8 < NT; ++t8) c[l][t8] = *reinterpret_cast<const double2 *>(&csp_s[g][l][8 * t8 + 2 * q]);
+#pragma unroll
+        for (int ks = 0; ks < NW / 4; ++ks) {
+            const int e = 4 * ks + q;
+#pragma unroll
+            for (int l = 0; l < LPT; ++l)
+#pragma unroll
+                for (int t8 = 0; t8 < NT; ++t8) {
+                    const double bv = (4 * ks < N * M) ? up_s[e < N * M ? e : 0][l][8 * t8 + g]
+                                                       : wy_s[e >= N * M ? e - N * M : 0][l][8 * t8 + g];
+                    mma(c[l][t8], aK[ks], bv);
+                }
+        }
+        __syncwarp();                            // every lane has read the old window
+#pragma unroll
+        for (int l = 0; l < LPT; ++l)
+#pragma unroll
+            for (int t8 = 0; t8 < NT; ++t8) *reinterpret_cast<double2 *>(&up_s[g][l][8 * t8 + 2 * q]) = c[l][t8];
+        __syncwarp();
+        // ---- plant: NMPC steps at once through the block map
+        double2 d[2][LPT][NT];
+#pragma unroll
+        for (int rt = 0; rt < 2; ++rt)
+#pragma unroll
+            for (int l = 0; l < LPT; ++l)
+#pragma unroll
+                for (int t8 = 0; t8 < NT; ++t8) d[rt][l][t8] = make_double2(0.0, 0.0);
+#pragma unroll
+        for (int ks = 0; ks < KB / 4; ++ks) {
+            const int e = 4 * ks + q;
+#pragma unroll
+            for (int l = 0; l < LPT; ++l)
+#pragma unroll
+                for (int t8 = 0; t8 < NT; ++t8) {
+                    const double bv = (4 * ks < NX) ? x_s[e < NX ? e : 0][l][8 * t8 + g]
+                                                    : up_s[e >= NX ? e - NX : 0][l][8 * t8 + g];
+#pragma unroll
+                    for (int rt = 0; rt < 2; ++rt) mma(d[rt][l][t8], aP[rt][ks], bv);
+                }
+        }
+        __syncwarp();                            // every lane has read the old state
+#pragma unroll
+        for (int l = 0; l < LPT; ++l)
+#pragma unroll
+            for (int t8 = 0; t8 < NT; ++t8) {
+                *reinterpret_cast<double2 *>(&Y_s[g][l][8 * t8 + 2 * q]) = d[0][l][t8];
+                if (g < NX) *reinterpret_cast<double2 *>(&x_s[g][l][8 * t8 + 2 * q]) = d[1][l][t8];
+            }
+        __syncwarp();
+        // ---- owner thread: noise, outputs, trajectory stores, output half of the window
+#pragma unroll
+        for (int l = 0; l < LPT; ++l) {
+#pragma unroll
+            for (int s = 0; s < NMPC; ++s) {
+                if (s < steps) {
+                    const int k = t0 + s;
+                    double u[M], y[P];
+#pragma unroll
+                    for (int i = 0; i < M; ++i) u[i] = up_s[s * M + i][l][tl];
+                    if constexpr (!PHILOX) {
+#pragma unroll
+                        for (int i = 0; i < P; ++i) y[i] = __ldg(a.w + (f0[l] + k) * P + i);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < P; ++i) {
+                            const int qs = s * P + i;          // word (qs & 3) of call t0*P/4 + (qs >> 2)
+                            if ((qs & 3) == 0) {
+                                uint32_t c0 = (uint32_t)(((unsigned)t0 * (unsigned)P) >> 2) + (uint32_t)(qs >> 2), c1 = 0u,
+                                         c2 = sid_lo[l], c3 = sid_hi[l];
+#pragma unroll
+                                for (int r = 0; r < 10; ++r) philox_round(c0, c1, c2, c3, a.rk[2 * r], a.rk[2 * r + 1]);
+                                nw[l][0] = c0; nw[l][1] = c1; nw[l][2] = c2; nw[l][3] = c3;
+                            }
+                            y[i] = a.eps * (2.0 * unit32_fast(nw[l][qs & 3]) - 3.0);
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < P; ++i) y[i] = Y_s[s * P + i][l][tl] + y[i];
+                    const size_t f = f0[l] + k;
+                    if (live[l]) {
+                        if (f & 1) {             // warp-uniform: completes the sector (f-1, f)
+                            if (k == 0) {
+                                *reinterpret_cast<double2 *>(a.u_sys + f * 2) = make_double2(u[0], u[1]);
+                                *reinterpret_cast<double2 *>(a.y_sys + f * 2) = make_double2(y[0], y[1]);
+                            } else {
+                                asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(a.u_sys + (f - 1) * 2),
+                                             "d"(pu[l][0]), "d"(pu[l][1]), "d"(u[0]), "d"(u[1])
+                                             : "memory");
+                                asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(a.y_sys + (f - 1) * 2),
+                                             "d"(py[l][0]), "d"(py[l][1]), "d"(y[0]), "d"(y[1])
+                                             : "memory");
+                            }
+                        }
+                    }
+                    pu[l][0] = u[0]; pu[l][1] = u[1]; py[l][0] = y[0]; py[l][1] = y[1];
+#pragma unroll
+                    for (int i = 0; i < P; ++i) wy_s[s * P + i][l][tl] = y[i];
+                }
+            }
+        }
+        __syncwarp();
+    };
+
+    int t0 = 0;
+    for (; t0 + NMPC <= a.n_steps; t0 += NMPC) block(t0, NMPC);
+    if (t0 < a.n_steps) {                        // last, partial block (controller_operation.py:278): its own block map
+#pragma unroll
+        for (int rt = 0; rt < 2; ++rt)
+#pragma unroll
+            for (int ks = 0; ks < KB / 4; ++ks)
+                aP[rt][ks] = (8 * rt + g < RB) ? cfp.Mt[(8 * rt + g) % RB][4 * ks + q] : 0.0;
+        block(t0, n_tail);
+    }
+#pragma unroll
+    for (int l = 0; l < LPT; ++l) {
+        if (!live[l]) continue;
+        const size_t fl = f0[l] + a.n_steps - 1;
+        if ((fl & 1) == 0) {                     // an unpaired final element is still in (pu, py)
+            *reinterpret_cast<double2 *>(a.u_sys + fl * 2) = make_double2(pu[l][0], pu[l][1]);
+            *reinterpret_cast<double2 *>(a.y_sys + fl * 2) = make_double2(py[l][0], py[l][1]);
+        }
+        bool finite = isfinite(py[l][0]) && isfinite(py[l][1]);
+#pragma unroll
+        for (int i = 0; i < NX; ++i) finite = finite && isfinite(x_s[i][l][tl]);
+        if (a.status) a.status[b[l]] = finite ? DDMPC_SOLVE_OPTIMAL : DDMPC_SOLVE_NONFINITE;
+        if (a.iters) a.iters[b[l]] = (a.n_steps + NMPC - 1) / NMPC;
+        if (a.x_final) {
+#pragma unroll
+            for (int i = 0; i < NX; ++i) a.x_final[(size_t)b[l] * NX + i] = x_s[i][l][tl];
+        }
+    }
+}
+
+// s-step block map of the plant into Mout (rows y_0..y_{NMPC-1} (zero beyond s), then x_s; columns x_0, u_0..)
+template <int M, int P, int NX, int NMPC>
+static void host_block_map(const ddmpc_plant *pl, int s, double (&Mout)[NMPC * P + NX][NX + NMPC * M]) {
+    double Ap[NMPC + 1][NX][NX] = {};
+    for (int i = 0; i < NX; ++i) Ap[0][i][i] = 1.0;
+    for (int k = 1; k <= s; ++k)
+        for (int i = 0; i < NX; ++i)
+            for (int j = 0; j < NX; ++j) {
+                double acc = 0.0;
+                for (int l = 0; l < NX; ++l) acc += pl->A[i * NX + l] * Ap[k - 1][l][j];
+                Ap[k][i][j] = acc;
+            }
+    double AB[NMPC][NX][M] = {};
+    for (int k = 0; k < s; ++k)
+        for (int i = 0; i < NX; ++i)
+            for (int j = 0; j < M; ++j) {
+                double acc = 0.0;
+                for (int l = 0; l < NX; ++l) acc += Ap[k][i][l] * pl->B[l * M + j];
+                AB[k][i][j] = acc;
+            }
+    for (auto &row : Mout)
+        for (double &v : row) v = 0.0;
+    for (int k = 0; k < s; ++k)
+        for (int i = 0; i < P; ++i) {
+            for (int c = 0; c < NX; ++c) {
+                double acc = 0.0;
+                for (int l = 0; l < NX; ++l) acc += pl->C[i * NX + l] * Ap[k][l][c];
+                Mout[k * P + i][c] = acc;
+            }
+            for (int j = 0; j < k; ++j)
+                for (int c = 0; c < M; ++c) {
+                    double acc = 0.0;
+                    for (int l = 0; l < NX; ++l) acc += pl->C[i * NX + l] * AB[k - 1 - j][l][c];
+                    Mout[k * P + i][NX + j * M + c] = acc;
+                }
+            for (int c = 0; c < M; ++c) Mout[k * P + i][NX + k * M + c] = pl->D[i * M + c];
+        }
+    for (int i = 0; i < NX; ++i) {
+        for (int c = 0; c < NX; ++c) Mout[NMPC * P + i][c] = Ap[s][i][c];
+        for (int j = 0; j < s; ++j)
+            for (int c = 0; c < M; ++c) Mout[NMPC * P + i][NX + j * M + c] = AB[s - 1 - j][i][c];
+    }
+}
+
 // gather the Ksp block of Ku (rows 0..NMPC*M-1, columns n*(m+p)..nth-1) into a dense device array
 __global__ void k_gather_ksp(const double *__restrict__ Ku, int nth, int nw, int rows, double *__restrict__ out) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -936,6 +1204,30 @@ static int launch_fast(const ddmpc_set *set, const ddmpc_plant *plant, const Fas
             return DDMPC_OK;
         } else {
             return -1;
+        }
+    }
+    {   // all-tensor-core variant (solve AND plant on the FP64 MMA pipe) for the four-tank n-step shape.
+        // Measured equal to the hybrid kernel (0.255 vs 0.250 ms on config 3: both are latency-bound at 1.7
+        // warps per scheduler, tensor pipe 47 % busy), so it is opt-in (DDMPC_PLANT_MMA=1): the hybrid kernel
+        // steps the plant literally as the reference does instead of through a block map.
+        constexpr bool MMA_OK = (M == 2 && P == 2 && NMPC * M == 8 && NMPC == N && (N * M) % 4 == 0 &&
+                                 (NX + NMPC * M) % 4 == 0 && NMPC * P + NX <= 16 && NMPC * P == 8);
+        const char *e = getenv("DDMPC_PLANT_MMA");
+        const bool want = e && e[0] == '1';
+        if constexpr (MMA_OK) {
+            if (want && pair && lpt == 2) {
+                MmaCoef<N, M, P, NX, NMPC> mc;
+                for (int k = 0; k < NMPC * M; ++k)
+                    for (int j = 0; j < NW; ++j) mc.Ku[k][j] = cache[(size_t)k * d.nth + j];
+                host_block_map<M, P, NX, NMPC>(plant, NMPC, mc.Mb);
+                const int n_tail = a.n_steps % NMPC;
+                host_block_map<M, P, NX, NMPC>(plant, n_tail ? n_tail : NMPC, mc.Mt);
+                const dim3 gridm(ceil_div(a.B, 64));
+                if (a.w) k_closed_loop_mma<N, M, P, NX, NMPC, false><<<gridm, 32, 0, st>>>(mc, a, n_tail);
+                else k_closed_loop_mma<N, M, P, NX, NMPC, true><<<gridm, 32, 0, st>>>(mc, a, n_tail);
+                DDMPC_LAUNCH_CHECK();
+                return DDMPC_OK;
+            }
         }
     }
     const int tpb = lpt == 1 ? 64 : 32;

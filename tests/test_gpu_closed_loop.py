@@ -342,3 +342,26 @@ def test_batched_reproduction_matches_reference_semantics(golden_repro):
     uc = res["schemes"]["UCON"]
     assert _rel(uc["u_sys"][0, :150].cpu().numpy(), g["u_UCON"][:150]) < 1e-5
     assert bool(uc["diverged"][0])                               # UCON diverges by design (reproduction.py:21-28)
+
+
+def test_all_tensor_core_variant_matches_default(monkeypatch):
+    """Opt-in k_closed_loop_mma (plant through the block map on the FP64 MMA pipe) vs the default fused kernel,
+    including a partial last block and uploaded noise."""
+    plant_o, prm, rng, x0, u_d, y_d = O.example_scenario(0)
+    cs, _ = _set(u_d, y_d)
+    B = 16384 + 70
+    r = np.random.default_rng(5)
+    xs = np.tile(plant_o.x, (B, 1)) + 0.05 * r.normal(size=(B, 4))
+    us = np.tile(prm["u_s"].T, (B, 1)) * r.uniform(0.7, 1.3, (B, 1))
+    ys = us @ _plant().equilibrium_gain().T
+    up0, yp0 = np.tile(u_d[-4:].reshape(1, -1), (B, 1)), np.tile(y_d[-4:].reshape(1, -1), (B, 1))
+    for n_steps, kw in ((41, dict(noise_seed=3, scenario_id0=11, noise_eps=0.002)),
+                        (12, dict(w=0.002 * r.uniform(-1, 1, (B, 12, 2))))):
+        monkeypatch.delenv("DDMPC_PLANT_MMA", raising=False)
+        u1, y1, s1, i1, x1 = cs.closed_loop(_plant(), xs, up0, yp0, us, ys, n_steps, want_x_final=True, **kw)
+        monkeypatch.setenv("DDMPC_PLANT_MMA", "1")
+        u2, y2, s2, i2, x2 = cs.closed_loop(_plant(), xs, up0, yp0, us, ys, n_steps, want_x_final=True, **kw)
+        monkeypatch.delenv("DDMPC_PLANT_MMA", raising=False)
+        assert int(s2.max()) == 0 and (i1 == i2).all()
+        assert _rel(u2.cpu().numpy(), u1.cpu().numpy()) < 1e-9 and _rel(y2.cpu().numpy(), y1.cpu().numpy()) < 1e-9
+        assert _rel(x2.cpu().numpy(), x1.cpu().numpy()) < 1e-9
