@@ -241,12 +241,35 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def bind_to_gpu_numa_node(dev_index: int):
+    """Run this rank on the CPUs local to its GPU, so the pinned staging buffers (first-touch) and the
+    copy-launching thread sit on the GPU's NUMA node.  Best effort; returns a short description."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[dev_index]) if vis and vis.split(",")[dev_index].isdigit() else dev_index
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        n_words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = {64 * w + b for w, word in enumerate(mask) for b in range(64) if (word >> b) & 1}
+        allowed = cpus & os.sched_getaffinity(0)
+        if allowed and allowed != os.sched_getaffinity(0):
+            os.sched_setaffinity(0, allowed)
+            return f"bound to {len(allowed)} GPU-local CPUs"
+        return "already local"
+    except Exception as exc:
+        return f"not bound ({type(exc).__name__})"
+
+
 def measure_e2e(args, cs, sc, plant, id0, solves_per_step, world, barrier, dev, u_sys):
     """`e2e`: the same metric through the host-buffer API (ControllerSet.closed_loop_host): every step copies its
     inputs from pinned host memory and brings the full trajectories back to pinned host memory."""
     import torch
     import torch.distributed as dist
     B = sc["x0"].shape[0]
+    old_affinity = os.sched_getaffinity(0)
+    numa = bind_to_gpu_numa_node(dev.index)
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
     hx0, hup, hyp, hus, hys = pin(sc["x0"]), pin(sc["u_past0"]), pin(sc["y_past0"]), pin(sc["u_s"]), pin(sc["y_s"])
     hu = torch.empty(B, N_STEPS, 2, dtype=torch.float64, pin_memory=True)
@@ -274,9 +297,11 @@ def measure_e2e(args, cs, sc, plant, id0, solves_per_step, world, barrier, dev, 
     assert torch.allclose(hu[:64], u_sys[:64].cpu(), rtol=1e-9, atol=1e-9), "host-API result differs from the device-resident run"
     h2d = sum(t.numel() * t.element_size() for t in (hx0, hup, hyp, hus, hys))
     d2h = hu.numel() * 8 + hy.numel() * 8 + B * 4
+    os.sched_setaffinity(0, old_affinity)      # the CPU baseline must see every core again
     return {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
            "ms_per_step": float(ems.item()) / args.e2e_steps,
-           "api": "ControllerSet.closed_loop_host (pinned host in, full trajectories out, 8 chunks on 2 streams)"}
+           "api": "ControllerSet.closed_loop_host (pinned host in, full trajectories out, 8 chunks on 2 streams)",
+           "numa": numa}
 
 
 

@@ -134,3 +134,23 @@ def test_empty_and_single():
     assert np.abs(u[0].cpu().numpy() - so.optimal_u).max() < 1e-8 * max(1.0, np.abs(so.optimal_u).max())
     u0, _, s0, _ = cs.solve_batch(up[:0], yp[:0], us[:0], ys[:0])
     assert u0.shape == (0, 60)
+
+
+@pytest.mark.parametrize("slack,c", [(0, 1.0), (1, 0.3)])
+def test_solve_batch_large_batch_kernel_matches_small_batch_kernel(slack, c):
+    """B > 64 takes the thread-per-solve kernel, B <= 64 the CTA-per-solve kernel: same results; spot-check vs oracle."""
+    cs, qp, prm, u_d, y_d = _set(slack, True, c)
+    B = 200
+    up, yp, us, ys = _thetas(u_d, y_d, prm, B, seed=11)
+    u_big, cost_big, st_big, it_big = cs.solve_batch(up, yp, us, ys)
+    parts = [cs.solve_batch(up[i:i + 50], yp[i:i + 50], us[i:i + 50], ys[i:i + 50]) for i in range(0, B, 50)]
+    import torch
+    u_small = torch.cat([p[0] for p in parts]); it_small = torch.cat([p[3] for p in parts])
+    cost_small = torch.cat([p[1] for p in parts])
+    assert int(st_big.max()) == 0
+    assert (it_big == it_small).all()
+    assert float((u_big - u_small).abs().max()) <= 1e-9 * max(1.0, float(u_small.abs().max()))
+    assert float((cost_big - cost_small).abs().max()) <= 1e-9 * max(1.0, float(cost_small.abs().max()))
+    for b in (0, 77, 199):
+        so = qp.solve(up[b], yp[b], us[b], ys[b])
+        assert np.abs(u_big[b].cpu().numpy() - so.optimal_u).max() < 1e-5 * max(1.0, np.abs(so.optimal_u).max())
