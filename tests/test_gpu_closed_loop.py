@@ -344,9 +344,10 @@ def test_batched_reproduction_matches_reference_semantics(golden_repro):
     assert bool(uc["diverged"][0])                               # UCON diverges by design (reproduction.py:21-28)
 
 
-def test_all_tensor_core_variant_matches_default(monkeypatch):
-    """Opt-in k_closed_loop_mma (plant through the block map on the FP64 MMA pipe) vs the default fused kernel,
-    including a partial last block and uploaded noise."""
+def test_tensor_core_variants_match_hybrid(monkeypatch):
+    """The warp-specialised kernel (k_closed_loop_ws: math warp + i/o warp, the default for large batches) and the
+    opt-in single-warp k_closed_loop_mma (both: plant through the block map on the FP64 MMA pipe) vs the hybrid
+    fused kernel (DDMPC_WS=0), including a partial last block, uploaded noise and a ragged batch."""
     plant_o, prm, rng, x0, u_d, y_d = O.example_scenario(0)
     cs, _ = _set(u_d, y_d)
     B = 16384 + 70
@@ -356,12 +357,42 @@ def test_all_tensor_core_variant_matches_default(monkeypatch):
     ys = us @ _plant().equilibrium_gain().T
     up0, yp0 = np.tile(u_d[-4:].reshape(1, -1), (B, 1)), np.tile(y_d[-4:].reshape(1, -1), (B, 1))
     for n_steps, kw in ((41, dict(noise_seed=3, scenario_id0=11, noise_eps=0.002)),
-                        (12, dict(w=0.002 * r.uniform(-1, 1, (B, 12, 2))))):
+                        (401, dict(noise_seed=0, scenario_id0=0, noise_eps=0.002)),
+                        (12, dict(w=0.002 * r.uniform(-1, 1, (B, 12, 2)))),
+                        (3, dict(w=0.002 * r.uniform(-1, 1, (B, 3, 2))))):
+        monkeypatch.setenv("DDMPC_WS", "0")
         monkeypatch.delenv("DDMPC_PLANT_MMA", raising=False)
         u1, y1, s1, i1, x1 = cs.closed_loop(_plant(), xs, up0, yp0, us, ys, n_steps, want_x_final=True, **kw)
-        monkeypatch.setenv("DDMPC_PLANT_MMA", "1")
-        u2, y2, s2, i2, x2 = cs.closed_loop(_plant(), xs, up0, yp0, us, ys, n_steps, want_x_final=True, **kw)
-        monkeypatch.delenv("DDMPC_PLANT_MMA", raising=False)
-        assert int(s2.max()) == 0 and (i1 == i2).all()
-        assert _rel(u2.cpu().numpy(), u1.cpu().numpy()) < 1e-9 and _rel(y2.cpu().numpy(), y1.cpu().numpy()) < 1e-9
-        assert _rel(x2.cpu().numpy(), x1.cpu().numpy()) < 1e-9
+        for env in (dict(DDMPC_WS="1"), dict(DDMPC_WS="0", DDMPC_PLANT_MMA="1")):
+            for k, v in env.items():
+                monkeypatch.setenv(k, v)
+            u2, y2, s2, i2, x2 = cs.closed_loop(_plant(), xs, up0, yp0, us, ys, n_steps, want_x_final=True, **kw)
+            monkeypatch.delenv("DDMPC_PLANT_MMA", raising=False)
+            monkeypatch.delenv("DDMPC_WS", raising=False)
+            assert int(s2.max()) == 0 and (i1 == i2).all(), env
+            assert _rel(u2.cpu().numpy(), u1.cpu().numpy()) < 1e-9 and _rel(y2.cpu().numpy(), y1.cpu().numpy()) < 1e-9, env
+            assert _rel(x2.cpu().numpy(), x1.cpu().numpy()) < 1e-9, env
+
+
+def test_warp_specialised_kernel_vs_oracle():
+    """Default large-batch path (k_closed_loop_ws) against the literal-KKT oracle on whole 401-step loops."""
+    plant_o, prm, rng, x0, u_d, y_d = O.example_scenario(0)
+    cs, _ = _set(u_d, y_d)
+    B, n_steps = 16384 + 3, 401
+    r = np.random.default_rng(8)
+    xs = np.tile(plant_o.x, (B, 1)) + 0.05 * r.normal(size=(B, 4))
+    us = np.tile(prm["u_s"].T, (B, 1)) * r.uniform(0.7, 1.3, (B, 1))
+    ys = us @ _plant().equilibrium_gain().T
+    up0, yp0 = np.tile(u_d[-4:].reshape(1, -1), (B, 1)), np.tile(y_d[-4:].reshape(1, -1), (B, 1))
+    u, y, st, it = cs.closed_loop(_plant(), xs, up0, yp0, us, ys, n_steps, noise_seed=21, scenario_id0=1000,
+                                  noise_eps=0.002)
+    assert int(st.max()) == 0 and int(it.min()) == 101 and int(it.max()) == 101
+    u, y = u.cpu().numpy(), y.cpu().numpy()
+    for b in (0, 1, 63, 64, 8191, B - 1):
+        w = O.philox_noise(21, np.array([1000 + b]), n_steps, 2, 0.002)[0]
+        po = O.four_tank_plant()
+        po.x = xs[b].copy()
+        ctrl = O.make_controller(prm, u_d, y_d, n_mpc_step=4)
+        ctrl.u_s, ctrl.y_s = us[b].reshape(-1, 1), ys[b].reshape(-1, 1)
+        u_ref, y_ref = O.closed_loop(po, ctrl, n_steps, w)
+        assert _rel(u[b], u_ref) < 1e-9 and _rel(y[b], y_ref) < 1e-9, b
