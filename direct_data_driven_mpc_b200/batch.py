@@ -65,12 +65,16 @@ class ControllerSet:
 
     u_d: (N, m) shared by every controller, or (count, N, m) one data set each.
     lamb_alpha / lamb_sigma: scalars or length-``count`` sequences.
+    input_bounds: optional ``(u_min, u_max)`` (scalars or length-m, ``None`` / inf = open side): the box
+    ``u_min <= ubar[k] <= u_max`` on every predicted input (paper Eq. 6; NOT part of the reference's
+    formulation, controller.py:447-504, so it is off by default).  ROBUST controllers only.
     """
 
     def __init__(self, n: int, m: int, p: int, u_d, y_d, L: int, Q, R, eps_max: Optional[float] = None,
                  lamb_alpha=None, lamb_sigma=None, c: Optional[float] = None, slack_type: int = _lib.SLACK_CONVEX,
                  controller_type: int = _lib.NOMINAL, n_mpc_step: int = 1, use_terminal_constraint: bool = True,
-                 count: Optional[int] = None, check_pe: bool = True, device: Optional[torch.device] = None):
+                 count: Optional[int] = None, check_pe: bool = True, device: Optional[torch.device] = None,
+                 input_bounds: Optional[Tuple[object, object]] = None):
         if not torch.cuda.is_available():
             raise RuntimeError("ControllerSet needs a CUDA device (no CPU fallback)")
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
@@ -116,6 +120,13 @@ class ControllerSet:
                           eps_max=scalar(eps_max), lamb_alpha=scalar(lamb_alpha), lamb_sigma=scalar(lamb_sigma),
                           c=scalar(c))
         self.eps_max = eps_max
+        self.input_bounds = None
+        if input_bounds is not None:
+            lo, hi = input_bounds
+            lo = np.full(m, -np.inf) if lo is None else np.broadcast_to(_f64(lo).reshape(-1), (m,)).copy()
+            hi = np.full(m, np.inf) if hi is None else np.broadcast_to(_f64(hi).reshape(-1), (m,)).copy()
+            self.input_bounds = (lo, hi)                       # kept alive: the struct holds raw pointers
+            prm.u_min, prm.u_max = lo.ctypes.data, hi.ctypes.data
         handle = C.c_void_p()
         with torch.cuda.device(self.device):
             stream = torch.cuda.current_stream().cuda_stream

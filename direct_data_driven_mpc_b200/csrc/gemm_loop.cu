@@ -192,7 +192,7 @@ int closed_loop_gemm_try(const ddmpc_set *set, const ddmpc_plant *plant, int B, 
                          const double *w, uint64_t seed, uint64_t id0, double eps, int n_steps, double *u_sys,
                          double *y_sys, int *status, int *iters, double *x_final, cudaStream_t st) {
     const Dims &d = set->plan.d;
-    if (ctrl_idx || set->plan.count != 1 || d.convex || !d.robust) return -1;
+    if (ctrl_idx || set->plan.count != 1 || d.nb > 0 || !d.robust) return -1;
     const char *force = getenv("DDMPC_FORCE_GENERIC");
     if (force && force[0] == '1') return -1;
     const int n = d.n, m = d.m, p = d.p, nxp = plant->n_x, nth = d.nth;

@@ -15,7 +15,8 @@ struct Dims {
     int nx;            // primal x = [ubar; ybar; sigma(robust)]
     int nfix, nf;      // fixed (initial/terminal) and free coordinates
     int nth;           // theta = [u_past; y_past; u_s; y_s]
-    int nb;            // box rows (CONVEX: sigma_pred = L*p), else 0
+    int nb;            // box rows = nbs + nbu
+    int nbs, nbu;      // CONVEX: sigma_pred rows (L*p) / input box: free predicted-input rows ((L-n)*m or L*m)
     int Lm;            // L*m = len(optimal_u)
     int robust, convex, terminal;
 };
@@ -36,10 +37,16 @@ struct Plan {
     DevBuf Lam;    // (nb, nb)       B A^-1 B^T                   (convex)
     DevBuf Yf;     // (nx, nb)       rho/2 * A^-1 B^T scattered   (convex; full primal)
     DevBuf rho2;   // (1)            rho/2
+    DevBuf rs;     // (nb)           row scale of the box rows (sigma rows 1, input rows sqrt(mean Lam_ss / mean Lam_uu))
+    DevBuf lo, hi; // (nb)           scaled bounds of the box rows
+    DevBuf bmax;   // (1)            largest finite |scaled bound| (residual tolerance scale)
+    DevBuf blo, bhi;   // (nb)       unscaled bounds, shared by the set
+    DevBuf umin, umax; // (m)        input box (device copy), empty when absent
     DevBuf F;      // (nfix, nth)    feasibility residual map     (nominal)
     DevBuf lamA, lamS;  // per-controller lamb_alpha*eps_max, lamb_sigma
     std::vector<int> pe_rank, status;
     double bound = 0.0;   // c * eps_max
+    std::vector<double> u_min, u_max;   // host copy of the input box (empty = none)
 };
 
 }  // namespace ddmpc

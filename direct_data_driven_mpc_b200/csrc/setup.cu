@@ -219,32 +219,65 @@ __global__ void k_fill_Bt(int nf, int nb, const int *__restrict__ bpos, double *
     Y[(long)blockIdx.y * bs + e] = (bpos[j] == a) ? 1.0 : 0.0;
 }
 
-// Lam = sym(B Y);  rho2 = nb / trace(Lam);  M = I + rho2 Lam.   One CTA per controller.
+// Row scales S, Lam = sym(S B Y S), rho2 = nb / trace(Lam), M = I + rho2 Lam and the scaled bounds.  One CTA per
+// controller.  The sigma rows (the first nbs) keep scale 1, so a CONVEX-only problem is untouched; the input rows
+// get sqrt(mean Lam_ss / mean Lam_uu): the two groups differ by five orders of magnitude in Lam (1e-3 vs 4e2 on
+// the four-tank data) and a single ADMM penalty only suits both after this equilibration (1 without sigma rows).
 __global__ void __launch_bounds__(256)
-k_lam_rho(int nf, int nb, const int *__restrict__ bpos, const double *__restrict__ Y, long bsY,
-          double *__restrict__ Lam, double *__restrict__ Mm, double *__restrict__ rho2) {
+k_lam_rho(int nf, int nb, int nbs, const int *__restrict__ bpos, const double *__restrict__ Y, long bsY,
+          const double *__restrict__ blo, const double *__restrict__ bhi, double *__restrict__ Lam,
+          double *__restrict__ Mm, double *__restrict__ rho2, double *__restrict__ rs, double *__restrict__ lo,
+          double *__restrict__ hi, double *__restrict__ bmax) {
     const int c = blockIdx.x, tid = threadIdx.x;
     Y += (long)c * bsY;
     Lam += (long)c * nb * nb;
     Mm += (long)c * nb * nb;
-    __shared__ double red[8];
-    __shared__ double s_rho;
-    double tr = 0.0;
-    for (int j = tid; j < nb; j += blockDim.x) tr += Y[(long)bpos[j] * nb + j];
-    for (int o = 16; o > 0; o >>= 1) tr += __shfl_xor_sync(0xffffffffu, tr, o);
-    if ((tid & 31) == 0) red[tid >> 5] = tr;
+    __shared__ double red[3][8];
+    __shared__ double s_rho, s_su;
+    double ts = 0.0, tu = 0.0, bm = 0.0;
+    for (int j = tid; j < nb; j += blockDim.x) {
+        const double dj = Y[(long)bpos[j] * nb + j];
+        if (j < nbs) ts += dj; else tu += dj;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        ts += __shfl_xor_sync(0xffffffffu, ts, o);
+        tu += __shfl_xor_sync(0xffffffffu, tu, o);
+    }
+    if ((tid & 31) == 0) { red[0][tid >> 5] = ts; red[1][tid >> 5] = tu; }
     __syncthreads();
     if (tid == 0) {
-        double s = 0.0;
-        for (int w = 0; w < (blockDim.x + 31) / 32; ++w) s += red[w];
-        s_rho = (s > 0.0) ? (double)nb / s : 1.0;
+        double a = 0.0, b = 0.0;
+        for (int w = 0; w < (blockDim.x + 31) / 32; ++w) { a += red[0][w]; b += red[1][w]; }
+        const int nbu = nb - nbs;
+        const double su = (nbs > 0 && nbu > 0 && a > 0.0 && b > 0.0) ? sqrt((a / nbs) / (b / nbu)) : 1.0;
+        const double tr = a + su * su * b;
+        s_su = su;
+        s_rho = (tr > 0.0) ? (double)nb / tr : 1.0;
         rho2[c] = s_rho;
     }
     __syncthreads();
-    const double rho = s_rho;
+    const double rho = s_rho, su = s_su;
+    for (int j = tid; j < nb; j += blockDim.x) {
+        const double r = j < nbs ? 1.0 : su;
+        const double l = r * blo[j], h = r * bhi[j];
+        rs[(long)c * nb + j] = r;
+        lo[(long)c * nb + j] = l;
+        hi[(long)c * nb + j] = h;
+        if (isfinite(l)) bm = fmax(bm, fabs(l));
+        if (isfinite(h)) bm = fmax(bm, fabs(h));
+    }
+    for (int o = 16; o > 0; o >>= 1) bm = fmax(bm, __shfl_xor_sync(0xffffffffu, bm, o));
+    if ((tid & 31) == 0) red[2][tid >> 5] = bm;
+    __syncthreads();
+    if (tid == 0) {
+        double m = 0.0;
+        for (int w = 0; w < (blockDim.x + 31) / 32; ++w) m = fmax(m, red[2][w]);
+        bmax[c] = m;
+    }
     for (int e = tid; e < nb * nb; e += blockDim.x) {
         const int i = e / nb, j = e % nb;
-        const double v = 0.5 * (Y[(long)bpos[i] * nb + j] + Y[(long)bpos[j] * nb + i]);
+        const double sc = (i < nbs ? 1.0 : su) * (j < nbs ? 1.0 : su);
+        const double v = sc * 0.5 * (Y[(long)bpos[i] * nb + j] + Y[(long)bpos[j] * nb + i]);
         Lam[e] = v;
         Mm[e] = rho * v + (i == j ? 1.0 : 0.0);
     }
@@ -254,7 +287,7 @@ k_lam_rho(int nf, int nb, const int *__restrict__ bpos, const double *__restrict
 __global__ void k_extract(FillArgs f, int nf, int nb, int Lm, const int *__restrict__ invperm,
                           const int *__restrict__ bpos, const double *__restrict__ X0f, long bsX0f,
                           const double *__restrict__ Cp, const double *__restrict__ Y, long bsY,
-                          const double *__restrict__ rho2,
+                          const double *__restrict__ rho2, const double *__restrict__ rs,
                           double *__restrict__ Ku, double *__restrict__ X0, double *__restrict__ Ks,
                           double *__restrict__ Psi, double *__restrict__ Yf) {
     const int c = blockIdx.y;
@@ -273,12 +306,12 @@ __global__ void k_extract(FillArgs f, int nf, int nb, int Lm, const int *__restr
         Y += (long)c * bsY;
         if (e < (long)nb * f.nth) {
             const int j = (int)(e / f.nth), t = (int)(e % f.nth);
-            Ks[(long)c * nb * f.nth + e] = X0f[(long)bpos[j] * f.nth + t];
+            Ks[(long)c * nb * f.nth + e] = rs[(long)c * nb + j] * X0f[(long)bpos[j] * f.nth + t];
         }
         if (e < (long)f.nx * nb) {
             const int i = (int)(e / nb), j = (int)(e % nb);
             const int a = invperm[i];
-            const double v = a < nf ? rho * Y[(long)a * nb + j] : 0.0;
+            const double v = a < nf ? rho * rs[(long)c * nb + j] * Y[(long)a * nb + j] : 0.0;
             Yf[(long)c * f.nx * nb + e] = v;
             if (i >= nm && i < f.nu) Psi[(long)c * Lm * nb + (long)(i - nm) * nb + j] = v;
         }
@@ -305,7 +338,9 @@ static Dims make_dims(const ddmpc_params &q) {
     d.nfix = q.n * (q.m + q.p) * (d.terminal ? 2 : 1);
     d.nf = d.nx - d.nfix;
     d.nth = q.n * (q.m + q.p) + q.m + q.p;
-    d.nb = d.convex ? q.L * q.p : 0;
+    d.nbs = d.convex ? q.L * q.p : 0;
+    d.nbu = (q.u_min || q.u_max) ? (d.terminal ? (q.L - q.n) * q.m : q.L * q.m) : 0;
+    d.nb = d.nbs + d.nbu;
     d.Lm = q.L * q.m;
     return d;
 }
@@ -323,6 +358,15 @@ static int validate(const ddmpc_params &q) {
         return fail(DDMPC_ERR_ROBUST_PARAMS,
                     "All robust MPC parameters (eps_max, lamb_alpha, lamb_sigma, c) must be provided for a "
                     "'ROBUST' controller.");
+    if (q.u_min || q.u_max) {
+        if (q.controller_type != DDMPC_ROBUST)
+            return fail(DDMPC_ERR_NOT_IMPLEMENTED, "The input box constraint is only implemented for 'ROBUST' controllers.");
+        for (int j = 0; j < q.m; ++j) {
+            const double l = q.u_min ? q.u_min[j] : -INFINITY, h = q.u_max ? q.u_max[j] : INFINITY;
+            if (std::isnan(l) || std::isnan(h) || l > h)
+                return fail(DDMPC_ERR_INVALID_ARG, "input box: u_min[%d] = %g must not exceed u_max[%d] = %g", j, l, j, h);
+        }
+    }
     return DDMPC_OK;
 }
 
@@ -411,7 +455,8 @@ static int build_robust(cudaStream_t st, Plan &pl, const FillArgs &fa, const int
         k_fill_Bt<<<g, 256, 0, st>>>(nf, nb, bpos_d, Y.d(), (long)nf * nb);
         DDMPC_LAUNCH_CHECK();
         DDMPC_TRY(potrs(st, C, nf, nb, P.d(), nx, sP, Y.d(), nb, (long)nf * nb));
-        k_lam_rho<<<C, 256, 0, st>>>(nf, nb, bpos_d, Y.d(), (long)nf * nb, pl.Lam.d(), Mm.d(), pl.rho2.d());
+        k_lam_rho<<<C, 256, 0, st>>>(nf, nb, d.nbs, bpos_d, Y.d(), (long)nf * nb, pl.blo.d(), pl.bhi.d(), pl.Lam.d(),
+                                     Mm.d(), pl.rho2.d(), pl.rs.d(), pl.lo.d(), pl.hi.d(), pl.bmax.d());
         DDMPC_LAUNCH_CHECK();
         DDMPC_TRY(potrf(st, C, nb, Mm.d(), nb, (long)nb * nb, info_d + 2 * C));
         DDMPC_TRY(set_identity(st, C, nb, pl.Phi.d(), nb, (long)nb * nb));
@@ -423,7 +468,7 @@ static int build_robust(cudaStream_t st, Plan &pl, const FillArgs &fa, const int
         if (nb > 0) tot = std::max(tot, (long)nx * nb);
         dim3 g(ceil_div(tot, 256), C);
         k_extract<<<g, 256, 0, st>>>(fa, nf, nb, d.Lm, invperm_d, bpos_d, X0f.d(), (long)nf * nth, Cp.d(),
-                                     nb > 0 ? Y.d() : nullptr, (long)nf * nb, pl.rho2.d(), pl.Ku.d(), pl.X0.d(),
+                                     nb > 0 ? Y.d() : nullptr, (long)nf * nb, pl.rho2.d(), pl.rs.d(), pl.Ku.d(), pl.X0.d(),
                                      pl.Ks.d(), pl.Psi.d(), pl.Yf.d());
         DDMPC_LAUNCH_CHECK();
     }
@@ -533,7 +578,7 @@ static int build_nominal(cudaStream_t st, Plan &pl, const FillArgs &fa, const in
     // extract: X0p holds every (permuted) row, so "nf" = nx here
     {
         dim3 g(ceil_div((long)r * nth, 256), C);
-        k_extract<<<g, 256, 0, st>>>(fa, r, 0, d.Lm, invperm_d, nullptr, X0p.d(), sT, Cp.d(), nullptr, 0, nullptr,
+        k_extract<<<g, 256, 0, st>>>(fa, r, 0, d.Lm, invperm_d, nullptr, X0p.d(), sT, Cp.d(), nullptr, 0, nullptr, nullptr,
                                      pl.Ku.d(), pl.X0.d(), nullptr, nullptr, nullptr);
         DDMPC_LAUNCH_CHECK();
     }
@@ -559,6 +604,7 @@ int set_create_device(const ddmpc_params *prm, int count, const double *u_d, siz
 
     std::unique_ptr<ddmpc_set> set(new ddmpc_set());
     set->prm = q;
+    set->prm.u_min = set->prm.u_max = nullptr;   // caller memory: the plan keeps its own copy
     Plan &pl = set->plan;
     pl.d = make_dims(q);
     pl.count = count;
@@ -614,7 +660,8 @@ int set_create_device(const ddmpc_params *prm, int count, const double *u_d, siz
         if (a != d.nf) return fail(DDMPC_ERR_INVALID_ARG, "internal: free count mismatch");
         for (int i = 0; i < d.nx; ++i) if (fixed[i]) perm[a++] = i;
         for (int k = 0; k < d.nx; ++k) invperm[perm[k]] = k;
-        for (int j = 0; j < d.nb; ++j) bpos[j] = invperm[d.nu + d.ny + q.n * q.p + j];
+        for (int j = 0; j < d.nbs; ++j) bpos[j] = invperm[d.nu + d.ny + q.n * q.p + j];   // sigma_pred
+        for (int j = 0; j < d.nbu; ++j) bpos[d.nbs + j] = invperm[q.n * q.m + j];          // free predicted inputs
     }
     DevBuf perm_d, invperm_d, bpos_d, info_d;
     DDMPC_CUDA(perm_d.alloc(sizeof(int) * d.nx));
@@ -656,6 +703,34 @@ int set_create_device(const ddmpc_params *prm, int count, const double *u_d, siz
         DDMPC_CUDA(pl.F.alloc(sizeof(double) * C * d.nfix * d.nth));
     }
     if (d.nb > 0) {
+        // box rows: sigma_pred in [-c eps_max, c eps_max] (controller.py:659-675), predicted inputs in [u_min, u_max]
+        std::vector<double> blo(d.nb), bhi(d.nb);
+        for (int j = 0; j < d.nbs; ++j) { blo[j] = -pl.bound; bhi[j] = pl.bound; }
+        for (int j = 0; j < d.nbu; ++j) {
+            blo[d.nbs + j] = q.u_min ? q.u_min[j % q.m] : -INFINITY;
+            bhi[d.nbs + j] = q.u_max ? q.u_max[j % q.m] : INFINITY;
+        }
+        DDMPC_CUDA(pl.blo.alloc(sizeof(double) * d.nb));
+        DDMPC_CUDA(pl.bhi.alloc(sizeof(double) * d.nb));
+        DDMPC_CUDA(cudaMemcpyAsync(pl.blo.p, blo.data(), sizeof(double) * d.nb, cudaMemcpyHostToDevice, st));
+        DDMPC_CUDA(cudaMemcpyAsync(pl.bhi.p, bhi.data(), sizeof(double) * d.nb, cudaMemcpyHostToDevice, st));
+        if (d.nbu > 0) {
+            pl.u_min.assign(q.m, -INFINITY);
+            pl.u_max.assign(q.m, INFINITY);
+            for (int j = 0; j < q.m; ++j) {
+                if (q.u_min) pl.u_min[j] = q.u_min[j];
+                if (q.u_max) pl.u_max[j] = q.u_max[j];
+            }
+            DDMPC_CUDA(pl.umin.alloc(sizeof(double) * q.m));
+            DDMPC_CUDA(pl.umax.alloc(sizeof(double) * q.m));
+            DDMPC_CUDA(cudaMemcpyAsync(pl.umin.p, pl.u_min.data(), sizeof(double) * q.m, cudaMemcpyHostToDevice, st));
+            DDMPC_CUDA(cudaMemcpyAsync(pl.umax.p, pl.u_max.data(), sizeof(double) * q.m, cudaMemcpyHostToDevice, st));
+        }
+        DDMPC_CUDA(cudaStreamSynchronize(st));   // blo / bhi are stack vectors
+        DDMPC_CUDA(pl.rs.alloc(sizeof(double) * C * d.nb));
+        DDMPC_CUDA(pl.lo.alloc(sizeof(double) * C * d.nb));
+        DDMPC_CUDA(pl.hi.alloc(sizeof(double) * C * d.nb));
+        DDMPC_CUDA(pl.bmax.alloc(sizeof(double) * C));
         DDMPC_CUDA(pl.Ks.alloc(sizeof(double) * C * d.nb * d.nth));
         DDMPC_CUDA(pl.Phi.alloc(sizeof(double) * C * d.nb * d.nb));
         DDMPC_CUDA(pl.Psi.alloc(sizeof(double) * C * d.Lm * d.nb));
@@ -809,6 +884,9 @@ int ddmpc_set_get(const ddmpc_set *set, const char *name, int index, double *out
     else if (nm == "Yf" && pl.Yf.p) { n = (size_t)d.nx * d.nb; src = pl.Yf.d() + index * n; }
     else if (nm == "F" && pl.F.p) { n = (size_t)d.nfix * d.nth; src = pl.F.d() + index * n; }
     else if (nm == "rho2") { n = 1; src = pl.rho2.d() + index; }
+    else if (nm == "row_scale" && pl.rs.p) { n = (size_t)d.nb; src = pl.rs.d() + index * n; }
+    else if (nm == "box_lo" && pl.lo.p) { n = (size_t)d.nb; src = pl.lo.d() + index * n; }
+    else if (nm == "box_hi" && pl.hi.p) { n = (size_t)d.nb; src = pl.hi.d() + index * n; }
     else return fail(DDMPC_ERR_INVALID_ARG, "set_get: unknown or unavailable matrix '%s'", name);
     if (n_elem) *n_elem = n;
     if (!out) return DDMPC_OK;

@@ -22,9 +22,26 @@ struct KArgs {
     int n, m, p, L, nth, nb, Lm, nx, nfix, r, cols, ny, nu;
     int convex, robust;
     const double *Ku, *Z, *Ks, *Phi, *Psi, *Lam, *rho2, *F, *X0, *Yf;
-    double bound, tol;
+    const double *lo, *hi, *bmax;    // per controller: scaled bounds of the box rows (nb), largest finite |bound|
+    const double *umin, *umax;       // input box (m) or NULL
+    int terminal;
+    double tol;
     int max_iter;
 };
+
+// Terminal equality + input box: the last n predicted inputs are fixed to u_s, so the QP is infeasible when u_s
+// itself violates the box (cvxpy would report "infeasible").
+__device__ __forceinline__ bool setpoint_outside_box(const KArgs &a, const double *th, int TS, int tid) {
+    if (!a.umin || !a.terminal) return false;
+    const int o = a.n * (a.m + a.p);
+    bool bad = false;
+    for (int j = 0; j < a.m; ++j) {
+        const double v = th[(size_t)(o + j) * TS + tid];
+        const double sl = 1e-9 * (1.0 + fabs(v));
+        bad = bad || v < a.umin[j] - sl || v > a.umax[j] + sl;
+    }
+    return bad;
+}
 
 #define SMV(arr, i) (arr)[(size_t)(i) * TS + tid]
 
@@ -34,14 +51,14 @@ struct KArgs {
 //      u = u0 - Psi t,  x = x0 - Yf t,  cost += rho2^2 t^T Lam t.
 // Iteration (DESIGN.md "ADMM on the condensed box rows"):
 //      d = s_unc - (z - w);  s = (z - w) + Phi d;  z+ = clip(s + w);  w+ = w + s - z+.
-__device__ __forceinline__ int admm_box(const KArgs &a, const double *__restrict__ Phi, double *s_unc, double *z,
+__device__ __forceinline__ int admm_box(const KArgs &a, const double *__restrict__ Phi, const double *__restrict__ lo,
+                                        const double *__restrict__ hi, double bscale, double *s_unc, double *z,
                                         double *w, double *d, double smax, int TS, int tid, int *status) {
     const int nb = a.nb;
-    const double b = a.bound;
-    const double thr = a.tol * fmax(b, smax);
+    const double thr = a.tol * fmax(bscale, smax);
     for (int j = 0; j < nb; ++j) {
         const double s = SMV(s_unc, j);
-        SMV(z, j) = fmin(fmax(s, -b), b);
+        SMV(z, j) = fmin(fmax(s, lo[j]), hi[j]);
         SMV(w, j) = 0.0;
     }
     int it = 0;
@@ -61,7 +78,7 @@ __device__ __forceinline__ int admm_box(const KArgs &a, const double *__restrict
             if (j < nb) acc0 = fma(row[j], SMV(d, j), acc0);
             const double zi = SMV(z, i), wi = SMV(w, i);
             const double si = (zi - wi) + (acc0 + acc1);
-            const double zn = fmin(fmax(si + wi, -b), b);
+            const double zn = fmin(fmax(si + wi, lo[i]), hi[i]);
             rp = fmax(rp, fabs(si - zn));
             rd = fmax(rd, fabs(zn - zi));
             SMV(w, i) = wi + si - zn;
@@ -137,17 +154,21 @@ __global__ void k_solve_batch(KArgs a, int B, const int *__restrict__ ctrl_idx, 
         for (int i = 0; i < a.nth; ++i) J = fma(SMV(th, i), dot_theta(Z + (size_t)i * a.nth, th, a.nth, TS, tid), J);
     }
     bool active = false;
-    if (a.convex) {
+    if (setpoint_outside_box(a, th, TS, tid)) status = max(status, (int)DDMPC_SOLVE_INFEASIBLE);
+    if (a.nb > 0) {
         const double *Ks = a.Ks + (size_t)c * a.nb * a.nth;
+        const double *lo = a.lo + (size_t)c * a.nb, *hi = a.hi + (size_t)c * a.nb;
         double smax = 0.0;
+        bool viol = false;
         for (int j = 0; j < a.nb; ++j) {
             const double s = dot_theta(Ks + (size_t)j * a.nth, th, a.nth, TS, tid);
             SMV(s_unc, j) = s;
             smax = fmax(smax, fabs(s));
+            viol = viol || s < lo[j] || s > hi[j];
         }
-        if (smax > a.bound && finite) {
+        if (viol && finite && status != DDMPC_SOLVE_INFEASIBLE) {
             active = true;
-            iters = admm_box(a, a.Phi + (size_t)c * a.nb * a.nb, s_unc, z, w, d, smax, TS, tid, &status);
+            iters = admm_box(a, a.Phi + (size_t)c * a.nb * a.nb, lo, hi, a.bmax[c], s_unc, z, w, d, smax, TS, tid, &status);
             const double *Psi = a.Psi + (size_t)c * a.Lm * a.nb;
             for (int k = 0; k < a.Lm; ++k) {
                 double acc = 0.0;
@@ -250,21 +271,25 @@ k_solve_small(KArgs a, int B, const int *__restrict__ ctrl_idx, const double *__
         J = block_sum(part, red);
     }
     bool active = false;
-    if (a.convex) {
+    if (setpoint_outside_box(a, th, 1, 0)) status = max(status, (int)DDMPC_SOLVE_INFEASIBLE);
+    if (a.nb > 0) {
         const double *Ks = a.Ks + (size_t)c * a.nb * a.nth;
-        double sm_l = 0.0;
+        const double *lo = a.lo + (size_t)c * a.nb, *hi = a.hi + (size_t)c * a.nb;
+        double sm_l = 0.0, vi_l = 0.0;
         for (int j = tid; j < a.nb; j += T) {
             const double s = dot_row(Ks + (size_t)j * a.nth, th, a.nth);
             su[j] = s;
             sm_l = fmax(sm_l, fabs(s));
+            if (s < lo[j] || s > hi[j]) vi_l = 1.0;
         }
         const double smax = block_max(sm_l, red);
-        if (smax > a.bound && finite) {
+        const bool viol = block_max(vi_l, red) != 0.0;
+        if (viol && finite && status != DDMPC_SOLVE_INFEASIBLE) {
             active = true;
             const double *Phi = a.Phi + (size_t)c * a.nb * a.nb;
-            const double bnd = a.bound, thr = a.tol * fmax(bnd, smax);
+            const double thr = a.tol * fmax(a.bmax[c], smax);
             for (int j = tid; j < a.nb; j += T) {
-                z[j] = fmin(fmax(su[j], -bnd), bnd);
+                z[j] = fmin(fmax(su[j], lo[j]), hi[j]);
                 w[j] = 0.0;
             }
             int it = 0;
@@ -278,7 +303,7 @@ k_solve_small(KArgs a, int B, const int *__restrict__ ctrl_idx, const double *__
                 for (int j = tid; j < a.nb; j += T) {
                     const double acc = dot_row(Phi + (size_t)j * a.nb, dd, a.nb);
                     const double si = (z[j] - w[j]) + acc;
-                    const double zn = fmin(fmax(si + w[j], -bnd), bnd);
+                    const double zn = fmin(fmax(si + w[j], lo[j]), hi[j]);
                     res = fmax(res, fmax(fabs(si - zn), fabs(zn - z[j])));
                     w[j] = w[j] + si - zn;
                     z[j] = zn;
@@ -430,9 +455,11 @@ __global__ void k_closed_loop(KArgs a, LoopArgs la, int B, const int *__restrict
            *d = w + (size_t)a.nb * TS;
     const int c = ctrl_idx ? ctrl_idx[b] : 0;
     const double *Ku = a.Ku + (size_t)c * a.Lm * a.nth;
-    const double *Ks = a.convex ? a.Ks + (size_t)c * a.nb * a.nth : nullptr;
-    const double *Phi = a.convex ? a.Phi + (size_t)c * a.nb * a.nb : nullptr;
-    const double *Psi = a.convex ? a.Psi + (size_t)c * a.Lm * a.nb : nullptr;
+    const bool boxed = a.nb > 0;
+    const double *Ks = boxed ? a.Ks + (size_t)c * a.nb * a.nth : nullptr;
+    const double *Phi = boxed ? a.Phi + (size_t)c * a.nb * a.nb : nullptr;
+    const double *Psi = boxed ? a.Psi + (size_t)c * a.Lm * a.nb : nullptr;
+    const double *lo = boxed ? a.lo + (size_t)c * a.nb : nullptr, *hi = boxed ? a.hi + (size_t)c * a.nb : nullptr;
     const double *F = a.F ? a.F + (size_t)c * a.nfix * a.nth : nullptr;
 
     for (int i = 0; i < nm; ++i) SMV(th, i) = u_past0[(size_t)b * nm + i];
@@ -442,6 +469,7 @@ __global__ void k_closed_loop(KArgs a, LoopArgs la, int B, const int *__restrict
     for (int i = 0; i < nxp; ++i) SMV(xs, i) = x0[(size_t)b * nxp + i];
 
     int status = DDMPC_SOLVE_OPTIMAL, iters = 0;
+    if (setpoint_outside_box(a, th, TS, tid)) status = DDMPC_SOLVE_INFEASIBLE;
     const uint64_t sid = la.id0 + (uint64_t)b;
     for (int t = 0; t < la.n_steps; t += la.n_mpc) {
         // ---- solve: planned inputs = first n_mpc*m rows of Ku theta (+ box correction)
@@ -453,15 +481,17 @@ __global__ void k_closed_loop(KArgs a, LoopArgs la, int B, const int *__restrict
         }
         for (int k = 0; k < nplan; ++k) SMV(up, k) = dot_theta(Ku + (size_t)k * a.nth, th, a.nth, TS, tid);
         int it = 1;
-        if (a.convex) {
+        if (boxed) {
             double smax = 0.0;
+            bool viol = false;
             for (int j = 0; j < a.nb; ++j) {
                 const double s = dot_theta(Ks + (size_t)j * a.nth, th, a.nth, TS, tid);
                 SMV(s_unc, j) = s;
                 smax = fmax(smax, fabs(s));
+                viol = viol || s < lo[j] || s > hi[j];
             }
-            if (smax > a.bound && isfinite(smax)) {
-                it = admm_box(a, Phi, s_unc, z, w, d, smax, TS, tid, &status);
+            if (viol && isfinite(smax)) {
+                it = admm_box(a, Phi, lo, hi, a.bmax[c], s_unc, z, w, d, smax, TS, tid, &status);
                 for (int k = 0; k < nplan; ++k) {
                     double acc = 0.0;
                     for (int j = 0; j < a.nb; ++j) acc = fma(Psi[(size_t)k * a.nb + j], SMV(s_unc, j), acc);
@@ -555,7 +585,9 @@ static KArgs make_kargs(const ddmpc_set *set, double tol, int max_iter) {
     a.Ks = pl.Ks.d(); a.Phi = pl.Phi.d(); a.Psi = pl.Psi.d(); a.Lam = pl.Lam.d(); a.Yf = pl.Yf.d();
     a.rho2 = pl.rho2.d();
     a.F = d.robust ? nullptr : pl.F.d();
-    a.bound = pl.bound;
+    a.lo = pl.lo.d(); a.hi = pl.hi.d(); a.bmax = pl.bmax.d();
+    a.umin = d.nbu > 0 ? pl.umin.d() : nullptr; a.umax = d.nbu > 0 ? pl.umax.d() : nullptr;
+    a.terminal = d.terminal;
     a.tol = tol > 0.0 ? tol : 1e-8;
     a.max_iter = max_iter > 0 ? max_iter : 1000;
     return a;

@@ -70,6 +70,11 @@ typedef struct {
     int32_t n_mpc_step;       /* n-step scheme: inputs applied per solve         */
     int32_t check_pe;         /* 1: run the persistency-of-excitation rank test  */
     double eps_max, lamb_alpha, lamb_sigma, c;
+    /* Optional input box u_min <= ubar[k] <= u_max on every predicted input (paper Eq. 6, u in U; the
+     * reference has no such constraint: controller.py:447-504).  HOST pointers to m values each, copied at
+     * creation; NULL / NULL (the default) leaves the problem exactly as the reference states it.  Entries may
+     * be -inf / +inf.  ROBUST controllers only (DDMPC_ERR_NOT_IMPLEMENTED for NOMINAL). */
+    const double *u_min, *u_max;
 } ddmpc_params;
 
 /* LTI plant of utilities/model_simulation.py:31-98, row-major host arrays. */

@@ -206,7 +206,10 @@ class OracleQP:
 
     def __init__(self, n, m, p, u_d, y_d, L, Q, R, eps_max=None, lamb_alpha=None,
                  lamb_sigma=None, c=None, slack_type=SLACK_CONVEX, ctrl_type=NOMINAL,
-                 use_terminal=True, cache_factor=True):
+                 use_terminal=True, cache_factor=True, input_bounds=None):
+        """input_bounds = (u_min, u_max): optional box on every predicted input ubar[n*m:] (paper Eq. 6, u in U).
+        NOT in the reference (its constraint list, controller.py:447-504, has no such entry): an extension that
+        only the oracle pins, off by default."""
         if slack_type == SLACK_NON_CONVEX and ctrl_type == ROBUST:
             raise NotImplementedError("NON_CONVEX slack constraint (controller.py:664-670)")
         self.n, self.m, self.p, self.L = n, m, p, L
@@ -227,6 +230,24 @@ class OracleQP:
         self.o_a, self.o_u, self.o_y, self.o_s = 0, c_, c_ + nu, c_ + nu + ny
         self.nz = c_ + nu + ny + (ny if self.robust else 0)
         self.bound = (c * eps_max) if self.convex else None
+        # inequality rows lo <= z[idx] <= hi: sigma[n*p:] (:659-675) and, if given, the free predicted inputs
+        idx, lo, hi = [], [], []
+        if self.convex:
+            for j in range(L * p):
+                idx.append(self.o_s + n * p + j); lo.append(-self.bound); hi.append(self.bound)
+        self.u_box = None
+        if input_bounds is not None:
+            if not self.robust:
+                raise NotImplementedError("input box: ROBUST controllers only")
+            bl, bh = input_bounds
+            bl = np.full(m, -np.inf) if bl is None else np.broadcast_to(np.asarray(bl, float).reshape(-1), (m,))
+            bh = np.full(m, np.inf) if bh is None else np.broadcast_to(np.asarray(bh, float).reshape(-1), (m,))
+            if np.any(bl > bh):
+                raise ValueError("input box: u_min must not exceed u_max")
+            self.u_box = (bl, bh)
+            for i in range((L - n) * m if use_terminal else L * m):     # terminal blocks are equalities
+                idx.append(self.o_u + n * m + i); lo.append(bl[i % m]); hi.append(bh[i % m])
+        self.ineq_idx, self.ineq_lo, self.ineq_hi = np.array(idx, int), np.array(lo, float), np.array(hi, float)
         self._cache_factor = cache_factor
         self._lu = None
         if self.robust:
@@ -305,32 +326,38 @@ class OracleQP:
         zt0 = self._kkt_solve(rhs)
         n_act = 0
         zt = zt0
-        if self.convex:
-            nb = self.L * self.p
-            o_sp = self.o_s + self.n * self.p             # sigma[n*p:]  (:659)
-            active: Dict[int, int] = {}
+        if self.u_box is not None and self.use_terminal:
+            us = np.reshape(u_s, (-1,))
+            if np.any(us < self.u_box[0] - 1e-9 * (1 + np.abs(us))) or np.any(us > self.u_box[1] + 1e-9 * (1 + np.abs(us))):
+                return QPSolution(status="infeasible")             # terminal equality ubar = u_s violates the box
+        if self.ineq_idx.size:
+            zi, lo, hi = self.ineq_idx, self.ineq_lo, self.ineq_hi
+            nb = zi.size
+            fin = np.concatenate([np.abs(lo[np.isfinite(lo)]), np.abs(hi[np.isfinite(hi)]), [0.0]])
+            vtol = 1e-13 * np.maximum(1.0, np.maximum(np.where(np.isfinite(lo), np.abs(lo), 0), np.where(np.isfinite(hi), np.abs(hi), 0)))
+            active: Dict[int, int] = {}                            # row -> +1 (upper bound) / -1 (lower bound)
             vcache: Dict[int, np.ndarray] = {}
             for _ in range(20 * nb + 20):
                 if active:
                     idx = sorted(active)
                     for j in idx:
                         if j not in vcache:
-                            e = np.zeros(self.K.shape[0]); e[o_sp + j] = 1.0
+                            e = np.zeros(self.K.shape[0]); e[zi[j]] = 1.0
                             vcache[j] = self._kkt_solve(e)
                     V = np.stack([vcache[j] for j in idx], axis=1)
-                    d = np.array([active[j] * self.bound for j in idx])
-                    S = V[[o_sp + j for j in idx], :]
-                    mu = np.linalg.solve(S, zt0[[o_sp + j for j in idx]] - d)
+                    d = np.array([hi[j] if active[j] > 0 else lo[j] for j in idx])
+                    S = V[zi[idx], :]
+                    mu = np.linalg.solve(S, zt0[zi[idx]] - d)
                     zt = zt0 - V @ mu
                 else:
                     idx, mu, zt = [], np.zeros(0), zt0
-                sp = zt[o_sp:o_sp + nb]
-                viol = np.abs(sp) - self.bound
+                vals = zt[zi]
+                viol = np.maximum(vals - hi, lo - vals) - vtol
                 for j in idx:
                     viol[j] = -np.inf
                 jmax = int(np.argmax(viol))
-                if viol[jmax] > 1e-13:
-                    active[jmax] = 1 if sp[jmax] > 0 else -1
+                if viol[jmax] > 0.0:
+                    active[jmax] = 1 if vals[jmax] > hi[jmax] else -1
                     continue
                 bad = [(active[j] * mu[k], j) for k, j in enumerate(idx) if active[j] * mu[k] < -1e-12]
                 if bad:
@@ -420,7 +447,7 @@ class OracleQP:
 class OracleController:
     def __init__(self, n, m, p, u_d, y_d, L, Q, R, u_s, y_s, eps_max=None, lamb_alpha=None,
                  lamb_sigma=None, c=None, slack_type=SLACK_CONVEX, ctrl_type=NOMINAL,
-                 n_mpc_step=1, use_terminal=True, cache_factor=True, check_pe=True):
+                 n_mpc_step=1, use_terminal=True, cache_factor=True, check_pe=True, input_bounds=None):
         self.n, self.m, self.p, self.L = n, m, p, L
         self.u_s, self.y_s, self.n_mpc_step = u_s, y_s, n_mpc_step
         N = u_d.shape[0]
@@ -432,7 +459,7 @@ class OracleController:
             if not ok:
                 raise ValueError("not persistently exciting")
         self.qp = OracleQP(n, m, p, u_d, y_d, L, Q, R, eps_max, lamb_alpha, lamb_sigma, c,
-                           slack_type, ctrl_type, use_terminal, cache_factor)
+                           slack_type, ctrl_type, use_terminal, cache_factor, input_bounds)
         self.u_past = u_d[-n:, :].reshape(-1, 1)          # controller.py:184
         self.y_past = y_d[-n:, :].reshape(-1, 1)          # controller.py:185
         self.solution: Optional[QPSolution] = None
@@ -488,7 +515,8 @@ def make_controller(params: Dict, u_d, y_d, **over) -> OracleController:
         n=kw["n"], m=m, p=p, u_d=u_d, y_d=y_d, L=kw["L"], Q=kw["Q"], R=kw["R"], u_s=kw["u_s"],
         y_s=kw["y_s"], eps_max=kw["eps_max"], lamb_alpha=kw["lamb_alpha"], lamb_sigma=kw["lamb_sigma"],
         c=kw["c"], slack_type=kw["slack_type"], ctrl_type=kw["ctrl_type"], n_mpc_step=kw["n_mpc_step"],
-        use_terminal=kw.get("use_terminal", True), cache_factor=kw.get("cache_factor", True))
+        use_terminal=kw.get("use_terminal", True), cache_factor=kw.get("cache_factor", True),
+        input_bounds=kw.get("input_bounds"))
 
 
 def example_scenario(seed: int, params: Optional[Dict] = None, plant: Optional[Plant] = None):

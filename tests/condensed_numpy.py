@@ -33,7 +33,7 @@ def theta_layout(n, m, p):
 
 
 def build_plan(n, m, p, u_d, y_d, L, Q, R, eps_max, lamb_alpha, lamb_sigma, c, slack_type,
-               ctrl_type, use_terminal, rank_tol=1e-11):
+               ctrl_type, use_terminal, rank_tol=1e-11, input_bounds=None):
     Lp = L + n
     nu, ny = Lp * m, Lp * p
     H = np.vstack([hankel(u_d, Lp), hankel(y_d, Lp)])
@@ -107,23 +107,45 @@ def build_plan(n, m, p, u_d, y_d, L, Q, R, eps_max, lamb_alpha, lamb_sigma, c, s
         pl.Z = X0.T @ P @ X0 - X0.T @ (D @ Tile) - (D @ Tile).T @ X0 + Tile.T @ D @ Tile
         pl.Z = 0.5 * (pl.Z + pl.Z.T)
         pl.feasF = None
-        if pl.convex:
-            nb = L * p
+        pl.nb = 0
+        if pl.convex or input_bounds is not None:
+            # box rows: sigma_pred (CONVEX) then the free predicted inputs (input box), as in setup.cu
             pos = {g: i for i, g in enumerate(free)}
-            bidx = np.array([pos[nu + ny + n * p + j] for j in range(nb)])
+            rows, lo, hi = [], [], []
+            if pl.convex:
+                rows += [nu + ny + n * p + j for j in range(L * p)]
+                lo += [-c * eps_max] * (L * p)
+                hi += [c * eps_max] * (L * p)
+            nbs = len(rows)
+            if input_bounds is not None:
+                bl = np.broadcast_to(np.asarray(-np.inf if input_bounds[0] is None else input_bounds[0], float).reshape(-1), (m,))
+                bh = np.broadcast_to(np.asarray(np.inf if input_bounds[1] is None else input_bounds[1], float).reshape(-1), (m,))
+                for j in range((L - n) * m if use_terminal else L * m):
+                    rows.append(n * m + j); lo.append(bl[j % m]); hi.append(bh[j % m])
+            nb = len(rows)
+            bidx = np.array([pos[g] for g in rows])
             Bsel = np.zeros((nb, len(free)))
             Bsel[np.arange(nb), bidx] = 1.0
             Y = sla.cho_solve((La, True), Bsel.T)       # A^-1 B^T
             Lam = Bsel @ Y
-            Lam = 0.5 * (Lam + Lam.T)
+            dg = np.diag(Lam)
+            rs = np.ones(nb)
+            if 0 < nbs < nb:
+                rs[nbs:] = np.sqrt(dg[:nbs].mean() / dg[nbs:].mean())
+            Y = Y * rs[None, :]
+            Lam = rs[:, None] * (0.5 * (Lam + Lam.T)) * rs[None, :]
             rho2 = nb / np.trace(Lam)                   # rho/2
             Phi = np.linalg.inv(np.eye(nb) + rho2 * Lam)
             Yfull = np.zeros((nx, nb))
             Yfull[free] = Y
-            pl.Ks = X0[nu + ny + n * p:, :]             # s_unc = Ks theta
+            pl.Ks = rs[:, None] * X0[rows, :]           # s_unc = Ks theta (scaled rows)
             pl.Phi, pl.Lam, pl.rho2 = 0.5 * (Phi + Phi.T), Lam, rho2
             pl.Psi = rho2 * Yfull[n * m:nu, :]          # u = u0 + Psi (v - s)
-            pl.bound = c * eps_max
+            pl.bound = c * eps_max if pl.convex else 0.0
+            pl.nb, pl.nbs, pl.rs = nb, nbs, rs
+            pl.lo, pl.hi = rs * np.array(lo), rs * np.array(hi)
+            fin = np.concatenate([np.abs(pl.lo[np.isfinite(pl.lo)]), np.abs(pl.hi[np.isfinite(pl.hi)]), [0.0]])
+            pl.bmax = float(fin.max())
     else:
         # nominal: t = [ubar; ybar] in range(H)
         lam, V = np.linalg.eigh(W)
@@ -165,26 +187,27 @@ def solve(pl: Plan, theta, tol=1e-9, max_iter=500, relax=1.0):
         fe = np.abs(pl.feasF @ theta).max()
         if fe > 1e-6 * (1.0 + np.abs(theta).max()):
             return u, cost, "infeasible", 1
-    if not pl.convex:
+    if not getattr(pl, "nb", 0):
         return u, cost, "optimal", 1
     s_unc = pl.Ks @ theta
-    b = pl.bound
-    if np.abs(s_unc).max() <= b:
+    lo, hi = pl.lo, pl.hi
+    if not np.any((s_unc < lo) | (s_unc > hi)):
         return u, cost, "optimal", 1
-    z = np.clip(s_unc, -b, b)
+    z = np.clip(s_unc, lo, hi)
     w = np.zeros_like(z)
     status = "optimal_inaccurate"
     it = 0
+    thr = tol * max(pl.bmax, np.abs(s_unc).max())
     for it in range(1, max_iter + 1):
         v = z - w
         s = v + pl.Phi @ (s_unc - v)
         sr = relax * s + (1 - relax) * z
-        z_new = np.clip(sr + w, -b, b)
+        z_new = np.clip(sr + w, lo, hi)
         w = w + sr - z_new
         r_pri = np.abs(s - z_new).max()
         r_dua = np.abs(z_new - z).max()
         z = z_new
-        if max(r_pri, r_dua) <= tol * max(b, 1e-300):
+        if max(r_pri, r_dua) <= thr:
             status = "optimal"
             break
     v = z - w

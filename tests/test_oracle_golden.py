@@ -150,6 +150,48 @@ def test_condensed_formulation_equals_literal_kkt(slack, term, c):
         assert abs(cost - so.cost) <= 1e-8 * max(1.0, abs(so.cost))
 
 
+@pytest.mark.parametrize("slack,term,box", [(O.SLACK_NONE, True, (-3.0, [5.0, 4.0])), (O.SLACK_CONVEX, True, (-3.0, 5.0)),
+                                            (O.SLACK_NONE, False, (None, 6.0)), (O.SLACK_CONVEX, False, ([-1.0, -2.0], None))])
+def test_input_box_condensed_admm_equals_oracle_active_set(slack, term, box):
+    """Input box (paper Eq. 6; an extension, absent from the reference): the condensed box-row ADMM with group row
+    scaling that the CUDA path implements == the oracle's active set on the literal KKT system."""
+    plant, params, rng, x0, u_d, y_d = O.example_scenario(1)
+    prm = O.four_tank_params()
+    qp = O.OracleQP(4, 2, 2, u_d, y_d, 30, prm["Q"], prm["R"], prm["eps_max"], prm["lamb_alpha"], prm["lamb_sigma"],
+                    1.0, slack, O.ROBUST, term, input_bounds=box)
+    pl = CN.build_plan(4, 2, 2, u_d, y_d, 30, params["Q"], params["R"], params["eps_max"], params["lamb_alpha"],
+                       params["lamb_sigma"], 1.0, slack, CN.ROBUST, term, input_bounds=box)
+    r = np.random.default_rng(3)
+    n_bind = 0
+    for _ in range(3):
+        k = int(r.integers(0, 396))
+        up, yp = u_d[k:k + 4].reshape(-1, 1), y_d[k:k + 4].reshape(-1, 1)
+        us, ys = params["u_s"] * r.uniform(0.8, 1.2), params["y_s"] * r.uniform(0.8, 1.2)
+        so = qp.solve(up, yp, us, ys)
+        u, cost, st, it = CN.solve(pl, CN.make_theta(4, 2, 2, up, yp, us, ys), tol=1e-10, max_iter=20000)
+        assert st == "optimal" and so.status == "optimal"
+        n_bind += so.n_active
+        lo = -np.inf if box[0] is None else np.tile(np.broadcast_to(np.asarray(box[0], float).reshape(-1), (2,)), 30)
+        hi = np.inf if box[1] is None else np.tile(np.broadcast_to(np.asarray(box[1], float).reshape(-1), (2,)), 30)
+        nfree = (26 if term else 30) * 2
+        assert np.all(so.optimal_u[:nfree] >= (lo if np.isscalar(lo) else lo[:nfree]) - 1e-9)
+        assert np.all(so.optimal_u[:nfree] <= (hi if np.isscalar(hi) else hi[:nfree]) + 1e-9)
+        assert np.abs(u - so.optimal_u).max() <= 1e-7 * max(1.0, np.abs(so.optimal_u).max())
+        assert abs(cost - so.cost) <= 1e-7 * max(1.0, abs(so.cost))
+    assert n_bind > 0                                   # the box really binds in these cases
+
+
+def test_input_box_infeasible_setpoint_and_nominal():
+    plant, params, rng, x0, u_d, y_d = O.example_scenario(0)
+    prm = O.four_tank_params()
+    qp = O.OracleQP(4, 2, 2, u_d, y_d, 30, prm["Q"], prm["R"], prm["eps_max"], prm["lamb_alpha"], prm["lamb_sigma"],
+                    1.0, O.SLACK_NONE, O.ROBUST, True, input_bounds=(-0.5, 0.5))
+    sol = qp.solve(u_d[-4:].reshape(-1, 1), y_d[-4:].reshape(-1, 1), prm["u_s"], prm["y_s"])    # u_s = 1 > 0.5
+    assert sol.status == "infeasible"
+    with pytest.raises(NotImplementedError):
+        O.OracleQP(4, 2, 2, u_d, y_d, 30, prm["Q"], prm["R"], ctrl_type=O.NOMINAL, input_bounds=(-1, 1))
+
+
 def test_nominal_noise_free_and_noisy():
     prm = O.four_tank_params()
     plant = O.four_tank_plant()
