@@ -7,7 +7,7 @@ import subprocess
 import sys
 
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
-SOURCES = ["setup.cu", "solve.cu", "fast_loop.cu", "gemm_loop.cu", "scenario_gen.cu"]
+SOURCES = ["setup.cu", "solve.cu", "fast_loop.cu", "gemm_loop.cu", "dmma_loop.cu", "scenario_gen.cu"]
 HEADERS = ["common.cuh", "linalg.cuh", "plan.cuh", os.path.join("..", "..", "include", "ddmpc.h")]
 LIB = os.path.join(CSRC, "libddmpc.so")
 

@@ -137,7 +137,7 @@ __global__ void k_gl_final(int B, int nxp, int iters_val, const double *__restri
 }
 
 // s-step block map of the plant, row-major ((s*p + n_x) x (n_x + s*m)), built on the host
-static std::vector<double> block_map(const ddmpc_plant *pl, int s) {
+std::vector<double> block_map(const ddmpc_plant *pl, int s) {
     const int nx = pl->n_x, m = pl->m, p = pl->p;
     const int rows = s * p + nx, cols = nx + s * m;
     std::vector<double> M((size_t)rows * cols, 0.0);

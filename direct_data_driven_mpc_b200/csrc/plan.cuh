@@ -64,6 +64,9 @@ struct ddmpc_set {
     // gemm_loop.cu: workspace (block maps of the plant + value-major loop state) and its host key
     mutable ddmpc::DevBuf gemm_ws;
     mutable std::vector<double> gemm_host;
+    // dmma_loop.cu: packed A fragments (gain rows + block maps of the plant) and their host key
+    mutable ddmpc::DevBuf dmma_ws;
+    mutable std::vector<double> dmma_key;
     // solve.cu: staging of the B = 1 host path (pinned host, device, private stream)
     mutable void *stage_host = nullptr;
     mutable ddmpc::DevBuf stage_dev;

@@ -574,6 +574,11 @@ int closed_loop_gemm_try(const ddmpc_set *set, const ddmpc_plant *plant, int B, 
                          const double *w, uint64_t seed, uint64_t id0, double eps, int n_steps, double *u_sys,
                          double *y_sys, int *status, int *iters, double *x_final, cudaStream_t st);
 
+int closed_loop_dmma_try(const ddmpc_set *set, const ddmpc_plant *plant, int B, const int *ctrl_idx, const double *x0,
+                         const double *u_past0, const double *y_past0, const double *u_s, const double *y_s,
+                         const double *w, uint64_t seed, uint64_t id0, double eps, int n_steps, double *u_sys,
+                         double *y_sys, int *status, int *iters, double *x_final, cudaStream_t st);
+
 static KArgs make_kargs(const ddmpc_set *set, double tol, int max_iter) {
     const Plan &pl = set->plan;
     const Dims &d = pl.d;
@@ -788,6 +793,11 @@ int ddmpc_closed_loop_batch(const ddmpc_set *set, const ddmpc_plant *plant, int 
         const int rc = closed_loop_fast_try(set, plant, B, ctrl_idx, x0, u_past0, y_past0, u_s, y_s, w, noise_seed,
                                             scenario_id0, noise_eps, n_steps, u_sys, y_sys, status, iters, x_final, tol,
                                             max_iter, st);
+        if (rc != -1) return rc;
+    }
+    {   // large systems, compiled shapes: one fused launch, a warp per 8 loops, both products on the FP64 tensor cores
+        const int rc = closed_loop_dmma_try(set, plant, B, ctrl_idx, x0, u_past0, y_past0, u_s, y_s, w, noise_seed,
+                                            scenario_id0, noise_eps, n_steps, u_sys, y_sys, status, iters, x_final, st);
         if (rc != -1) return rc;
     }
     {   // large systems: the batch as the N dimension of FP64 tensor-core GEMMs

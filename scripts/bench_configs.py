@@ -55,9 +55,11 @@ if "4" in which:
         cs = ControllerSet(prm["n"], 4, 4, sc["u_d"], sc["y_d"], prm["L"], prm["Q"], prm["R"], prm["eps_max"], prm["lamb_alpha"],
                            prm["lamb_sigma"], prm["c"], 0, 1, nmpc, True)
         torch.cuda.synchronize(); t_setup = time.perf_counter() - t
-        args = (pl, sc["x0"], sc["u_past0"], sc["y_past0"], sc["u_s"], sc["y_s"], 401)
-        kw = dict(noise_seed=0, noise_eps=0.002)
-        dt = timed(lambda: cs.closed_loop(*args, **kw), n=2)
+        tdev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+        args = (pl, tdev(sc["x0"]), tdev(sc["u_past0"]), tdev(sc["y_past0"]), tdev(sc["u_s"]), tdev(sc["y_s"]), 401)
+        out = (torch.empty(B, 401, 4, dtype=torch.float64, device=dev), torch.empty(B, 401, 4, dtype=torch.float64, device=dev))
+        kw = dict(noise_seed=0, noise_eps=0.002, out=out)
+        dt = timed(lambda: cs.closed_loop(*args, **kw), n=5)
         u, y, st, it = cs.closed_loop(*args, **kw)
         err = float((y[:, -1] - torch.from_numpy(sc["y_s"]).to(dev)).abs().max())
         print(json.dumps({"config": 4, "n_mpc_step": nmpc, "loops": B, "pe_rank_status": cs.info(0), "setup_s": t_setup,

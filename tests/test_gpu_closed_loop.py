@@ -23,6 +23,11 @@ def _set(u_d, y_d, slack=0, term=True, n_mpc=4, c=1.0):
                          prm["lamb_sigma"], c, slack, 1, n_mpc, term), prm
 
 
+def _launches():
+    from direct_data_driven_mpc_b200 import _lib
+    return _lib.kernel_launches()
+
+
 def _rel(a, b):
     return np.abs(a - b).max() / max(1.0, np.abs(b).max())
 
@@ -280,6 +285,47 @@ def test_config4_gemm_path_vs_generic_and_oracle(n_mpc, n_steps, monkeypatch):
         qp.set_past_input_output_data(sc["u_past0"][b].reshape(-1, 1), sc["y_past0"][b].reshape(-1, 1))
         u_ref, y_ref = O.closed_loop(plant_o, qp, n_steps, w[b])
         assert _rel(u1[b], u_ref) < 1e-5 and _rel(y1[b], y_ref) < 1e-5
+
+
+@pytest.mark.parametrize("n_mpc,n_steps,B", [(1, 23, 515), (20, 47, 515), (20, 401, 264)])
+def test_config4_fused_dmma_kernel_vs_generic_and_oracle(n_mpc, n_steps, B, monkeypatch):
+    """k_closed_loop_dmma (one launch, a warp per 8 loops, ring window in shared memory) vs the generic
+    thread-per-loop kernel on a ragged batch, and vs the oracle on a sample; Philox and uploaded noise."""
+    from direct_data_driven_mpc_b200 import ControllerSet, scenarios as S
+    sc = S.config4_batch(B, n_mpc_step=n_mpc)
+    prm, pl = sc["params"], sc["plant"]
+    cs = ControllerSet(prm["n"], 4, 4, sc["u_d"], sc["y_d"], prm["L"], prm["Q"], prm["R"], prm["eps_max"],
+                       prm["lamb_alpha"], prm["lamb_sigma"], prm["c"], 0, 1, n_mpc, True)
+    r = np.random.default_rng(1)
+    x0 = sc["x0"] + 0.1 * r.normal(size=sc["x0"].shape)
+    u_s = sc["u_s"] * r.uniform(0.8, 1.2, (B, 1))
+    y_s = u_s @ pl.equilibrium_gain().T
+    w = pl.eps_max * r.uniform(-1, 1, (B, n_steps, 4))
+    for noise in ("philox", "uploaded"):
+        kw = dict(w=w) if noise == "uploaded" else dict(noise_seed=5, scenario_id0=1000, noise_eps=0.002)
+        launches0 = _launches()
+        u1, y1, s1, i1, xf1 = cs.closed_loop(pl, x0, sc["u_past0"], sc["y_past0"], u_s, y_s, n_steps,
+                                             want_x_final=True, **kw)
+        assert _launches() - launches0 == 1                        # the fused kernel, not the per-iteration GEMMs
+        monkeypatch.setenv("DDMPC_FORCE_GENERIC", "1")
+        u2, y2, s2, i2, xf2 = cs.closed_loop(pl, x0, sc["u_past0"], sc["y_past0"], u_s, y_s, n_steps,
+                                             want_x_final=True, **kw)
+        monkeypatch.delenv("DDMPC_FORCE_GENERIC", raising=False)
+        assert int(s1.max()) == 0 and int(s2.max()) == 0
+        assert (i1 == i2).all()
+        assert _rel(u1.cpu().numpy(), u2.cpu().numpy()) < 1e-9 and _rel(y1.cpu().numpy(), y2.cpu().numpy()) < 1e-9
+        assert _rel(xf1.cpu().numpy(), xf2.cpu().numpy()) < 1e-9
+    qp = O.OracleController(20, 4, 4, sc["u_d"], sc["y_d"], 40, prm["Q"], prm["R"], prm["u_s"], prm["y_s"],
+                            prm["eps_max"], prm["lamb_alpha"], prm["lamb_sigma"], prm["c"], O.SLACK_NONE, O.ROBUST,
+                            n_mpc, True, check_pe=False)
+    u1, y1 = u1.cpu().numpy(), y1.cpu().numpy()
+    for b in (0, B - 1):
+        plant_o = O.Plant(pl.A, pl.B, pl.C, pl.D, pl.eps_max)
+        plant_o.x = x0[b].copy()
+        qp.u_s, qp.y_s = u_s[b].reshape(-1, 1), y_s[b].reshape(-1, 1)
+        qp.set_past_input_output_data(sc["u_past0"][b].reshape(-1, 1), sc["y_past0"][b].reshape(-1, 1))
+        u_ref, y_ref = O.closed_loop(plant_o, qp, min(n_steps, 60), w[b][:60])
+        assert _rel(u1[b][:60], u_ref) < 1e-5 and _rel(y1[b][:60], y_ref) < 1e-5
 
 
 @pytest.mark.parametrize("c", [1.0, 0.3])
