@@ -303,6 +303,76 @@ inline int pivot_rank(cudaStream_t st, int batch, int n, double *A, long ld, lon
 }
 
 // ---------------------------------------------------------------------------
+// Second-stage rank test on the matrix itself (not its Gram matrix): row-pivoted modified Gram-Schmidt (an LQ
+// factorisation with pivoting) of M (R x C, row-major, destroyed), one CTA per batch entry, one warp per row.
+// Entries whose first-stage verdict rank_io[b] already equals `full` are skipped.  A pivot counts while the
+// largest remaining row norm (recomputed exactly every step) exceeds max(R, C) * eps * ||M||_F, the cut of
+// np.linalg.matrix_rank (S > S.max() * max(M, N) * eps, hankel_matrix.py:82) with ||M||_F standing in for S.max().
+// Resolves singular-value ratios down to ~1e-13, where the Gram test stops at ~1e-6.
+// ---------------------------------------------------------------------------
+static __global__ void __launch_bounds__(512)
+k_rowqr_rank(int R, int C, double *__restrict__ M, long bs, int full, int *__restrict__ rank_io) {
+    extern __shared__ double sh[];          // nrm2[R], alive[R]
+    const int b = blockIdx.x;
+    if (rank_io[b] == full) return;
+    M += (long)b * bs;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NW = blockDim.x >> 5;
+    double *nrm2 = sh, *alive = sh + R;
+    __shared__ double s_thr, s_piv2;
+    __shared__ int s_pv;
+    for (int i = tid; i < R; i += blockDim.x) alive[i] = 1.0;
+    __syncthreads();
+    int r = 0;
+    for (; r < R; ++r) {
+        for (int i = warp; i < R; i += NW) {
+            if (alive[i] == 0.0) continue;
+            const double *row = M + (long)i * C;
+            double acc = 0.0;
+            for (int j = lane; j < C; j += 32) acc = fma(row[j], row[j], acc);
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (lane == 0) nrm2[i] = acc;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            double best = -1.0, fro2 = 0.0;
+            int bi = -1;
+            for (int i = 0; i < R; ++i)
+                if (alive[i] != 0.0) {
+                    fro2 += nrm2[i];
+                    if (nrm2[i] > best) { best = nrm2[i]; bi = i; }
+                }
+            if (r == 0) s_thr = (double)(R > C ? R : C) * 2.220446049250313e-16 * sqrt(fro2);
+            s_pv = (bi >= 0 && sqrt(best) > s_thr) ? bi : -1;
+            s_piv2 = best;
+            if (s_pv >= 0) alive[s_pv] = 0.0;
+        }
+        __syncthreads();
+        const int pv = s_pv;
+        if (pv < 0) break;
+        const double inv = 1.0 / s_piv2;
+        const double *prow = M + (long)pv * C;
+        for (int i = warp; i < R; i += NW) {
+            if (alive[i] == 0.0) continue;
+            double *row = M + (long)i * C;
+            double acc = 0.0;
+            for (int j = lane; j < C; j += 32) acc = fma(row[j], prow[j], acc);
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            const double d = acc * inv;
+            for (int j = lane; j < C; j += 32) row[j] = fma(-d, prow[j], row[j]);
+        }
+        __syncthreads();
+    }
+    if (tid == 0) rank_io[b] = r;
+}
+
+inline int rowqr_rank(cudaStream_t st, int batch, int R, int C, double *M, long bs, int full, int *rank_io) {
+    if (R <= 0 || batch <= 0) return DDMPC_OK;
+    k_rowqr_rank<<<batch, 512, sizeof(double) * 2 * R, st>>>(R, C, M, bs, full, rank_io);
+    DDMPC_LAUNCH_CHECK();
+    return DDMPC_OK;
+}
+
+// ---------------------------------------------------------------------------
 // Symmetric eigen-decomposition by parallel-ordered cyclic Jacobi.  One CTA per
 // batch entry; A (n x n, ld) is destroyed (its diagonal ends as the spectrum),
 // V (n x n, ldv; may be NULL) receives the eigenvectors as columns, lam (n) the

@@ -380,11 +380,14 @@ int pe_rank_device(cudaStream_t st, int batch, const double *X, long bsX, int N,
     Mat Hm = mat(Hpe.d(), cols, 1, (long)rows * cols);
     DDMPC_TRY(gemm(st, batch, rows, rows, cols, 1.0, Hm, tr(Hm), 0.0, G.d(), rows, 1, (long)rows * rows));
     DDMPC_TRY(symmetrize(st, batch, rows, G.d(), rows, (long)rows * rows));
-    // Rank = number of pivots of a diagonally pivoted elimination of the Gram matrix above
-    // 1e-12 x the largest.  The Gram matrix squares the singular values (lambda = sigma^2) and
-    // resolves sigma only down to ~sqrt(eps)*sigma_max, hence this cut (sigma/sigma_max > 1e-6)
-    // instead of matrix_rank's max(M,N)*eps; see DESIGN.md "PE rank test".
+    // Stage 1: number of pivots of a diagonally pivoted elimination of the Gram matrix above 1e-12 x the largest.
+    // The Gram matrix squares the singular values, so this proves full rank only for sigma_min/sigma_max > 1e-6 -
+    // true for every well-excited data set, and cheap (n^3 per controller, batched).
+    // Stage 2 (only for entries stage 1 could not certify): pivoted Gram-Schmidt on H itself with the cut of
+    // np.linalg.matrix_rank (hankel_matrix.py:82), so ill-conditioned but full-rank data is accepted exactly as
+    // the reference accepts it, and rank-deficient data reports the reference's rank.
     DDMPC_TRY(pivot_rank(st, batch, rows, G.d(), rows, (long)rows * rows, 1e-12, rank_dev));
+    DDMPC_TRY(rowqr_rank(st, batch, rows, cols, Hpe.d(), (long)rows * cols, rows, rank_dev));
     DDMPC_CUDA(cudaStreamSynchronize(st));
     return DDMPC_OK;
 }

@@ -64,6 +64,21 @@ def test_pe_rank():
     # odd sizes
     X3 = rng.normal(size=(90, 3))
     assert evaluate_persistent_excitation(X3, 7) == O.evaluate_persistent_excitation(X3, 7)
+    # ill-conditioned but full rank (sigma_min / sigma_max ~ 1e-9): the Gram test cannot certify it, the second
+    # stage (pivoted Gram-Schmidt on H with matrix_rank's cut) accepts it exactly as the reference does
+    for scale in (1e-7, 1e-9, 1e-11):
+        Xi = Xs + scale * rng.normal(size=Xs.shape)
+        ref = O.evaluate_persistent_excitation(Xi, 12)
+        assert ref == (24, True)
+        assert evaluate_persistent_excitation(Xi, 12) == ref, scale
+    # the same verdicts through the controller constructor (controller.py:285-296)
+    from direct_data_driven_mpc_b200 import ControllerSet
+    ud = np.hstack([np.sin(0.3 * t) + np.sin(0.7 * t), np.cos(0.2 * t)])[:120] + 1e-9 * rng.normal(size=(120, 2))
+    yd = rng.normal(size=(120, 2))
+    cs = ControllerSet(2, 2, 2, ud, yd, 8, np.eye(16), np.eye(16), 0.01, 1.0, 10.0, 1.0, 0, 1, 1, True)
+    rank, status = cs.info(0)                                      # order L + 2n = 12: rank 2 * 12 -> PE accepted;
+    assert rank == 24 and status != 7                              # (data this ill-conditioned may still fail the
+                                                                   # Gram factorisation: status 10, not "not PE")
 
 
 def _four_tank_set(slack, term, c=1.0, n_mpc=4, seed=0, ctrl=1):
