@@ -179,7 +179,7 @@ def workload_config(loops, world):
             "l2": "each step writes 841 MB of trajectories per GPU (> 126 MB L2); no flush needed",
             "parallelism": f"scenario-sharded x{world}, no data-path collective; one NCCL all_gather of per-loop "
                            "metrics after the timed steps",
-            "launch": "each step is one k_closed_loop_fast launch replayed from a CUDA graph"}
+            "launch": "each step is one k_closed_loop_ws launch (warp-specialised all-tensor-core kernel) replayed from a CUDA graph"}
 
 
 # --------------------------------------------------------------------------
@@ -277,7 +277,7 @@ def measure_e2e(args, cs, sc, plant, id0, solves_per_step, world, barrier, dev, 
 
     def e2e_step():
         return cs.closed_loop_host(plant, hx0, hup, hyp, hus, hys, N_STEPS, w=None, noise_seed=0,
-                                   scenario_id0=id0, noise_eps=0.002, out=(hu, hy), chunks=8)
+                                   scenario_id0=id0, noise_eps=0.002, out=(hu, hy), chunks=4)
 
     e2e_step()
     e2e_step()
@@ -300,9 +300,56 @@ def measure_e2e(args, cs, sc, plant, id0, solves_per_step, world, barrier, dev, 
     os.sched_setaffinity(0, old_affinity)      # the CPU baseline must see every core again
     return {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
            "ms_per_step": float(ems.item()) / args.e2e_steps,
-           "api": "ControllerSet.closed_loop_host (pinned host in, full trajectories out, 8 chunks on 2 streams)",
+           "api": "ControllerSet.closed_loop_host (pinned host in, full trajectories out, 4 chunks on 2 persistent streams)",
            "numa": numa}
 
+
+
+def secondary_config4(dev):
+    """BASELINE config 4 (synthetic n = 20, m = p = 4, N = 2000, L = 40; 16384 closed loops of 401 steps) through the
+    fused FP64 tensor-core kernel (dmma_loop.cu), device-resident inputs, CUDA events.  Not the headline: reported next
+    to it so the tensor-core-bound configuration has a measured number in the same run."""
+    import torch
+    from direct_data_driven_mpc_b200 import ControllerSet
+    from direct_data_driven_mpc_b200 import scenarios as S
+    out = {"workload": "config 4: synthetic stable LTI n=20 m=p=4 N=2000 L=40 robust, 16384 loops x 401 steps",
+           "fp64_peak_tflops": 37.2, "fp64_peak_source": "scripts/probes/fp64_pipes.cu: 64 FMA/clk/SM x 148 SMs x 1965 MHz"}
+    B = 16384
+    for nmpc in (1, 20):
+        sc = S.config4_batch(B, n_mpc_step=nmpc)
+        prm, pl = sc["params"], sc["plant"]
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        cs = ControllerSet(prm["n"], 4, 4, sc["u_d"], sc["y_d"], prm["L"], prm["Q"], prm["R"], prm["eps_max"],
+                           prm["lamb_alpha"], prm["lamb_sigma"], prm["c"], 0, 1, nmpc, True, device=dev)
+        torch.cuda.synchronize()
+        setup_ms = (time.perf_counter() - t) * 1e3
+        td = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+        args = (pl, td(sc["x0"]), td(sc["u_past0"]), td(sc["y_past0"]), td(sc["u_s"]), td(sc["y_s"]), N_STEPS)
+        bufs = (torch.empty(B, N_STEPS, 4, dtype=torch.float64, device=dev),
+                torch.empty(B, N_STEPS, 4, dtype=torch.float64, device=dev))
+        run = lambda: cs.closed_loop(*args, noise_seed=0, noise_eps=0.002, out=bufs)
+        for _ in range(3):
+            _, _, st, it = run()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 10
+        e0.record()
+        for _ in range(reps):
+            run()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        solves = int(it.sum().item())
+        # executed DMMA per 8 loops and MPC iteration: solve ceil(n_mpc*m/8) x n_theta/4, plant ceil((n_mpc*p+n_x)/8) x (n_x+n_mpc*m)/4
+        dmma = -(-nmpc * 4 // 8) * (168 // 4) + -(-(nmpc * 4 + 20) // 8) * ((20 + nmpc * 4) // 4)
+        flops = 2.0 * 256 * dmma * (B / 8) * (solves / B)
+        err = float((bufs[1][:, -1] - args[5]).abs().max())
+        out[f"n_mpc_{nmpc}"] = {"loop_ms": ms, "solves_per_s": solves / (ms * 1e-3), "setup_ms": setup_ms,
+                                "status_max": int(st.max().item()), "final_tracking_error_max": err,
+                                "executed_tflops": flops / (ms * 1e-3) / 1e12,
+                                "frac_of_fp64_peak": flops / (ms * 1e-3) / 1e12 / 37.2}
+        del cs
+    return out
 
 
 def main():
@@ -437,13 +484,19 @@ def main():
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get("k_closed_loop_fast_dram_bytes_per_launch")
+            traffic = json.load(open(tpath)).get("k_closed_loop_ws_dram_bytes_per_launch")
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": "k_closed_loop_fast", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    # the default kernel for this batch size is the warp-specialised all-tensor-core one (fast_loop.cu): per n-step
+    # block and 64 loops 32 + 48 DMMA m8n8k4 (256 FMA each, zero padding of the 12-row plant block map included)
+    roofline = {"bound": "hbm", "kernel": "k_closed_loop_ws", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": k_ms,
-                "flops_per_solve_executed": 2 * (8 * 20) + 4 * 2 * (4 * 4 + 4 * 2 + 2 * 4 + 2 * 2)}
+                "flops_per_solve_executed": 2 * 80 * 256 // 64,
+                "store_pattern_floor_ms": 0.204,
+                "store_pattern_note": "841 MB written as 32-byte sectors 6416 B apart (reference layout (B, n_steps, m)) take "
+                                      "0.204 ms on a B200 with no compute at all (scripts/probes/store_pattern.cu, "
+                                      "profiles/r1_probes.txt); a fully coalesced write of the same bytes takes 0.138 ms"}
 
     # ---- end to end through the host-buffer API: pinned inputs H2D, trajectories D2H, every step
     e2e = None
@@ -451,7 +504,12 @@ def main():
         e2e = measure_e2e(args, cs, sc, plant, id0, solves_per_step, world, barrier, dev, u_sys)
     except Exception as exc:  # pragma: no cover - never lose the main line over an auxiliary measurement
         e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": None, "d2h_bytes_per_step": None, "error": repr(exc)}
-    cb, latency = None, None
+    cb, latency, secondary = None, None, None
+    if rank == 0 and world == 1:
+        try:
+            secondary = secondary_config4(dev)
+        except Exception as exc:  # pragma: no cover
+            secondary = {"error": repr(exc)}
     if rank == 0:
         from direct_data_driven_mpc_b200 import (DataDrivenMPCType, DirectDataDrivenMPCController,
                                                  SlackVarConstraintTypes)
@@ -485,7 +543,7 @@ def main():
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(B, world),
             "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cb,
-            "single_loop_latency": latency,
+            "single_loop_latency": latency, "secondary": secondary,
             "setup_ms": setup_ms, "solves_per_step_per_gpu": solves_per_step,
             "final_tracking_error_max": float(track.max().item()),
         }

@@ -442,3 +442,25 @@ def test_warp_specialised_kernel_vs_oracle():
         ctrl.u_s, ctrl.y_s = us[b].reshape(-1, 1), ys[b].reshape(-1, 1)
         u_ref, y_ref = O.closed_loop(po, ctrl, n_steps, w)
         assert _rel(u[b], u_ref) < 1e-9 and _rel(y[b], y_ref) < 1e-9, b
+
+
+@pytest.mark.parametrize("chunks", [1, 3])
+def test_closed_loop_host_matches_device_api(chunks):
+    """Host-buffer entry point (the bench's `e2e` path): pinned or plain host arrays in, pinned trajectories out,
+    chunked over two persistent streams; equals the device-resident call, also when called again with another size."""
+    import torch
+    plant_o, prm, rng, x0, u_d, y_d = O.example_scenario(0)
+    cs, _ = _set(u_d, y_d)
+    r = np.random.default_rng(11)
+    for B, n_steps in ((1000, 41), (77, 12)):
+        xs = np.tile(plant_o.x, (B, 1)) + 0.05 * r.normal(size=(B, 4))
+        us = np.tile(prm["u_s"].T, (B, 1)) * r.uniform(0.7, 1.3, (B, 1))
+        ys = us @ _plant().equilibrium_gain().T
+        up0, yp0 = np.tile(u_d[-4:].reshape(1, -1), (B, 1)), np.tile(y_d[-4:].reshape(1, -1), (B, 1))
+        w = 0.002 * r.uniform(-1, 1, (B, n_steps, 2))
+        for kw in (dict(w=w), dict(noise_seed=4, scenario_id0=123, noise_eps=0.002)):
+            u1, y1, s1, _ = cs.closed_loop(_plant(), xs, up0, yp0, us, ys, n_steps, **kw)
+            hu, hy, hs = cs.closed_loop_host(_plant(), torch.from_numpy(xs).pin_memory(), up0, yp0, us, ys, n_steps,
+                                             chunks=chunks, **kw)
+            assert hu.is_pinned() and tuple(hu.shape) == (B, n_steps, 2) and int(hs.max()) == 0
+            assert _rel(hu.numpy(), u1.cpu().numpy()) < 1e-9 and _rel(hy.numpy(), y1.cpu().numpy()) < 1e-9
