@@ -232,21 +232,31 @@ class DirectDataDrivenMPCController:
         return (f(self.u_past, self.n * self.m), f(self.y_past, self.n * self.p), f(self.u_s, self.m),
                 f(self.y_s, self.p))
 
+    def _solve_buffers(self):
+        # per-step path: persistent host buffers and their raw addresses (no allocation, no ctypes conversion per call)
+        b = getattr(self, "_sbuf", None)
+        if b is None:
+            arr = {"up": np.empty(self.n * self.m), "yp": np.empty(self.n * self.p), "us": np.empty(self.m),
+                   "ys": np.empty(self.p), "out": np.empty(self.L * self.m), "cost": np.empty(1),
+                   "status": np.zeros(1, dtype=np.int32), "iters": np.zeros(1, dtype=np.int32)}
+            b = self._sbuf = (arr, {k: v.ctypes.data for k, v in arr.items()})
+        return b
+
     def solve_mpc_problem(self) -> str:
-        up, yp, us, ys = self._theta()
-        out = np.empty(self.L * self.m, dtype=np.float64)
-        cost = np.empty(1, dtype=np.float64)
-        status = np.zeros(1, dtype=np.int32)
-        iters = np.zeros(1, dtype=np.int32)
+        arr, ptr = self._solve_buffers()
+        arr["up"][:] = np.asarray(self.u_past, dtype=np.float64).reshape(-1)[:self.n * self.m]
+        arr["yp"][:] = np.asarray(self.y_past, dtype=np.float64).reshape(-1)[:self.n * self.p]
+        arr["us"][:] = np.asarray(self.u_s, dtype=np.float64).reshape(-1)[:self.m]
+        arr["ys"][:] = np.asarray(self.y_s, dtype=np.float64).reshape(-1)[:self.p]
         _lib.check(_lib.lib.ddmpc_solve_batch_host(
-            self._set, 1, None, up.ctypes.data, yp.ctypes.data, us.ctypes.data, ys.ctypes.data,
-            self._solve_tol, self._solve_max_iter, out.ctypes.data, cost.ctypes.data, status.ctypes.data,
-            iters.ctypes.data))
-        self._last_u, self._last_theta = out, (up, yp, us, ys)
+            self._set, 1, None, ptr["up"], ptr["yp"], ptr["us"], ptr["ys"], self._solve_tol, self._solve_max_iter,
+            ptr["out"], ptr["cost"], ptr["status"], ptr["iters"]))
+        self._last_u = arr["out"].copy()
+        self._last_theta = (arr["up"].copy(), arr["yp"].copy(), arr["us"].copy(), arr["ys"].copy())
         self._primal_cache = None
-        self.problem.status = _lib.STATUS_STRINGS.get(int(status[0]), "solver_error")
-        self.problem.value = float(cost[0])
-        self.solver_iterations = int(iters[0])
+        self.problem.status = _lib.STATUS_STRINGS.get(int(arr["status"][0]), "solver_error")
+        self.problem.value = float(arr["cost"][0])
+        self.solver_iterations = int(arr["iters"][0])
         return self.problem.status
 
     def get_problem_solve_status(self) -> str:

@@ -236,7 +236,7 @@ k_solve_small(KArgs a, int B, const int *__restrict__ ctrl_idx, const double *__
               int *__restrict__ iters_out, double *__restrict__ t_out) {
     extern __shared__ double sm[];
     const int b = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
-    double *th = sm, *su = th + a.nth, *z = su + a.nb, *w = z + a.nb, *dd = w + a.nb, *red = dd + a.nb;
+    double *th = sm, *su = th + a.nth, *z = su + a.nb, *w = z + a.nb, *dd = w + a.nb, *red = dd + a.nb, *uo = red + 64;
     const int c = ctrl_idx ? ctrl_idx[b] : 0;
     const int nm = a.n * a.m, npp = a.n * a.p;
     double tmax = 0.0, bad = 0.0;
@@ -262,7 +262,8 @@ k_solve_small(KArgs a, int B, const int *__restrict__ ctrl_idx, const double *__
         if (fe > 1e-6 * (1.0 + thmax)) status = max(status, (int)DDMPC_SOLVE_INFEASIBLE);
     }
     const double *Ku = a.Ku + (size_t)c * a.Lm * a.nth;
-    for (int k = tid; k < a.Lm; k += T) optimal_u[(size_t)b * a.Lm + k] = dot_row(Ku + (size_t)k * a.nth, th, a.nth);
+    // (the result is staged in shared memory and written once: optimal_u may be mapped host memory)
+    for (int k = tid; k < a.Lm; k += T) uo[k] = dot_row(Ku + (size_t)k * a.nth, th, a.nth);
     double J = 0.0;
     if (cost) {
         const double *Z = a.Z + (size_t)c * a.nth * a.nth;
@@ -318,7 +319,7 @@ k_solve_small(KArgs a, int B, const int *__restrict__ ctrl_idx, const double *__
             for (int j = tid; j < a.nb; j += T) su[j] = dot_row(Phi + (size_t)j * a.nb, dd, a.nb);   // t = Phi d
             __syncthreads();
             const double *Psi = a.Psi + (size_t)c * a.Lm * a.nb;
-            for (int k = tid; k < a.Lm; k += T) optimal_u[(size_t)b * a.Lm + k] -= dot_row(Psi + (size_t)k * a.nb, su, a.nb);
+            for (int k = tid; k < a.Lm; k += T) uo[k] -= dot_row(Psi + (size_t)k * a.nb, su, a.nb);
             if (cost) {
                 const double *Lam = a.Lam + (size_t)c * a.nb * a.nb;
                 const double rho = a.rho2[c];
@@ -328,6 +329,7 @@ k_solve_small(KArgs a, int B, const int *__restrict__ ctrl_idx, const double *__
             }
         }
     }
+    for (int k = tid; k < a.Lm; k += T) optimal_u[(size_t)b * a.Lm + k] = uo[k];   // same thread wrote uo[k]
     if (t_out)
         for (int j = tid; j < a.nb; j += T) t_out[(size_t)b * a.nb + j] = active ? su[j] : 0.0;
     if (tid == 0) {
@@ -616,7 +618,7 @@ int solve_batch_device(const ddmpc_set *set, int B, const int *ctrl_idx, const d
         return fail(DDMPC_ERR_INVALID_ARG, "solve_batch: null argument");
     KArgs a = make_kargs(set, tol, max_iter);
     if (B <= 64) {   // latency path: one CTA per solve
-        const size_t sh = sizeof(double) * ((size_t)a.nth + 4 * (size_t)a.nb + 64);
+        const size_t sh = sizeof(double) * ((size_t)a.nth + 4 * (size_t)a.nb + 64 + (size_t)a.Lm);
         if (sh <= 200 * 1024) {
             if (sh > 48 * 1024)
                 DDMPC_CUDA(cudaFuncSetAttribute(k_solve_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
@@ -676,8 +678,9 @@ int ddmpc_solve_batch(const ddmpc_set *set, int B, const int32_t *ctrl_idx, cons
                               nullptr, (cudaStream_t)stream);
 }
 
-// B == 1 (the controller object of the reference API): persistent pinned + device staging buffers,
-// two async copies and one kernel on a private stream - no allocation on the per-step path.
+// B == 1 (the controller object of the reference API): one persistent pinned buffer that the kernel reads and
+// writes directly over PCIe (pinned allocations are device-accessible under unified addressing), one kernel on a
+// private stream, one synchronise - no allocation and no copy command on the per-step path.
 static int solve_one_host_staged(const ddmpc_set *set, const int32_t *ctrl_idx, const double *u_past,
                                  const double *y_past, const double *u_s, const double *y_s, double tol, int max_iter,
                                  double *optimal_u, double *cost, int32_t *status, int32_t *iters) {
@@ -685,26 +688,25 @@ static int solve_one_host_staged(const ddmpc_set *set, const int32_t *ctrl_idx, 
     const int nm = d.n * d.m, npp = d.n * d.p;
     const size_t n_in = (size_t)d.nth + 1, n_out = (size_t)d.Lm + 3;   // doubles (+ ctrl / cost, status, iters)
     if (!set->stage_host) {
-        DDMPC_CUDA(cudaHostAlloc(&set->stage_host, sizeof(double) * (n_in + n_out), cudaHostAllocDefault));
-        DDMPC_CUDA(set->stage_dev.alloc(sizeof(double) * (n_in + n_out)));
+        DDMPC_CUDA(cudaHostAlloc(&set->stage_host, sizeof(double) * (n_in + n_out), cudaHostAllocMapped));
         DDMPC_CUDA(cudaStreamCreateWithFlags(&set->stage_stream, cudaStreamNonBlocking));
     }
-    double *h = (double *)set->stage_host, *dv = set->stage_dev.d();
+    double *h = (double *)set->stage_host;
     std::copy(u_past, u_past + nm, h);
     std::copy(y_past, y_past + npp, h + nm);
     std::copy(u_s, u_s + d.m, h + nm + npp);
     std::copy(y_s, y_s + d.p, h + nm + npp + d.m);
     int32_t *hci = reinterpret_cast<int32_t *>(h + d.nth);
     hci[0] = ctrl_idx ? ctrl_idx[0] : 0;
+    double *dv = nullptr;
+    DDMPC_CUDA(cudaHostGetDevicePointer((void **)&dv, h, 0));
     cudaStream_t st = set->stage_stream;
-    DDMPC_CUDA(cudaMemcpyAsync(dv, h, sizeof(double) * n_in, cudaMemcpyHostToDevice, st));
     double *dout = dv + n_in;
     int32_t *dints = reinterpret_cast<int32_t *>(dout + d.Lm + 1);
     DDMPC_TRY(solve_batch_device(set, 1, reinterpret_cast<const int *>(dv + d.nth), dv, dv + nm, dv + nm + npp,
                                  dv + nm + npp + d.m, tol, max_iter, dout, dout + d.Lm, dints, dints + 1, nullptr, st));
-    double *hout = h + n_in;
-    DDMPC_CUDA(cudaMemcpyAsync(hout, dout, sizeof(double) * n_out, cudaMemcpyDeviceToHost, st));
     DDMPC_CUDA(cudaStreamSynchronize(st));
+    const double *hout = h + n_in;
     std::copy(hout, hout + d.Lm, optimal_u);
     if (cost) *cost = hout[d.Lm];
     const int32_t *hints = reinterpret_cast<const int32_t *>(hout + d.Lm + 1);
