@@ -48,7 +48,26 @@ inline int fail(int code, const char *fmt, ...) {
 
 inline int ceil_div(long a, long b) { return (int)((a + b - 1) / b); }
 
-// RAII device buffer (setup scratch + plan storage)
+// RAII device buffer (setup scratch + plan storage).  Memory comes from the device's stream-ordered pool
+// (cudaMallocAsync on the legacy default stream) with a 1 GiB release threshold: a batched controller setup
+// allocates and frees a dozen buffers of up to hundreds of MB, and with cudaMalloc/cudaFree (each a device-wide
+// synchronisation plus page-table work) that cost 80-250 ms of wall time per call against 13 ms of kernels.
+// Every scratch lifetime in this library ends with a stream synchronise before the buffers go out of scope, and
+// ddmpc_set_destroy synchronises the device, so returning memory to the pool never races with work using it.
+inline cudaError_t pool_ready() {
+    static cudaError_t state = [] {
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        cudaMemPool_t pool;
+        e = cudaDeviceGetDefaultMemPool(&pool, dev);
+        if (e != cudaSuccess) return e;
+        uint64_t keep = 1ull << 30;
+        return cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }();
+    return state;
+}
+
 struct DevBuf {
     void *p = nullptr;
     size_t bytes = 0;
@@ -57,15 +76,19 @@ struct DevBuf {
     DevBuf &operator=(const DevBuf &) = delete;
     ~DevBuf() { release(); }
     void release() {
-        if (p) cudaFree(p);
+        if (p) cudaFreeAsync(p, (cudaStream_t)0);
         p = nullptr;
         bytes = 0;
     }
     cudaError_t alloc(size_t n) {
         release();
         if (n == 0) n = 8;
-        bytes = n;
-        return cudaMalloc(&p, n);
+        cudaError_t e = pool_ready();
+        if (e != cudaSuccess) return e;
+        e = cudaMallocAsync(&p, n, (cudaStream_t)0);
+        if (e == cudaSuccess) bytes = n;
+        else p = nullptr;
+        return e;
     }
     double *d() const { return (double *)p; }
     int *i() const { return (int *)p; }

@@ -39,6 +39,7 @@ struct FastArgs {
     int *status, *iters;
     uint32_t rk[20];     // Philox round keys (key + r * Weyl), filled on the host
     int zmask;           // always 0: defeats loop-invariant hoisting of coefficient loads
+    int dbg_nostore;     // measurement aid (DDMPC_DEBUG_NOSTORE=1): k_closed_loop_ws skips the trajectory stores
     // CONVEX slack bound (device operators of controller 0, see plan.cuh)
     const double *Ks, *Phi, *Psi;   // (nb, nth), (nb, nb), (L*m, nb)
     double bound, tol;
@@ -1222,7 +1223,7 @@ k_closed_loop_ws(const __grid_constant__ MmaCoef<N, M, P, NX, NMPC> cfp, const F
 #pragma unroll
                         for (int i = 0; i < P; ++i) y[i] = wy_s[yb][s * P + i][l][SW(s * P + i, tl)];
                         const size_t f = f0[l] + k;
-                        if (live[l] && (f & 1)) {          // warp-uniform: completes the sector (f-1, f)
+                        if (live[l] && (f & 1) && !a.dbg_nostore) {   // warp-uniform: completes the sector (f-1, f)
                             if (k == 0) {
                                 *reinterpret_cast<double2 *>(a.u_sys + f * 2) = make_double2(u[0], u[1]);
                                 *reinterpret_cast<double2 *>(a.y_sys + f * 2) = make_double2(y[0], y[1]);
@@ -1488,6 +1489,7 @@ static int launch_fast(const ddmpc_set *set, const ddmpc_plant *plant, const Fas
                 const dim3 gridw(ceil_div(a.B, 64));
                 // 7 CTAs (30 KB of shared memory each) per SM put the 1024 CTAs of a 65,536-loop batch in ONE wave
                 // on 148 SMs: ask for the largest shared-memory carveout instead of trusting the default
+                if (const char *ens = getenv("DDMPC_DEBUG_NOSTORE")) a.dbg_nostore = ens[0] == '1';
                 const char *emw = getenv("DDMPC_WS_MATH_WARPS");
                 const int mw = (emw && emw[0] == '1') ? 1 : 2;
                 static bool carveout_set = false;

@@ -853,7 +853,11 @@ int ddmpc_set_create_host(const ddmpc_params *params, int count, const double *u
                              lamb_sigma, nullptr, out);
 }
 
-void ddmpc_set_destroy(ddmpc_set *set) { delete set; }
+void ddmpc_set_destroy(ddmpc_set *set) {
+    if (!set) return;
+    cudaDeviceSynchronize();   // the plan's buffers go back to the stream-ordered pool: nothing may still be using them
+    delete set;
+}
 
 int ddmpc_set_count(const ddmpc_set *set) { return set ? set->plan.count : 0; }
 
