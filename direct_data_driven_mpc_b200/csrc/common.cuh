@@ -10,6 +10,8 @@
 
 #include "../../include/ddmpc.h"
 
+#define DDMPC_ADMM_RELAX 1.8   // over-relaxation of the box-row ADMM (all three implementations share it)
+
 namespace ddmpc {
 
 extern thread_local char g_last_error[512];

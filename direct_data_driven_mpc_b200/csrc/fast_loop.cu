@@ -102,9 +102,10 @@ __device__ __noinline__ int admm_box_warp(const FastArgs &a, int R, ThetaF th, U
                 }
                 for (; j < nb; ++j) acc0 = fma(__ldg(col + (size_t)j * nb), dsh[j], acc0);
                 const double si = (z[rr] - w[rr]) + (acc0 + acc1);
-                const double zn = fmin(fmax(si + w[rr], -a.bound), a.bound);
+                const double sr = DDMPC_ADMM_RELAX * si + (1.0 - DDMPC_ADMM_RELAX) * z[rr];   // over-relaxation (solve.cu)
+                const double zn = fmin(fmax(sr + w[rr], -a.bound), a.bound);
                 res = fmax(res, fmax(fabs(si - zn), fabs(zn - z[rr])));
-                w[rr] = w[rr] + si - zn;
+                w[rr] = w[rr] + sr - zn;
                 z[rr] = zn;
             }
         }

@@ -49,8 +49,9 @@ __device__ __forceinline__ bool setpoint_outside_box(const KArgs &a, const doubl
 // In : s_unc (unconstrained slack rows), smax = max|s_unc| > bound.
 // Out: s_unc overwritten by t = Phi d at the fixed point, so that
 //      u = u0 - Psi t,  x = x0 - Yf t,  cost += rho2^2 t^T Lam t.
-// Iteration (DESIGN.md "ADMM on the condensed box rows"):
-//      d = s_unc - (z - w);  s = (z - w) + Phi d;  z+ = clip(s + w);  w+ = w + s - z+.
+// Iteration (DESIGN.md "ADMM on the condensed box rows"), over-relaxed with alpha = DDMPC_ADMM_RELAX:
+//      d = s_unc - (z - w);  s = (z - w) + Phi d;  sr = alpha s + (1 - alpha) z;  z+ = clip(sr + w);  w+ = w + sr - z+.
+// alpha = 1.8 cuts the iteration count 2-3x on the slack box and 1.9x on the input box (1.9 and above degrade).
 __device__ __forceinline__ int admm_box(const KArgs &a, const double *__restrict__ Phi, const double *__restrict__ lo,
                                         const double *__restrict__ hi, double bscale, double *s_unc, double *z,
                                         double *w, double *d, double smax, int TS, int tid, int *status) {
@@ -78,10 +79,11 @@ __device__ __forceinline__ int admm_box(const KArgs &a, const double *__restrict
             if (j < nb) acc0 = fma(row[j], SMV(d, j), acc0);
             const double zi = SMV(z, i), wi = SMV(w, i);
             const double si = (zi - wi) + (acc0 + acc1);
-            const double zn = fmin(fmax(si + wi, lo[i]), hi[i]);
+            const double sr = DDMPC_ADMM_RELAX * si + (1.0 - DDMPC_ADMM_RELAX) * zi;
+            const double zn = fmin(fmax(sr + wi, lo[i]), hi[i]);
             rp = fmax(rp, fabs(si - zn));
             rd = fmax(rd, fabs(zn - zi));
-            SMV(w, i) = wi + si - zn;
+            SMV(w, i) = wi + sr - zn;
             SMV(z, i) = zn;
         }
         conv = fmax(rp, rd) <= thr;
@@ -304,9 +306,10 @@ k_solve_small(KArgs a, int B, const int *__restrict__ ctrl_idx, const double *__
                 for (int j = tid; j < a.nb; j += T) {
                     const double acc = dot_row(Phi + (size_t)j * a.nb, dd, a.nb);
                     const double si = (z[j] - w[j]) + acc;
-                    const double zn = fmin(fmax(si + w[j], lo[j]), hi[j]);
+                    const double sr = DDMPC_ADMM_RELAX * si + (1.0 - DDMPC_ADMM_RELAX) * z[j];
+                    const double zn = fmin(fmax(sr + w[j], lo[j]), hi[j]);
                     res = fmax(res, fmax(fabs(si - zn), fabs(zn - z[j])));
-                    w[j] = w[j] + si - zn;
+                    w[j] = w[j] + sr - zn;
                     z[j] = zn;
                 }
                 conv = block_max(res, red) <= thr;

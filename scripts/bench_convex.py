@@ -8,7 +8,8 @@ sc = S.config3_batch(B); prm, pl = sc["params"], sc["plant"]
 for c in (100.0, 1.0, 0.3):
     cs = ControllerSet(4, 2, 2, sc["u_d"], sc["y_d"], 30, prm["Q"], prm["R"], prm["eps_max"], prm["lamb_alpha"], prm["lamb_sigma"],
                        c, 1, 1, 4, True)
-    args = (pl, sc["x0"], sc["u_past0"], sc["y_past0"], sc["u_s"], sc["y_s"], 401)
+    td = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    args = (pl, td(sc["x0"]), td(sc["u_past0"]), td(sc["y_past0"]), td(sc["u_s"]), td(sc["y_s"]), 401)
     kw = dict(noise_seed=0, noise_eps=0.002)
     u, y, st, it = cs.closed_loop(*args, **kw); torch.cuda.synchronize()
     t = time.perf_counter(); u, y, st, it = cs.closed_loop(*args, **kw); torch.cuda.synchronize(); dt = time.perf_counter() - t

@@ -179,7 +179,7 @@ def make_theta(n, m, p, u_past, y_past, u_s, y_s):
     return np.concatenate([np.reshape(u_past, -1), np.reshape(y_past, -1), np.reshape(u_s, -1), np.reshape(y_s, -1)])
 
 
-def solve(pl: Plan, theta, tol=1e-9, max_iter=500, relax=1.0):
+def solve(pl: Plan, theta, tol=1e-9, max_iter=500, relax=1.8):
     """Returns (optimal_u, cost, status, iters)."""
     u = pl.Ku @ theta
     cost = float(theta @ pl.Z @ theta)
