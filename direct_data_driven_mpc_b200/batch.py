@@ -93,9 +93,9 @@ class ControllerSet:
         Qd = _dev_f64(Q, self.device)
         Rd = _dev_f64(R, self.device)
         if tuple(Qd.shape) != (p * L, p * L):
-            raise ValueError("Output weighting square matrix Q should be of order (p * L)")
+            raise ValueError("Output weighting square matrix Q should beof order (p * L)")   # sic: controller.py:338-339
         if tuple(Rd.shape) != (m * L, m * L):
-            raise ValueError("Input weighting square matrix R should be of order (m * L)")
+            raise ValueError("Input weighting square matrix R should beof order (m * L)")   # sic: controller.py:342-343
         robust = controller_type == _lib.ROBUST
         self.robust = robust
         nan = float("nan")

@@ -153,9 +153,9 @@ class DirectDataDrivenMPCController:
 
     def check_weighting_matrices_dimensions(self) -> None:
         if self.Q.shape != (self.p * self.L, self.p * self.L):
-            raise ValueError("Output weighting square matrix Q should be of order (p * L)")
+            raise ValueError("Output weighting square matrix Q should beof order (p * L)")   # sic: controller.py:338-339
         if self.R.shape != (self.m * self.L, self.m * self.L):
-            raise ValueError("Input weighting square matrix R should be of order (m * L)")
+            raise ValueError("Input weighting square matrix R should beof order (m * L)")   # sic: controller.py:342-343
 
     # ---- construction of the device plan (controller.py:345-387) ------------
     def initialize_data_driven_mpc(self) -> None:

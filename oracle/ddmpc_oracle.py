@@ -1,5 +1,6 @@
 """FP64 NumPy/SciPy oracle of the DD-MPC hot path.  TEST INFRASTRUCTURE ONLY
-(see ``oracle/__init__.py``: parity at the cvxpy boundary is UNPINNED).
+(see ``oracle/__init__.py``: pinned against the unmodified reference class run with a cvxpy stand-in;
+parity UNPINNED only at the level of cvxpy's own solver tolerance).
 
 Every function cites the reference lines it restates (paths relative to the
 reference checkout).  The QP is solved literally as stated by the reference:

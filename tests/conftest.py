@@ -43,3 +43,10 @@ def golden_repro():
 @pytest.fixture(scope="session")
 def golden_hankel():
     return np.load(os.path.join(GOLDEN, "hankel.npz"))
+
+
+@pytest.fixture(scope="session")
+def refclass():
+    """Fixtures produced by the UNMODIFIED reference controller class (tests/golden/make_golden_refclass.py)."""
+    return {k: np.load(os.path.join(GOLDEN, f"refclass_{k}.npz")) for k in
+            ("example_seed0", "reproduction_seed4", "variants", "errors")}
