@@ -22,7 +22,7 @@ import sys
 
 import numpy as np
 
-REF = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
+REF = next((a for a in sys.argv[1:] if not a.startswith("--")), "/root/reference")
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
@@ -263,11 +263,44 @@ def fixture_errors():
                         **{f"err_{k}": np.array(v) for k, v in out.items()})
 
 
+def fixture_config4(n_steps=3):
+    """BASELINE config 4 (synthetic n = 20, m = p = 4, N = 2000, L = 40): the reference class on the large problem
+    (2661 variables, 800 equalities), three closed-loop steps of the 1-step scheme and one 20-step block."""
+    from direct_data_driven_mpc_b200 import scenarios as S
+    out = {}
+    for nmpc, steps in ((1, n_steps), (20, 20)):
+        sc = S.config4_batch(1, n_mpc_step=nmpc)
+        prm, pl = sc["params"], sc["plant"]
+        ctrl = DirectDataDrivenMPCController(
+            n=20, m=4, p=4, u_d=sc["u_d"], y_d=sc["y_d"], L=40, Q=prm["Q"], R=prm["R"], u_s=prm["u_s"], y_s=prm["y_s"],
+            eps_max=prm["eps_max"], lamb_alpha=prm["lamb_alpha"], lamb_sigma=prm["lamb_sigma"], c=prm["c"],
+            slack_var_constraint_type=SlackVarConstraintTypes.NONE, controller_type=DataDrivenMPCType.ROBUST,
+            n_mpc_step=nmpc, use_terminal_constraint=True)
+        r = np.random.default_rng(3)
+        x0 = sc["x0"][0] + 0.1 * r.normal(size=20)
+        w = pl.eps_max * r.uniform(-1, 1, (steps, 4))
+        plant = O.Plant(pl.A, pl.B, pl.C, pl.D, pl.eps_max); plant.x = x0.copy()
+        rec = Recorder(ctrl)
+        u, y = O.closed_loop(plant, rec, steps, w)      # same loop as controller_operation.py:269-305, noise supplied
+        oc = O.OracleController(20, 4, 4, sc["u_d"], sc["y_d"], 40, prm["Q"], prm["R"], prm["u_s"], prm["y_s"], prm["eps_max"],
+                                prm["lamb_alpha"], prm["lamb_sigma"], prm["c"], O.SLACK_NONE, O.ROBUST, nmpc, True, check_pe=False)
+        po = O.Plant(pl.A, pl.B, pl.C, pl.D, pl.eps_max); po.x = x0.copy()
+        uo, yo = O.closed_loop(po, oc, steps, w)
+        print(f"config 4 n_mpc={nmpc}: {len(rec.log)} reference-class solves; oracle vs reference class: u {rel(uo, u):.2e} y {rel(yo, y):.2e}")
+        out.update({f"x0_{nmpc}": x0, f"w_{nmpc}": w, f"u_{nmpc}": u, f"y_{nmpc}": y,
+                    f"opt_u_{nmpc}": np.stack([l[2] for l in rec.log]), f"cost_{nmpc}": np.array([l[3] for l in rec.log])})
+    np.savez_compressed(os.path.join(HERE, "refclass_config4.npz"), **out)
+
+
 if __name__ == "__main__":
+    if "--config4-only" in sys.argv:
+        fixture_config4()
+        sys.exit(0)
     fixture_errors()
     fixture_variants()
     fixture_example()
     fixture_reproduction()
+    fixture_config4()
     for f in sorted(os.listdir(HERE)):
         if f.startswith("refclass_"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -107,3 +107,26 @@ def test_class_facade_errors_and_setpoints_vs_reference_class(refclass):
     ctrl.set_input_output_setpoints(u_s=g["setpoint_us"], y_s=g["setpoint_ys"])
     assert _rel(ctrl.optimal_u, g["setpoint_opt_u"]) < 1e-8
     assert np.array_equal(ctrl.u_past, g["setpoint_u_past"])
+
+
+@pytest.mark.parametrize("n_mpc", [1, 20])
+def test_config4_large_problem_vs_reference_class(refclass, n_mpc):
+    """BASELINE config 4 (2661 variables / 800 equalities in the reference's formulation): the fused FP64 tensor-core
+    kernel (batch of 512 copies) and the batched solve against closed-loop steps of the reference class."""
+    from direct_data_driven_mpc_b200 import ControllerSet, scenarios as S
+    g = refclass["config4"]
+    sc = S.config4_batch(1, n_mpc_step=n_mpc)
+    prm, pl = sc["params"], sc["plant"]
+    cs = ControllerSet(20, 4, 4, sc["u_d"], sc["y_d"], 40, prm["Q"], prm["R"], prm["eps_max"], prm["lamb_alpha"],
+                       prm["lamb_sigma"], prm["c"], 0, 1, n_mpc, True)
+    w, steps = g[f"w_{n_mpc}"], g[f"w_{n_mpc}"].shape[0]
+    for B in (1, 512):                                   # generic kernel / fused DMMA kernel
+        t = lambda a: np.tile(np.asarray(a).reshape(1, -1), (B, 1))
+        u, y, st, _ = cs.closed_loop(pl, t(g[f"x0_{n_mpc}"]), t(sc["u_past0"]), t(sc["y_past0"]), t(prm["u_s"]), t(prm["y_s"]),
+                                     steps, w=np.tile(w[None], (B, 1, 1)))
+        assert int(st.max()) == 0
+        for b in {0, B - 1}:
+            assert _rel(u[b].cpu().numpy(), g[f"u_{n_mpc}"]) < 1e-8 and _rel(y[b].cpu().numpy(), g[f"y_{n_mpc}"]) < 1e-8
+    uo, cost, st, _ = cs.solve_batch(sc["u_past0"], sc["y_past0"], prm["u_s"].T, prm["y_s"].T)
+    assert _rel(uo.cpu().numpy()[0], g[f"opt_u_{n_mpc}"][0]) < 1e-8              # first solve: the whole L*m prediction
+    assert abs(float(cost[0]) - g[f"cost_{n_mpc}"][0]) <= 1e-7 * max(1.0, abs(g[f"cost_{n_mpc}"][0]))

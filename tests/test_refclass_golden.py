@@ -87,3 +87,19 @@ def test_reference_error_messages_on_host(refclass):
         with pytest.raises(ValueError if kind == "ValueError" else NotImplementedError) as ei:
             DirectDataDrivenMPCController(**{**base, **over})
         assert str(ei.value) == text, name
+
+
+@pytest.mark.parametrize("n_mpc", [1, 20])
+def test_config4_large_problem(refclass, n_mpc):
+    """BASELINE config 4 (n = 20, m = p = 4, N = 2000, L = 40): oracle vs closed-loop steps of the reference class."""
+    from direct_data_driven_mpc_b200 import scenarios as S
+    g = refclass["config4"]
+    sc = S.config4_batch(1, n_mpc_step=n_mpc)
+    prm, pl = sc["params"], sc["plant"]
+    oc = O.OracleController(20, 4, 4, sc["u_d"], sc["y_d"], 40, prm["Q"], prm["R"], prm["u_s"], prm["y_s"], prm["eps_max"],
+                            prm["lamb_alpha"], prm["lamb_sigma"], prm["c"], O.SLACK_NONE, O.ROBUST, n_mpc, True, check_pe=False)
+    po = O.Plant(pl.A, pl.B, pl.C, pl.D, pl.eps_max)
+    po.x = g[f"x0_{n_mpc}"].copy()
+    u, y = O.closed_loop(po, oc, g[f"w_{n_mpc}"].shape[0], g[f"w_{n_mpc}"])
+    assert _rel(u, g[f"u_{n_mpc}"]) < 1e-9 and _rel(y, g[f"y_{n_mpc}"]) < 1e-9
+    assert _rel(oc.history[0][2], g[f"opt_u_{n_mpc}"][0]) < 1e-9
