@@ -27,7 +27,8 @@ class Params(C.Structure):
                 ("controller_type", C.c_int32), ("slack_type", C.c_int32), ("use_terminal", C.c_int32),
                 ("n_mpc_step", C.c_int32), ("check_pe", C.c_int32),
                 ("eps_max", C.c_double), ("lamb_alpha", C.c_double), ("lamb_sigma", C.c_double), ("c", C.c_double),
-                ("u_min", C.c_void_p), ("u_max", C.c_void_p)]   # optional input box (host pointers, m values each)
+                ("u_min", C.c_void_p), ("u_max", C.c_void_p),   # optional input box (host pointers, m values each)
+                ("y_min", C.c_void_p), ("y_max", C.c_void_p)]   # optional output box (host pointers, p values each)
 
 
 class Plant(C.Structure):

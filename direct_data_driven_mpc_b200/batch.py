@@ -68,13 +68,15 @@ class ControllerSet:
     input_bounds: optional ``(u_min, u_max)`` (scalars or length-m, ``None`` / inf = open side): the box
     ``u_min <= ubar[k] <= u_max`` on every predicted input (paper Eq. 6; NOT part of the reference's
     formulation, controller.py:447-504, so it is off by default).  ROBUST controllers only.
+    output_bounds: optional ``(y_min, y_max)``, the same for every predicted output ``ybar[k]`` (length p).
     """
 
     def __init__(self, n: int, m: int, p: int, u_d, y_d, L: int, Q, R, eps_max: Optional[float] = None,
                  lamb_alpha=None, lamb_sigma=None, c: Optional[float] = None, slack_type: int = _lib.SLACK_CONVEX,
                  controller_type: int = _lib.NOMINAL, n_mpc_step: int = 1, use_terminal_constraint: bool = True,
                  count: Optional[int] = None, check_pe: bool = True, device: Optional[torch.device] = None,
-                 input_bounds: Optional[Tuple[object, object]] = None):
+                 input_bounds: Optional[Tuple[object, object]] = None,
+                 output_bounds: Optional[Tuple[object, object]] = None):
         if not torch.cuda.is_available():
             raise RuntimeError("ControllerSet needs a CUDA device (no CPU fallback)")
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
@@ -127,6 +129,13 @@ class ControllerSet:
             hi = np.full(m, np.inf) if hi is None else np.broadcast_to(_f64(hi).reshape(-1), (m,)).copy()
             self.input_bounds = (lo, hi)                       # kept alive: the struct holds raw pointers
             prm.u_min, prm.u_max = lo.ctypes.data, hi.ctypes.data
+        self.output_bounds = None
+        if output_bounds is not None:
+            lo, hi = output_bounds
+            lo = np.full(p, -np.inf) if lo is None else np.broadcast_to(_f64(lo).reshape(-1), (p,)).copy()
+            hi = np.full(p, np.inf) if hi is None else np.broadcast_to(_f64(hi).reshape(-1), (p,)).copy()
+            self.output_bounds = (lo, hi)
+            prm.y_min, prm.y_max = lo.ctypes.data, hi.ctypes.data
         handle = C.c_void_p()
         with torch.cuda.device(self.device):
             stream = torch.cuda.current_stream().cuda_stream

@@ -77,7 +77,7 @@ class DirectDataDrivenMPCController:
                  c: Optional[float] = None,
                  slack_var_constraint_type: SlackVarConstraintTypes = SlackVarConstraintTypes.CONVEX,
                  controller_type: DataDrivenMPCType = DataDrivenMPCType.NOMINAL, n_mpc_step: int = 1,
-                 use_terminal_constraint: bool = True, input_bounds=None):
+                 use_terminal_constraint: bool = True, input_bounds=None, output_bounds=None):
         # input_bounds: optional (u_min, u_max) box on every predicted input (paper Eq. 6).  An extension: the
         # reference class has no such argument (controller.py:95-116) and never constrains ubar (:447-504).
         self._set = None
@@ -87,6 +87,12 @@ class DirectDataDrivenMPCController:
             lo = np.full(m, -np.inf) if lo is None else np.broadcast_to(np.asarray(lo, dtype=np.float64).reshape(-1), (m,)).copy()
             hi = np.full(m, np.inf) if hi is None else np.broadcast_to(np.asarray(hi, dtype=np.float64).reshape(-1), (m,)).copy()
             self.input_bounds = (lo, hi)
+        self.output_bounds = None
+        if output_bounds is not None:                                 # same extension for the predicted outputs ybar
+            lo, hi = output_bounds
+            lo = np.full(p, -np.inf) if lo is None else np.broadcast_to(np.asarray(lo, dtype=np.float64).reshape(-1), (p,)).copy()
+            hi = np.full(p, np.inf) if hi is None else np.broadcast_to(np.asarray(hi, dtype=np.float64).reshape(-1), (p,)).copy()
+            self.output_bounds = (lo, hi)
         self._solve_tol, self._solve_max_iter = 1e-8, 2000
         self.controller_type = controller_type
         if controller_type not in _CTRL_CODE:                         # controller.py:165-168
@@ -173,6 +179,8 @@ class DirectDataDrivenMPCController:
             c=_nan_if_none(self.c) if robust else 0.0)
         if self.input_bounds is not None:
             prm.u_min, prm.u_max = self.input_bounds[0].ctypes.data, self.input_bounds[1].ctypes.data
+        if self.output_bounds is not None:
+            prm.y_min, prm.y_max = self.output_bounds[0].ctypes.data, self.output_bounds[1].ctypes.data
         ud = np.ascontiguousarray(self.u_d, dtype=np.float64)
         yd = np.ascontiguousarray(self.y_d, dtype=np.float64)
         Q = np.ascontiguousarray(self.Q, dtype=np.float64)

@@ -1607,7 +1607,7 @@ int closed_loop_fast_try(const ddmpc_set *set, const ddmpc_plant *plant, int B, 
                          cudaStream_t st) {
     const Dims &d = set->plan.d;
     if (ctrl_idx || set->plan.count != 1 || !d.robust) return -1;
-    if (d.nbu > 0) return -1;                    // input box: per-row bounds, generic kernel
+    if (d.nbu > 0 || d.nby > 0) return -1;       // input / output box: per-row bounds, generic kernel
     const char *force = getenv("DDMPC_FORCE_GENERIC");
     if (force && force[0] == '1') return -1;
     FastArgs fa{};

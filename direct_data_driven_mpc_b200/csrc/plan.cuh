@@ -15,8 +15,9 @@ struct Dims {
     int nx;            // primal x = [ubar; ybar; sigma(robust)]
     int nfix, nf;      // fixed (initial/terminal) and free coordinates
     int nth;           // theta = [u_past; y_past; u_s; y_s]
-    int nb;            // box rows = nbs + nbu
-    int nbs, nbu;      // CONVEX: sigma_pred rows (L*p) / input box: free predicted-input rows ((L-n)*m or L*m)
+    int nb;            // box rows = nbs + nbu + nby
+    int nbs, nbu, nby; // CONVEX: sigma_pred rows (L*p) / input box: free predicted-input rows ((L-n)*m or L*m) /
+                       // output box: free predicted-output rows ((L-n)*p or L*p)
     int Lm;            // L*m = len(optimal_u)
     int robust, convex, terminal;
 };
@@ -42,6 +43,7 @@ struct Plan {
     DevBuf bmax;   // (1)            largest finite |scaled bound| (residual tolerance scale)
     DevBuf blo, bhi;   // (nb)       unscaled bounds, shared by the set
     DevBuf umin, umax; // (m)        input box (device copy), empty when absent
+    DevBuf ymin, ymax; // (p)        output box (device copy), empty when absent
     DevBuf F;      // (nfix, nth)    feasibility residual map     (nominal)
     DevBuf lamA, lamS;  // per-controller lamb_alpha*eps_max, lamb_sigma
     std::vector<int> pe_rank, status;

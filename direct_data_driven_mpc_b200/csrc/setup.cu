@@ -220,11 +220,12 @@ __global__ void k_fill_Bt(int nf, int nb, const int *__restrict__ bpos, double *
 }
 
 // Row scales S, Lam = sym(S B Y S), rho2 = nb / trace(Lam), M = I + rho2 Lam and the scaled bounds.  One CTA per
-// controller.  The sigma rows (the first nbs) keep scale 1, so a CONVEX-only problem is untouched; the input rows
-// get sqrt(mean Lam_ss / mean Lam_uu): the two groups differ by five orders of magnitude in Lam (1e-3 vs 4e2 on
-// the four-tank data) and a single ADMM penalty only suits both after this equilibration (1 without sigma rows).
+// controller.  The box rows come in up to three groups - sigma_pred (CONVEX), predicted inputs, predicted outputs -
+// whose diagonal of Lam differs by orders of magnitude (1e-3 vs 4e2 for sigma vs inputs on the four-tank data), and a
+// single ADMM penalty only suits all of them after equilibration: the first non-empty group keeps scale 1 (a
+// CONVEX-only problem is untouched), every other group g gets sqrt(mean Lam_ref / mean Lam_gg).
 __global__ void __launch_bounds__(256)
-k_lam_rho(int nf, int nb, int nbs, const int *__restrict__ bpos, const double *__restrict__ Y, long bsY,
+k_lam_rho(int nf, int nb, int nbs, int nbu, const int *__restrict__ bpos, const double *__restrict__ Y, long bsY,
           const double *__restrict__ blo, const double *__restrict__ bhi, double *__restrict__ Lam,
           double *__restrict__ Mm, double *__restrict__ rho2, double *__restrict__ rs, double *__restrict__ lo,
           double *__restrict__ hi, double *__restrict__ bmax) {
@@ -232,33 +233,37 @@ k_lam_rho(int nf, int nb, int nbs, const int *__restrict__ bpos, const double *_
     Y += (long)c * bsY;
     Lam += (long)c * nb * nb;
     Mm += (long)c * nb * nb;
-    __shared__ double red[3][8];
-    __shared__ double s_rho, s_su;
-    double ts = 0.0, tu = 0.0, bm = 0.0;
-    for (int j = tid; j < nb; j += blockDim.x) {
-        const double dj = Y[(long)bpos[j] * nb + j];
-        if (j < nbs) ts += dj; else tu += dj;
-    }
-    for (int o = 16; o > 0; o >>= 1) {
-        ts += __shfl_xor_sync(0xffffffffu, ts, o);
-        tu += __shfl_xor_sync(0xffffffffu, tu, o);
-    }
-    if ((tid & 31) == 0) { red[0][tid >> 5] = ts; red[1][tid >> 5] = tu; }
+    __shared__ double red[4][8];
+    __shared__ double s_rho, s_sc[3];
+    const int g1 = nbs, g2 = nbs + nbu;
+    auto group = [&](int j) { return j < g1 ? 0 : (j < g2 ? 1 : 2); };
+    double t[3] = {0.0, 0.0, 0.0}, bm = 0.0;
+    for (int j = tid; j < nb; j += blockDim.x) t[group(j)] += Y[(long)bpos[j] * nb + j];
+    for (int o = 16; o > 0; o >>= 1)
+        for (int g = 0; g < 3; ++g) t[g] += __shfl_xor_sync(0xffffffffu, t[g], o);
+    if ((tid & 31) == 0)
+        for (int g = 0; g < 3; ++g) red[g][tid >> 5] = t[g];
     __syncthreads();
     if (tid == 0) {
-        double a = 0.0, b = 0.0;
-        for (int w = 0; w < (blockDim.x + 31) / 32; ++w) { a += red[0][w]; b += red[1][w]; }
-        const int nbu = nb - nbs;
-        const double su = (nbs > 0 && nbu > 0 && a > 0.0 && b > 0.0) ? sqrt((a / nbs) / (b / nbu)) : 1.0;
-        const double tr = a + su * su * b;
-        s_su = su;
+        const int cnt[3] = {nbs, nbu, nb - nbs - nbu};
+        double mean[3], tr = 0.0, ref = 0.0;
+        for (int g = 0; g < 3; ++g) {
+            double a = 0.0;
+            for (int w = 0; w < (blockDim.x + 31) / 32; ++w) a += red[g][w];
+            mean[g] = cnt[g] > 0 ? a / cnt[g] : 0.0;
+            if (ref == 0.0 && mean[g] > 0.0) ref = mean[g];
+        }
+        for (int g = 0; g < 3; ++g) {
+            s_sc[g] = (mean[g] > 0.0 && ref > 0.0) ? sqrt(ref / mean[g]) : 1.0;
+            tr += s_sc[g] * s_sc[g] * mean[g] * cnt[g];
+        }
         s_rho = (tr > 0.0) ? (double)nb / tr : 1.0;
         rho2[c] = s_rho;
     }
     __syncthreads();
-    const double rho = s_rho, su = s_su;
+    const double rho = s_rho;
     for (int j = tid; j < nb; j += blockDim.x) {
-        const double r = j < nbs ? 1.0 : su;
+        const double r = s_sc[group(j)];
         const double l = r * blo[j], h = r * bhi[j];
         rs[(long)c * nb + j] = r;
         lo[(long)c * nb + j] = l;
@@ -267,17 +272,16 @@ k_lam_rho(int nf, int nb, int nbs, const int *__restrict__ bpos, const double *_
         if (isfinite(h)) bm = fmax(bm, fabs(h));
     }
     for (int o = 16; o > 0; o >>= 1) bm = fmax(bm, __shfl_xor_sync(0xffffffffu, bm, o));
-    if ((tid & 31) == 0) red[2][tid >> 5] = bm;
+    if ((tid & 31) == 0) red[3][tid >> 5] = bm;
     __syncthreads();
     if (tid == 0) {
         double m = 0.0;
-        for (int w = 0; w < (blockDim.x + 31) / 32; ++w) m = fmax(m, red[2][w]);
+        for (int w = 0; w < (blockDim.x + 31) / 32; ++w) m = fmax(m, red[3][w]);
         bmax[c] = m;
     }
     for (int e = tid; e < nb * nb; e += blockDim.x) {
         const int i = e / nb, j = e % nb;
-        const double sc = (i < nbs ? 1.0 : su) * (j < nbs ? 1.0 : su);
-        const double v = sc * 0.5 * (Y[(long)bpos[i] * nb + j] + Y[(long)bpos[j] * nb + i]);
+        const double v = s_sc[group(i)] * s_sc[group(j)] * 0.5 * (Y[(long)bpos[i] * nb + j] + Y[(long)bpos[j] * nb + i]);
         Lam[e] = v;
         Mm[e] = rho * v + (i == j ? 1.0 : 0.0);
     }
@@ -340,7 +344,8 @@ static Dims make_dims(const ddmpc_params &q) {
     d.nth = q.n * (q.m + q.p) + q.m + q.p;
     d.nbs = d.convex ? q.L * q.p : 0;
     d.nbu = (q.u_min || q.u_max) ? (d.terminal ? (q.L - q.n) * q.m : q.L * q.m) : 0;
-    d.nb = d.nbs + d.nbu;
+    d.nby = (q.y_min || q.y_max) ? (d.terminal ? (q.L - q.n) * q.p : q.L * q.p) : 0;
+    d.nb = d.nbs + d.nbu + d.nby;
     d.Lm = q.L * q.m;
     return d;
 }
@@ -358,13 +363,18 @@ static int validate(const ddmpc_params &q) {
         return fail(DDMPC_ERR_ROBUST_PARAMS,
                     "All robust MPC parameters (eps_max, lamb_alpha, lamb_sigma, c) must be provided for a "
                     "'ROBUST' controller.");
-    if (q.u_min || q.u_max) {
+    if (q.u_min || q.u_max || q.y_min || q.y_max) {
         if (q.controller_type != DDMPC_ROBUST)
-            return fail(DDMPC_ERR_NOT_IMPLEMENTED, "The input box constraint is only implemented for 'ROBUST' controllers.");
-        for (int j = 0; j < q.m; ++j) {
+            return fail(DDMPC_ERR_NOT_IMPLEMENTED, "The input / output box constraints are only implemented for 'ROBUST' controllers.");
+        for (int j = 0; j < q.m && (q.u_min || q.u_max); ++j) {
             const double l = q.u_min ? q.u_min[j] : -INFINITY, h = q.u_max ? q.u_max[j] : INFINITY;
             if (std::isnan(l) || std::isnan(h) || l > h)
                 return fail(DDMPC_ERR_INVALID_ARG, "input box: u_min[%d] = %g must not exceed u_max[%d] = %g", j, l, j, h);
+        }
+        for (int j = 0; j < q.p && (q.y_min || q.y_max); ++j) {
+            const double l = q.y_min ? q.y_min[j] : -INFINITY, h = q.y_max ? q.y_max[j] : INFINITY;
+            if (std::isnan(l) || std::isnan(h) || l > h)
+                return fail(DDMPC_ERR_INVALID_ARG, "output box: y_min[%d] = %g must not exceed y_max[%d] = %g", j, l, j, h);
         }
     }
     return DDMPC_OK;
@@ -458,7 +468,7 @@ static int build_robust(cudaStream_t st, Plan &pl, const FillArgs &fa, const int
         k_fill_Bt<<<g, 256, 0, st>>>(nf, nb, bpos_d, Y.d(), (long)nf * nb);
         DDMPC_LAUNCH_CHECK();
         DDMPC_TRY(potrs(st, C, nf, nb, P.d(), nx, sP, Y.d(), nb, (long)nf * nb));
-        k_lam_rho<<<C, 256, 0, st>>>(nf, nb, d.nbs, bpos_d, Y.d(), (long)nf * nb, pl.blo.d(), pl.bhi.d(), pl.Lam.d(),
+        k_lam_rho<<<C, 256, 0, st>>>(nf, nb, d.nbs, d.nbu, bpos_d, Y.d(), (long)nf * nb, pl.blo.d(), pl.bhi.d(), pl.Lam.d(),
                                      Mm.d(), pl.rho2.d(), pl.rs.d(), pl.lo.d(), pl.hi.d(), pl.bmax.d());
         DDMPC_LAUNCH_CHECK();
         DDMPC_TRY(potrf(st, C, nb, Mm.d(), nb, (long)nb * nb, info_d + 2 * C));
@@ -607,7 +617,7 @@ int set_create_device(const ddmpc_params *prm, int count, const double *u_d, siz
 
     std::unique_ptr<ddmpc_set> set(new ddmpc_set());
     set->prm = q;
-    set->prm.u_min = set->prm.u_max = nullptr;   // caller memory: the plan keeps its own copy
+    set->prm.u_min = set->prm.u_max = set->prm.y_min = set->prm.y_max = nullptr;   // caller memory: the plan keeps its own copy
     Plan &pl = set->plan;
     pl.d = make_dims(q);
     pl.count = count;
@@ -665,6 +675,7 @@ int set_create_device(const ddmpc_params *prm, int count, const double *u_d, siz
         for (int k = 0; k < d.nx; ++k) invperm[perm[k]] = k;
         for (int j = 0; j < d.nbs; ++j) bpos[j] = invperm[d.nu + d.ny + q.n * q.p + j];   // sigma_pred
         for (int j = 0; j < d.nbu; ++j) bpos[d.nbs + j] = invperm[q.n * q.m + j];          // free predicted inputs
+        for (int j = 0; j < d.nby; ++j) bpos[d.nbs + d.nbu + j] = invperm[d.nu + q.n * q.p + j];   // free predicted outputs
     }
     DevBuf perm_d, invperm_d, bpos_d, info_d;
     DDMPC_CUDA(perm_d.alloc(sizeof(int) * d.nx));
@@ -712,6 +723,21 @@ int set_create_device(const ddmpc_params *prm, int count, const double *u_d, siz
         for (int j = 0; j < d.nbu; ++j) {
             blo[d.nbs + j] = q.u_min ? q.u_min[j % q.m] : -INFINITY;
             bhi[d.nbs + j] = q.u_max ? q.u_max[j % q.m] : INFINITY;
+        }
+        for (int j = 0; j < d.nby; ++j) {
+            blo[d.nbs + d.nbu + j] = q.y_min ? q.y_min[j % q.p] : -INFINITY;
+            bhi[d.nbs + d.nbu + j] = q.y_max ? q.y_max[j % q.p] : INFINITY;
+        }
+        if (d.nby > 0) {
+            std::vector<double> yl(q.p, -INFINITY), yh(q.p, INFINITY);
+            for (int j = 0; j < q.p; ++j) {
+                if (q.y_min) yl[j] = q.y_min[j];
+                if (q.y_max) yh[j] = q.y_max[j];
+            }
+            DDMPC_CUDA(pl.ymin.alloc(sizeof(double) * q.p));
+            DDMPC_CUDA(pl.ymax.alloc(sizeof(double) * q.p));
+            DDMPC_CUDA(cudaMemcpy(pl.ymin.p, yl.data(), sizeof(double) * q.p, cudaMemcpyHostToDevice));
+            DDMPC_CUDA(cudaMemcpy(pl.ymax.p, yh.data(), sizeof(double) * q.p, cudaMemcpyHostToDevice));
         }
         DDMPC_CUDA(pl.blo.alloc(sizeof(double) * d.nb));
         DDMPC_CUDA(pl.bhi.alloc(sizeof(double) * d.nb));

@@ -24,21 +24,27 @@ struct KArgs {
     const double *Ku, *Z, *Ks, *Phi, *Psi, *Lam, *rho2, *F, *X0, *Yf;
     const double *lo, *hi, *bmax;    // per controller: scaled bounds of the box rows (nb), largest finite |bound|
     const double *umin, *umax;       // input box (m) or NULL
+    const double *ymin, *ymax;       // output box (p) or NULL
     int terminal;
     double tol;
     int max_iter;
 };
 
-// Terminal equality + input box: the last n predicted inputs are fixed to u_s, so the QP is infeasible when u_s
-// itself violates the box (cvxpy would report "infeasible").
+// Terminal equality + input / output box: the last n predicted inputs (outputs) are fixed to u_s (y_s), so the QP is
+// infeasible when the set-point itself violates the box (cvxpy would report "infeasible").
 __device__ __forceinline__ bool setpoint_outside_box(const KArgs &a, const double *th, int TS, int tid) {
-    if (!a.umin || !a.terminal) return false;
+    if (!a.terminal || (!a.umin && !a.ymin)) return false;
     const int o = a.n * (a.m + a.p);
     bool bad = false;
-    for (int j = 0; j < a.m; ++j) {
+    for (int j = 0; j < a.m && a.umin; ++j) {
         const double v = th[(size_t)(o + j) * TS + tid];
         const double sl = 1e-9 * (1.0 + fabs(v));
         bad = bad || v < a.umin[j] - sl || v > a.umax[j] + sl;
+    }
+    for (int j = 0; j < a.p && a.ymin; ++j) {
+        const double v = th[(size_t)(o + a.m + j) * TS + tid];
+        const double sl = 1e-9 * (1.0 + fabs(v));
+        bad = bad || v < a.ymin[j] - sl || v > a.ymax[j] + sl;
     }
     return bad;
 }
@@ -597,6 +603,7 @@ static KArgs make_kargs(const ddmpc_set *set, double tol, int max_iter) {
     a.F = d.robust ? nullptr : pl.F.d();
     a.lo = pl.lo.d(); a.hi = pl.hi.d(); a.bmax = pl.bmax.d();
     a.umin = d.nbu > 0 ? pl.umin.d() : nullptr; a.umax = d.nbu > 0 ? pl.umax.d() : nullptr;
+    a.ymin = d.nby > 0 ? pl.ymin.d() : nullptr; a.ymax = d.nby > 0 ? pl.ymax.d() : nullptr;
     a.terminal = d.terminal;
     a.tol = tol > 0.0 ? tol : 1e-8;
     a.max_iter = max_iter > 0 ? max_iter : 1000;

@@ -75,6 +75,9 @@ typedef struct {
      * creation; NULL / NULL (the default) leaves the problem exactly as the reference states it.  Entries may
      * be -inf / +inf.  ROBUST controllers only (DDMPC_ERR_NOT_IMPLEMENTED for NOMINAL). */
     const double *u_min, *u_max;
+    /* Optional output box y_min <= ybar[k] <= y_max on every predicted output (paper Eq. 6, y in Y), same
+     * conventions: HOST pointers to p values each, NULL / NULL = as the reference, ROBUST only. */
+    const double *y_min, *y_max;
 } ddmpc_params;
 
 /* LTI plant of utilities/model_simulation.py:31-98, row-major host arrays. */

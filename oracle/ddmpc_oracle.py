@@ -207,10 +207,10 @@ class OracleQP:
 
     def __init__(self, n, m, p, u_d, y_d, L, Q, R, eps_max=None, lamb_alpha=None,
                  lamb_sigma=None, c=None, slack_type=SLACK_CONVEX, ctrl_type=NOMINAL,
-                 use_terminal=True, cache_factor=True, input_bounds=None):
-        """input_bounds = (u_min, u_max): optional box on every predicted input ubar[n*m:] (paper Eq. 6, u in U).
-        NOT in the reference (its constraint list, controller.py:447-504, has no such entry): an extension that
-        only the oracle pins, off by default."""
+                 use_terminal=True, cache_factor=True, input_bounds=None, output_bounds=None):
+        """input_bounds = (u_min, u_max) / output_bounds = (y_min, y_max): optional boxes on every predicted input
+        ubar[n*m:] / output ybar[n*p:] (paper Eq. 6, u in U, y in Y).  NOT in the reference (its constraint list,
+        controller.py:447-504, has no such entry): extensions that only the oracle pins, off by default."""
         if slack_type == SLACK_NON_CONVEX and ctrl_type == ROBUST:
             raise NotImplementedError("NON_CONVEX slack constraint (controller.py:664-670)")
         self.n, self.m, self.p, self.L = n, m, p, L
@@ -248,6 +248,18 @@ class OracleQP:
             self.u_box = (bl, bh)
             for i in range((L - n) * m if use_terminal else L * m):     # terminal blocks are equalities
                 idx.append(self.o_u + n * m + i); lo.append(bl[i % m]); hi.append(bh[i % m])
+        self.y_box = None
+        if output_bounds is not None:
+            if not self.robust:
+                raise NotImplementedError("output box: ROBUST controllers only")
+            bl, bh = output_bounds
+            bl = np.full(p, -np.inf) if bl is None else np.broadcast_to(np.asarray(bl, float).reshape(-1), (p,))
+            bh = np.full(p, np.inf) if bh is None else np.broadcast_to(np.asarray(bh, float).reshape(-1), (p,))
+            if np.any(bl > bh):
+                raise ValueError("output box: y_min must not exceed y_max")
+            self.y_box = (bl, bh)
+            for i in range((L - n) * p if use_terminal else L * p):     # terminal blocks are equalities
+                idx.append(self.o_y + n * p + i); lo.append(bl[i % p]); hi.append(bh[i % p])
         self.ineq_idx, self.ineq_lo, self.ineq_hi = np.array(idx, int), np.array(lo, float), np.array(hi, float)
         self._cache_factor = cache_factor
         self._lu = None
@@ -331,6 +343,10 @@ class OracleQP:
             us = np.reshape(u_s, (-1,))
             if np.any(us < self.u_box[0] - 1e-9 * (1 + np.abs(us))) or np.any(us > self.u_box[1] + 1e-9 * (1 + np.abs(us))):
                 return QPSolution(status="infeasible")             # terminal equality ubar = u_s violates the box
+        if self.y_box is not None and self.use_terminal:
+            ysv = np.reshape(y_s, (-1,))
+            if np.any(ysv < self.y_box[0] - 1e-9 * (1 + np.abs(ysv))) or np.any(ysv > self.y_box[1] + 1e-9 * (1 + np.abs(ysv))):
+                return QPSolution(status="infeasible")             # terminal equality ybar = y_s violates the box
         if self.ineq_idx.size:
             zi, lo, hi = self.ineq_idx, self.ineq_lo, self.ineq_hi
             nb = zi.size
@@ -448,7 +464,8 @@ class OracleQP:
 class OracleController:
     def __init__(self, n, m, p, u_d, y_d, L, Q, R, u_s, y_s, eps_max=None, lamb_alpha=None,
                  lamb_sigma=None, c=None, slack_type=SLACK_CONVEX, ctrl_type=NOMINAL,
-                 n_mpc_step=1, use_terminal=True, cache_factor=True, check_pe=True, input_bounds=None):
+                 n_mpc_step=1, use_terminal=True, cache_factor=True, check_pe=True, input_bounds=None,
+                 output_bounds=None):
         self.n, self.m, self.p, self.L = n, m, p, L
         self.u_s, self.y_s, self.n_mpc_step = u_s, y_s, n_mpc_step
         N = u_d.shape[0]
@@ -460,7 +477,7 @@ class OracleController:
             if not ok:
                 raise ValueError("not persistently exciting")
         self.qp = OracleQP(n, m, p, u_d, y_d, L, Q, R, eps_max, lamb_alpha, lamb_sigma, c,
-                           slack_type, ctrl_type, use_terminal, cache_factor, input_bounds)
+                           slack_type, ctrl_type, use_terminal, cache_factor, input_bounds, output_bounds)
         self.u_past = u_d[-n:, :].reshape(-1, 1)          # controller.py:184
         self.y_past = y_d[-n:, :].reshape(-1, 1)          # controller.py:185
         self.solution: Optional[QPSolution] = None
@@ -517,7 +534,7 @@ def make_controller(params: Dict, u_d, y_d, **over) -> OracleController:
         y_s=kw["y_s"], eps_max=kw["eps_max"], lamb_alpha=kw["lamb_alpha"], lamb_sigma=kw["lamb_sigma"],
         c=kw["c"], slack_type=kw["slack_type"], ctrl_type=kw["ctrl_type"], n_mpc_step=kw["n_mpc_step"],
         use_terminal=kw.get("use_terminal", True), cache_factor=kw.get("cache_factor", True),
-        input_bounds=kw.get("input_bounds"))
+        input_bounds=kw.get("input_bounds"), output_bounds=kw.get("output_bounds"))
 
 
 def example_scenario(seed: int, params: Optional[Dict] = None, plant: Optional[Plant] = None):

@@ -33,7 +33,7 @@ def theta_layout(n, m, p):
 
 
 def build_plan(n, m, p, u_d, y_d, L, Q, R, eps_max, lamb_alpha, lamb_sigma, c, slack_type,
-               ctrl_type, use_terminal, rank_tol=1e-11, input_bounds=None):
+               ctrl_type, use_terminal, rank_tol=1e-11, input_bounds=None, output_bounds=None):
     Lp = L + n
     nu, ny = Lp * m, Lp * p
     H = np.vstack([hankel(u_d, Lp), hankel(y_d, Lp)])
@@ -108,7 +108,7 @@ def build_plan(n, m, p, u_d, y_d, L, Q, R, eps_max, lamb_alpha, lamb_sigma, c, s
         pl.Z = 0.5 * (pl.Z + pl.Z.T)
         pl.feasF = None
         pl.nb = 0
-        if pl.convex or input_bounds is not None:
+        if pl.convex or input_bounds is not None or output_bounds is not None:
             # box rows: sigma_pred (CONVEX) then the free predicted inputs (input box), as in setup.cu
             pos = {g: i for i, g in enumerate(free)}
             rows, lo, hi = [], [], []
@@ -122,6 +122,12 @@ def build_plan(n, m, p, u_d, y_d, L, Q, R, eps_max, lamb_alpha, lamb_sigma, c, s
                 bh = np.broadcast_to(np.asarray(np.inf if input_bounds[1] is None else input_bounds[1], float).reshape(-1), (m,))
                 for j in range((L - n) * m if use_terminal else L * m):
                     rows.append(n * m + j); lo.append(bl[j % m]); hi.append(bh[j % m])
+            nbu_end = len(rows)
+            if output_bounds is not None:
+                bl = np.broadcast_to(np.asarray(-np.inf if output_bounds[0] is None else output_bounds[0], float).reshape(-1), (p,))
+                bh = np.broadcast_to(np.asarray(np.inf if output_bounds[1] is None else output_bounds[1], float).reshape(-1), (p,))
+                for j in range((L - n) * p if use_terminal else L * p):
+                    rows.append(nu + n * p + j); lo.append(bl[j % p]); hi.append(bh[j % p])
             nb = len(rows)
             bidx = np.array([pos[g] for g in rows])
             Bsel = np.zeros((nb, len(free)))
@@ -129,9 +135,10 @@ def build_plan(n, m, p, u_d, y_d, L, Q, R, eps_max, lamb_alpha, lamb_sigma, c, s
             Y = sla.cho_solve((La, True), Bsel.T)       # A^-1 B^T
             Lam = Bsel @ Y
             dg = np.diag(Lam)
-            rs = np.ones(nb)
-            if 0 < nbs < nb:
-                rs[nbs:] = np.sqrt(dg[:nbs].mean() / dg[nbs:].mean())
+            rs = np.ones(nb)                            # group equilibration as in k_lam_rho (first non-empty group = 1)
+            groups = [g for g in (slice(0, nbs), slice(nbs, nbu_end), slice(nbu_end, nb)) if g.stop > g.start]
+            for g in groups[1:]:
+                rs[g] = np.sqrt(dg[groups[0]].mean() / dg[g].mean())
             Y = Y * rs[None, :]
             Lam = rs[:, None] * (0.5 * (Lam + Lam.T)) * rs[None, :]
             rho2 = nb / np.trace(Lam)                   # rho/2

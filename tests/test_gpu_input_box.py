@@ -15,13 +15,13 @@ def _plant():
     return LTIPlant(**{k: O.FOUR_TANK[k] for k in "ABCD"}, eps_max=0.002)
 
 
-def _pair(slack, term, box, n_mpc=1, seed=0, c=1.0):
+def _pair(slack, term, box, n_mpc=1, seed=0, c=1.0, ybox=None):
     from direct_data_driven_mpc_b200 import ControllerSet
     plant, prm, rng, x0, u_d, y_d = O.example_scenario(seed)
     cs = ControllerSet(4, 2, 2, u_d, y_d, 30, prm["Q"], prm["R"], prm["eps_max"], prm["lamb_alpha"],
-                       prm["lamb_sigma"], c, slack, 1, n_mpc, term, input_bounds=box)
+                       prm["lamb_sigma"], c, slack, 1, n_mpc, term, input_bounds=box, output_bounds=ybox)
     qp = O.OracleQP(4, 2, 2, u_d, y_d, 30, prm["Q"], prm["R"], prm["eps_max"], prm["lamb_alpha"], prm["lamb_sigma"],
-                    c, slack, O.ROBUST, term, input_bounds=box)
+                    c, slack, O.ROBUST, term, input_bounds=box, output_bounds=ybox)
     return cs, qp, prm, u_d, y_d, plant
 
 
@@ -127,3 +127,39 @@ def test_controller_class_with_input_box():
     assert ctrl.get_problem_solve_status() == "optimal" and ctrl.solver_iterations >= 1
     assert np.abs(u_g - u_ref).max() / np.abs(u_ref).max() < 1e-5
     assert u_g.max() <= 5.0 + 1e-6
+
+
+@pytest.mark.parametrize("slack,ub,yb", [(0, None, (None, [0.66, 0.775])), (1, (-3.0, 5.0), (0.0, [0.68, 0.79])),
+                                         (0, (-3.0, [5.0, 4.0]), ([0.1, 0.1], None))])
+def test_output_box_solves_and_closed_loop_vs_oracle(slack, ub, yb):
+    """Output box on ybar (alone / with the input box / with the CONVEX slack bound): batched solve and a closed loop."""
+    cs, qp, prm, u_d, y_d, plant_o = _pair(slack, True, ub, n_mpc=4, ybox=yb)
+    B = 6
+    r = np.random.default_rng(9)
+    up, yp = np.tile(u_d[-4:].reshape(1, -1), (B, 1)), np.tile(y_d[-4:].reshape(1, -1), (B, 1))
+    us = prm["u_s"].reshape(1, -1) * r.uniform(0.97, 1.0, (B, 1))
+    ys = prm["y_s"].reshape(1, -1) * r.uniform(0.97, 1.0, (B, 1))
+    u, cost, st, it = cs.solve_batch(up, yp, us, ys, tol=1e-8, max_iter=50000)
+    assert int(st.max()) == 0 and int(it.max()) > 1
+    n_act = 0
+    for b in range(B):
+        so = qp.solve(up[b], yp[b], us[b], ys[b])
+        n_act += so.n_active
+        assert np.abs(u[b].cpu().numpy() - so.optimal_u).max() / max(1.0, np.abs(so.optimal_u).max()) < 1e-5, b
+        assert abs(float(cost[b]) - so.cost) <= 1e-5 * max(1.0, abs(so.cost))
+    assert n_act > 0
+    n_steps = 41
+    xs = np.tile(plant_o.x, (2, 1))
+    w = 0.002 * r.uniform(-1, 1, (2, n_steps, 2))
+    uu, yy, st, _ = cs.closed_loop(_plant(), xs, up[:2], yp[:2], np.tile(prm["u_s"].T, (2, 1)), np.tile(prm["y_s"].T, (2, 1)),
+                                   n_steps, w=w, max_iter=50000)
+    assert int(st.max()) == 0
+    po = O.four_tank_plant()
+    po.x = xs[1].copy()
+    ctrl = O.make_controller(prm, u_d, y_d, n_mpc_step=4, slack_type=slack, input_bounds=ub, output_bounds=yb)
+    u_ref, y_ref = O.closed_loop(po, ctrl, n_steps, w[1])
+    assert np.abs(uu[1].cpu().numpy() - u_ref).max() / np.abs(u_ref).max() < 1e-5
+    # set-point outside the output box with the terminal equality: infeasible
+    cs2, qp2, *_ = _pair(0, True, None, ybox=(None, 0.5))
+    _, _, st2, _ = cs2.solve_batch(up[:1], yp[:1], prm["u_s"].T, prm["y_s"].T)
+    assert int(st2[0]) == 2

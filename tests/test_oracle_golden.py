@@ -181,6 +181,32 @@ def test_input_box_condensed_admm_equals_oracle_active_set(slack, term, box):
     assert n_bind > 0                                   # the box really binds in these cases
 
 
+@pytest.mark.parametrize("slack,ub,yb", [(0, None, (None, [0.66, 0.775])), (1, (-3.0, 5.0), (0.0, [0.68, 0.79])),
+                                         (0, (-3.0, [5.0, 4.0]), ([0.1, 0.1], None))])
+def test_output_box_condensed_admm_equals_oracle_active_set(slack, ub, yb):
+    """Output box on ybar (paper Eq. 6, y in Y; an extension), alone and together with the input box and the CONVEX
+    slack bound: three row groups, equilibrated as in k_lam_rho; condensed ADMM == oracle active set."""
+    plant, prm, rng, x0, u_d, y_d = O.example_scenario(0)
+    qp = O.OracleQP(4, 2, 2, u_d, y_d, 30, prm["Q"], prm["R"], prm["eps_max"], prm["lamb_alpha"], prm["lamb_sigma"], 1.0,
+                    slack, O.ROBUST, True, input_bounds=ub, output_bounds=yb)
+    pl = CN.build_plan(4, 2, 2, u_d, y_d, 30, prm["Q"], prm["R"], prm["eps_max"], prm["lamb_alpha"], prm["lamb_sigma"], 1.0,
+                       slack, CN.ROBUST, True, input_bounds=ub, output_bounds=yb)
+    so = qp.solve(u_d[-4:].reshape(-1, 1), y_d[-4:].reshape(-1, 1), prm["u_s"], prm["y_s"])
+    u, cost, st, it = CN.solve(pl, CN.make_theta(4, 2, 2, u_d[-4:], y_d[-4:], prm["u_s"], prm["y_s"]), tol=1e-10, max_iter=50000)
+    assert st == "optimal" and so.status == "optimal" and so.n_active > 0
+    yfree = so.ybar[8:8 + 52].reshape(-1, 2)
+    if yb[1] is not None:
+        assert np.all(yfree <= np.asarray(yb[1]) + 1e-9)
+    if yb[0] is not None:
+        assert np.all(yfree >= np.asarray(yb[0]) - 1e-9)
+    assert np.abs(u - so.optimal_u).max() <= 1e-7 * max(1.0, np.abs(so.optimal_u).max())
+    assert abs(cost - so.cost) <= 1e-7 * max(1.0, abs(so.cost))
+    # terminal equality ybar = y_s outside the output box: infeasible
+    qp2 = O.OracleQP(4, 2, 2, u_d, y_d, 30, prm["Q"], prm["R"], prm["eps_max"], prm["lamb_alpha"], prm["lamb_sigma"], 1.0,
+                     slack, O.ROBUST, True, output_bounds=(None, 0.5))
+    assert qp2.solve(u_d[-4:].reshape(-1, 1), y_d[-4:].reshape(-1, 1), prm["u_s"], prm["y_s"]).status == "infeasible"
+
+
 def test_input_box_infeasible_setpoint_and_nominal():
     plant, params, rng, x0, u_d, y_d = O.example_scenario(0)
     prm = O.four_tank_params()
