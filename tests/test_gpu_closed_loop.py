@@ -464,3 +464,35 @@ def test_closed_loop_host_matches_device_api(chunks):
                                              chunks=chunks, **kw)
             assert hu.is_pinned() and tuple(hu.shape) == (B, n_steps, 2) and int(hs.max()) == 0
             assert _rel(hu.numpy(), u1.cpu().numpy()) < 1e-9 and _rel(hy.numpy(), y1.cpu().numpy()) < 1e-9
+
+
+def test_fused_kernels_are_run_to_run_deterministic():
+    """Every fused kernel, run three times on the same inputs, must return bit-identical trajectories: the warp-
+    specialised kernel rotates shared-memory buffers between warps and the config-4 kernel rotates a ring in place, so
+    a missing barrier would show up as run-to-run differences (compute-sanitizer is not available on the GPU pool)."""
+    import torch
+    from direct_data_driven_mpc_b200 import ControllerSet, scenarios as S
+    plant_o, prm, rng, x0, u_d, y_d = O.example_scenario(0)
+    r = np.random.default_rng(2)
+    B = 16384 + 9
+    xs = np.tile(plant_o.x, (B, 1)) + 0.05 * r.normal(size=(B, 4))
+    t = lambda a, b=B: np.tile(np.asarray(a).reshape(1, -1), (b, 1))
+    runs = []
+    cs, _ = _set(u_d, y_d)                                         # warp-specialised all-tensor-core kernel
+    runs.append(lambda: cs.closed_loop(_plant(), xs, t(u_d[-4:]), t(y_d[-4:]), t(prm["u_s"]), t(prm["y_s"]), 45,
+                                       noise_seed=7, noise_eps=0.002))
+    cc, _ = _set(u_d, y_d, slack=1, c=0.3)                         # fused CONVEX kernel with active bounds
+    runs.append(lambda: cc.closed_loop(_plant(), xs, t(u_d[-4:]), t(y_d[-4:]), t(prm["u_s"]), t(prm["y_s"]), 13,
+                                       noise_seed=7, noise_eps=0.002))
+    for n_mpc in (1, 20):                                          # config-4 fused DMMA kernel, both shapes
+        sc = S.config4_batch(520, n_mpc_step=n_mpc)
+        p4 = sc["params"]
+        c4 = ControllerSet(20, 4, 4, sc["u_d"], sc["y_d"], 40, p4["Q"], p4["R"], p4["eps_max"], p4["lamb_alpha"],
+                           p4["lamb_sigma"], p4["c"], 0, 1, n_mpc, True)
+        runs.append(lambda c4=c4, sc=sc: c4.closed_loop(sc["plant"], sc["x0"], sc["u_past0"], sc["y_past0"], sc["u_s"],
+                                                        sc["y_s"], 47, noise_seed=3, noise_eps=0.002))
+    for k, fn in enumerate(runs):
+        u0, y0, s0, i0 = fn()
+        for _ in range(2):
+            u1, y1, s1, i1 = fn()
+            assert torch.equal(u0, u1) and torch.equal(y0, y1) and torch.equal(i0, i1), k
