@@ -496,3 +496,34 @@ def test_fused_kernels_are_run_to_run_deterministic():
         for _ in range(2):
             u1, y1, s1, i1 = fn()
             assert torch.equal(u0, u1) and torch.equal(y0, y1) and torch.equal(i0, i1), k
+
+
+@pytest.mark.parametrize("name,ctype,slack,term,n_mpc,n_steps,tol", [
+    ("ROBUST TEC n-step", 1, 0, True, 4, 401, 1e-6), ("ROBUST TEC 1-step", 1, 0, True, 1, 101, 1e-6),
+    ("ROBUST UCON 1-step", 1, 0, False, 1, 101, 1e-6), ("ROBUST CONVEX n-step", 1, 1, True, 4, 201, 1e-5),
+    ("NOMINAL 1-step", 0, 0, True, 1, 41, 1e-5)])
+def test_config2_per_seed_variants_vs_oracle(name, ctype, slack, term, n_mpc, n_steps, tol):
+    """BASELINE config 2 parity sample: loop b = the example script with `--seed b` - its own data, hence
+    its own controller, and the measurement noise its generator draws next - for b < 32 and every controller
+    variant, batched through ControllerSet(count=32) + ctrl_idx against the oracle."""
+    from direct_data_driven_mpc_b200 import ControllerSet
+    B = 32
+    prm = O.four_tank_params()
+    data = [O.example_scenario(s) for s in range(B)]              # (plant, params, rng, x0, u_d, y_d); rng continues
+    ud, yd = np.stack([d[4] for d in data]), np.stack([d[5] for d in data])
+    xs = np.stack([d[0].x for d in data])
+    w = np.stack([0.002 * d[2].uniform(-1.0, 1.0, (n_steps, 2)) for d in data])      # controller_operation.py:263
+    robust = ctype == 1
+    cs = ControllerSet(4, 2, 2, ud, yd, 30, prm["Q"], prm["R"], prm["eps_max"] if robust else None,
+                       prm["lamb_alpha"] if robust else None, prm["lamb_sigma"] if robust else None, 1.0 if robust else None,
+                       slack, ctype, n_mpc, term)
+    assert (cs.statuses() == 0).all()
+    u, y, st, it = cs.closed_loop(_plant(), xs, ud[:, -4:].reshape(B, -1), yd[:, -4:].reshape(B, -1),
+                                  np.tile(prm["u_s"].T, (B, 1)), np.tile(prm["y_s"].T, (B, 1)), n_steps, w=w,
+                                  ctrl_idx=np.arange(B))
+    u, y = u.cpu().numpy(), y.cpu().numpy()
+    assert int(st.max()) == 0, name
+    for b in range(B):
+        ctrl = O.make_controller(prm, ud[b], yd[b], n_mpc_step=n_mpc, use_terminal=term, slack_type=slack, ctrl_type=ctype)
+        u_ref, y_ref = O.closed_loop(data[b][0], ctrl, n_steps, w[b])
+        assert _rel(u[b], u_ref) < tol and _rel(y[b], y_ref) < tol, (name, b, _rel(u[b], u_ref))
