@@ -154,3 +154,29 @@ def test_solve_batch_large_batch_kernel_matches_small_batch_kernel(slack, c):
     for b in (0, 77, 199):
         so = qp.solve(up[b], yp[b], us[b], ys[b])
         assert np.abs(u_big[b].cpu().numpy() - so.optimal_u).max() < 1e-5 * max(1.0, np.abs(so.optimal_u).max())
+
+
+@pytest.mark.parametrize("L", [8, 20, 60])
+def test_config5_lambda_horizon_grid_vs_oracle(L):
+    """BASELINE config 5 parity sample: corners of the lambda_alpha*eps x lambda_sigma grid at three horizons, one
+    controller per grid point built by one ControllerSet(count=...) call, every controller against its own oracle."""
+    from direct_data_driven_mpc_b200 import ControllerSet
+    plant, prm, rng, x0, u_d, y_d = O.example_scenario(0)
+    la = np.array([1e-3, 1e-3, 1e1, 1e1, 0.1]) / prm["eps_max"]
+    ls = np.array([1e1, 1e5, 1e1, 1e5, 1e3])
+    Q, R = 3.0 * np.eye(2 * L), 1e-4 * np.eye(2 * L)
+    cs = ControllerSet(4, 2, 2, u_d, y_d, L, Q, R, prm["eps_max"], la, ls, 1.0, 0, 1, 4, True, count=la.size)
+    assert (cs.statuses() == 0).all()
+    r = np.random.default_rng(L)
+    ks = r.integers(0, 396, la.size)
+    up = np.stack([u_d[k:k + 4].reshape(-1) for k in ks])
+    yp = np.stack([y_d[k:k + 4].reshape(-1) for k in ks])
+    us, ys = np.tile(prm["u_s"].T, (la.size, 1)), np.tile(prm["y_s"].T, (la.size, 1))
+    u, cost, st, _ = cs.solve_batch(up, yp, us, ys, ctrl_idx=np.arange(la.size))
+    assert int(st.max()) == 0
+    for c in range(la.size):
+        qp = O.OracleQP(4, 2, 2, u_d, y_d, L, Q, R, prm["eps_max"], la[c], ls[c], 1.0, O.SLACK_NONE, O.ROBUST, True)
+        so = qp.solve(up[c], yp[c], us[c], ys[c])
+        rel = np.abs(u[c].cpu().numpy() - so.optimal_u).max() / max(1.0, np.abs(so.optimal_u).max())
+        assert rel < 1e-7, (L, c, rel)
+        assert abs(float(cost[c]) - so.cost) <= 1e-6 * max(1.0, abs(so.cost))
