@@ -26,6 +26,7 @@ struct Dims {
 struct Plan {
     Dims d{};
     int count = 0;
+    int data_count = 0;   // 1 when every controller shares one (u_d, y_d): H, W, Om exist once (lambda sweeps), else count
     DevBuf H;      // (r, cols)      stacked Hankel [H_u; H_y]   (HLn_ud / HLn_yd)
     DevBuf Om;     // (r, r)         W^-1, W = H H^T             (robust; alpha recovery)
     DevBuf W;      // (r, r)         Gram matrix (kept for inspection)

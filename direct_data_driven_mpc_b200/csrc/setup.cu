@@ -408,7 +408,7 @@ static int build_robust(cudaStream_t st, Plan &pl, const FillArgs &fa, const int
     const int C = pl.count, r = d.r, nx = d.nx, nf = d.nf, nfix = d.nfix, nth = d.nth, nb = d.nb;
     const long sW = (long)r * r, sP = (long)nx * nx;
     DevBuf Lw, P, Cp, DTp, ZT, Nn, X0f, G1, Y, Mm;
-    DDMPC_CUDA(Lw.alloc(sizeof(double) * C * sW));
+    DDMPC_CUDA(Lw.alloc(sizeof(double) * pl.data_count * sW));
     DDMPC_CUDA(P.alloc(sizeof(double) * C * sP));
     DDMPC_CUDA(Cp.alloc(sizeof(double) * (size_t)nx * nth));
     DDMPC_CUDA(DTp.alloc(sizeof(double) * (size_t)nx * nth));
@@ -417,20 +417,23 @@ static int build_robust(cudaStream_t st, Plan &pl, const FillArgs &fa, const int
     DDMPC_CUDA(X0f.alloc(sizeof(double) * (size_t)C * nf * nth));
     DDMPC_CUDA(G1.alloc(sizeof(double) * (size_t)C * nfix * nth));
 
-    // W = H H^T ; Om = W^-1
+    // W = H H^T ; Om = W^-1.  With one data set shared by the whole set (lambda sweeps, BASELINE config 5) the Hankel
+    // stack, its Gram matrix, the Cholesky factor and the r x r inverse exist once instead of `count` times.
+    const int CW = pl.data_count;
+    const long sOm = CW == 1 ? 0 : sW;
     Mat Hm = mat(pl.H.d(), d.cols, 1, (long)r * d.cols);
-    DDMPC_TRY(gemm(st, C, r, r, d.cols, 1.0, Hm, tr(Hm), 0.0, pl.W.d(), r, 1, sW));
-    DDMPC_TRY(symmetrize(st, C, r, pl.W.d(), r, sW));
-    DDMPC_TRY(copy_bcast(st, C, sW, pl.W.d(), sW, Lw.d(), sW));
-    DDMPC_TRY(potrf(st, C, r, Lw.d(), r, sW, info_d));
-    DDMPC_TRY(set_identity(st, C, r, pl.Om.d(), r, sW));
-    DDMPC_TRY(potrs(st, C, r, r, Lw.d(), r, sW, pl.Om.d(), r, sW));
-    DDMPC_TRY(symmetrize(st, C, r, pl.Om.d(), r, sW));
+    DDMPC_TRY(gemm(st, CW, r, r, d.cols, 1.0, Hm, tr(Hm), 0.0, pl.W.d(), r, 1, sW));
+    DDMPC_TRY(symmetrize(st, CW, r, pl.W.d(), r, sW));
+    DDMPC_TRY(copy_bcast(st, CW, sW, pl.W.d(), sW, Lw.d(), sW));
+    DDMPC_TRY(potrf(st, CW, r, Lw.d(), r, sW, info_d));
+    DDMPC_TRY(set_identity(st, CW, r, pl.Om.d(), r, sW));
+    DDMPC_TRY(potrs(st, CW, r, r, Lw.d(), r, sW, pl.Om.d(), r, sW));
+    DDMPC_TRY(symmetrize(st, CW, r, pl.Om.d(), r, sW));
 
     // reduced Hessian (permuted [free; fixed]) and the theta maps
     {
         dim3 g(ceil_div(sP, 256), C);
-        k_fill_P<<<g, 256, 0, st>>>(fa, perm_d, Rd, Qd, pl.lamA.d(), pl.lamS.d(), pl.Om.d(), sW, P.d(), sP);
+        k_fill_P<<<g, 256, 0, st>>>(fa, perm_d, Rd, Qd, pl.lamA.d(), pl.lamS.d(), pl.Om.d(), sOm, P.d(), sP);
         DDMPC_LAUNCH_CHECK();
         k_fill_CDT<<<ceil_div((long)nx * nth, 256), 256, 0, st>>>(fa, perm_d, Rd, Qd, Cp.d(), DTp.d());
         DDMPC_LAUNCH_CHECK();
@@ -621,6 +624,7 @@ int set_create_device(const ddmpc_params *prm, int count, const double *u_d, siz
     Plan &pl = set->plan;
     pl.d = make_dims(q);
     pl.count = count;
+    pl.data_count = (ud_stride == 0 && yd_stride == 0) ? 1 : count;
     pl.pe_rank.assign(count, -1);
     pl.status.assign(count, DDMPC_OK);
     const Dims &d = pl.d;
@@ -704,15 +708,16 @@ int set_create_device(const ddmpc_params *prm, int count, const double *u_d, siz
 
     // operator storage
     const size_t C = count;
-    DDMPC_CUDA(pl.H.alloc(sizeof(double) * C * d.r * d.cols));
+    const size_t CD = pl.data_count;
+    DDMPC_CUDA(pl.H.alloc(sizeof(double) * CD * d.r * d.cols));
     DDMPC_CUDA(pl.Ku.alloc(sizeof(double) * C * d.Lm * d.nth));
     DDMPC_CUDA(pl.Z.alloc(sizeof(double) * C * d.nth * d.nth));
     DDMPC_CUDA(pl.X0.alloc(sizeof(double) * C * d.nx * d.nth));
     DDMPC_CUDA(pl.rho2.alloc(sizeof(double) * C));
     DDMPC_CUDA(cudaMemsetAsync(pl.rho2.p, 0, sizeof(double) * C, st));
     if (d.robust) {
-        DDMPC_CUDA(pl.W.alloc(sizeof(double) * C * d.r * d.r));
-        DDMPC_CUDA(pl.Om.alloc(sizeof(double) * C * d.r * d.r));
+        DDMPC_CUDA(pl.W.alloc(sizeof(double) * CD * d.r * d.r));
+        DDMPC_CUDA(pl.Om.alloc(sizeof(double) * CD * d.r * d.r));
     } else {
         DDMPC_CUDA(pl.F.alloc(sizeof(double) * C * d.nfix * d.nth));
     }
@@ -769,8 +774,8 @@ int set_create_device(const ddmpc_params *prm, int count, const double *u_d, siz
 
     // K1: Hankel matrices H_{L+n}(u^d), H_{L+n}(y^d)  (controller.py:376-377)
     const long sH = (long)d.r * d.cols;
-    DDMPC_TRY(launch_hankel(st, count, u_d, (long)ud_stride, q.N, q.m, d.Lp, 0, nullptr, pl.H.d(), d.cols, sH));
-    DDMPC_TRY(launch_hankel(st, count, y_d, (long)yd_stride, q.N, q.p, d.Lp, d.nu, nullptr, pl.H.d(), d.cols, sH));
+    DDMPC_TRY(launch_hankel(st, pl.data_count, u_d, (long)ud_stride, q.N, q.m, d.Lp, 0, nullptr, pl.H.d(), d.cols, sH));
+    DDMPC_TRY(launch_hankel(st, pl.data_count, y_d, (long)yd_stride, q.N, q.p, d.Lp, d.nu, nullptr, pl.H.d(), d.cols, sH));
 
     FillArgs fa{q.n, q.m, q.p, q.L, d.nu, d.ny, d.nx, d.nth, d.terminal, d.robust};
     if (d.robust) {
@@ -778,7 +783,7 @@ int set_create_device(const ddmpc_params *prm, int count, const double *u_d, siz
         std::vector<int> info(3 * count);
         DDMPC_CUDA(cudaMemcpy(info.data(), info_d.p, sizeof(int) * 3 * count, cudaMemcpyDeviceToHost));
         for (int c = 0; c < count; ++c)
-            if (pl.status[c] == DDMPC_OK && (info[c] || info[count + c] || info[2 * count + c]))
+            if (pl.status[c] == DDMPC_OK && (info[pl.data_count == 1 ? 0 : c] || info[count + c] || info[2 * count + c]))
                 pl.status[c] = DDMPC_ERR_FACTORIZATION;
     } else {
         DDMPC_TRY(build_nominal(st, pl, fa, perm_d.i(), invperm_d.i(), u_d, (long)ud_stride, y_d, (long)yd_stride, R, Q));
@@ -902,11 +907,12 @@ int ddmpc_set_get(const ddmpc_set *set, const char *name, int index, double *out
     const double *src = nullptr;
     size_t n = 0;
     const size_t sH = (size_t)d.r * d.cols;
-    if (nm == "H") { src = pl.H.d() + index * sH; n = sH; }
-    else if (nm == "HLn_ud") { src = pl.H.d() + index * sH; n = (size_t)d.nu * d.cols; }
-    else if (nm == "HLn_yd") { src = pl.H.d() + index * sH + (size_t)d.nu * d.cols; n = (size_t)d.ny * d.cols; }
-    else if (nm == "W" && pl.W.p) { n = (size_t)d.r * d.r; src = pl.W.d() + index * n; }
-    else if (nm == "Om" && pl.Om.p) { n = (size_t)d.r * d.r; src = pl.Om.d() + index * n; }
+    const size_t di = pl.data_count == 1 ? 0 : (size_t)index;   // shared data: one H / W / Om for the whole set
+    if (nm == "H") { src = pl.H.d() + di * sH; n = sH; }
+    else if (nm == "HLn_ud") { src = pl.H.d() + di * sH; n = (size_t)d.nu * d.cols; }
+    else if (nm == "HLn_yd") { src = pl.H.d() + di * sH + (size_t)d.nu * d.cols; n = (size_t)d.ny * d.cols; }
+    else if (nm == "W" && pl.W.p) { n = (size_t)d.r * d.r; src = pl.W.d() + di * n; }
+    else if (nm == "Om" && pl.Om.p) { n = (size_t)d.r * d.r; src = pl.Om.d() + di * n; }
     else if (nm == "Ku") { n = (size_t)d.Lm * d.nth; src = pl.Ku.d() + index * n; }
     else if (nm == "Z") { n = (size_t)d.nth * d.nth; src = pl.Z.d() + index * n; }
     else if (nm == "X0") { n = (size_t)d.nx * d.nth; src = pl.X0.d() + index * n; }

@@ -375,12 +375,12 @@ __global__ void k_full_x(KArgs a, int B, const int *__restrict__ ctrl_idx, const
 }
 
 // g = Om (T x)   (B x r)   then   alpha = H^T g   (B x cols)
-__global__ void k_full_g(KArgs a, int B, const int *__restrict__ ctrl_idx, const double *__restrict__ Om,
+__global__ void k_full_g(KArgs a, int B, const int *__restrict__ ctrl_idx, int shared_data, const double *__restrict__ Om,
                          const double *__restrict__ x, double *__restrict__ g) {
     const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= (size_t)B * a.r) return;
     const int b = (int)(e / a.r), i = (int)(e % a.r);
-    const int c = ctrl_idx ? ctrl_idx[b] : 0;
+    const int c = (ctrl_idx && !shared_data) ? ctrl_idx[b] : 0;
     const double *row = Om + ((size_t)c * a.r + i) * a.r;
     const double *xb = x + (size_t)b * a.nx;
     double acc = 0.0;
@@ -391,12 +391,12 @@ __global__ void k_full_g(KArgs a, int B, const int *__restrict__ ctrl_idx, const
     }
     g[e] = acc;
 }
-__global__ void k_full_alpha(KArgs a, int B, const int *__restrict__ ctrl_idx, const double *__restrict__ H,
+__global__ void k_full_alpha(KArgs a, int B, const int *__restrict__ ctrl_idx, int shared_data, const double *__restrict__ H,
                              const double *__restrict__ g, double *__restrict__ alpha) {
     const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= (size_t)B * a.cols) return;
     const int b = (int)(e / a.cols), col = (int)(e % a.cols);
-    const int c = ctrl_idx ? ctrl_idx[b] : 0;
+    const int c = (ctrl_idx && !shared_data) ? ctrl_idx[b] : 0;
     const double *Hc = H + (size_t)c * a.r * a.cols;
     double acc = 0.0;
     for (int k = 0; k < a.r; ++k) acc = fma(Hc[(size_t)k * a.cols + col], g[(size_t)b * a.r + k], acc);
@@ -775,9 +775,10 @@ int ddmpc_solve_full_batch(const ddmpc_set *set, int B, const int32_t *ctrl_idx,
     DDMPC_LAUNCH_CHECK();
     if (alpha) {
         DDMPC_CUDA(gb.alloc(sizeof(double) * (size_t)B * d.r));
-        k_full_g<<<ceil_div((long)B * d.r, T), T, 0, st>>>(a, B, ctrl_idx, pl.Om.d(), xb.d(), gb.d());
+        const int shared_data = pl.data_count == 1 ? 1 : 0;
+        k_full_g<<<ceil_div((long)B * d.r, T), T, 0, st>>>(a, B, ctrl_idx, shared_data, pl.Om.d(), xb.d(), gb.d());
         DDMPC_LAUNCH_CHECK();
-        k_full_alpha<<<ceil_div((long)B * d.cols, T), T, 0, st>>>(a, B, ctrl_idx, pl.H.d(), gb.d(), alpha);
+        k_full_alpha<<<ceil_div((long)B * d.cols, T), T, 0, st>>>(a, B, ctrl_idx, shared_data, pl.H.d(), gb.d(), alpha);
         DDMPC_LAUNCH_CHECK();
     }
     DDMPC_CUDA(cudaStreamSynchronize(st));  // scratch lifetime

@@ -78,8 +78,10 @@ if "5" in which:
     per_L = {}
     for L in range(8, 61, 4):
         Q, R = 3.0 * np.eye(2 * L), 1e-4 * np.eye(2 * L)
+        mk = lambda: ControllerSet(4, 2, 2, u_d, y_d, L, Q, R, prm["eps_max"], LA, LS, 1.0, 0, 1, 4, True, count=LA.size)
+        cs = mk(); del cs                     # warm the stream-ordered memory pool for this size (first-touch cudaMalloc)
         torch.cuda.synchronize(); t = time.perf_counter()
-        cs = ControllerSet(4, 2, 2, u_d, y_d, L, Q, R, prm["eps_max"], LA, LS, 1.0, 0, 1, 4, True, count=LA.size)
+        cs = mk()
         torch.cuda.synchronize(); dt = time.perf_counter() - t
         ok = int((cs.statuses() == 0).sum())
         nl = 64
