@@ -46,6 +46,7 @@ struct Plan {
     DevBuf umin, umax; // (m)        input box (device copy), empty when absent
     DevBuf ymin, ymax; // (p)        output box (device copy), empty when absent
     DevBuf F;      // (nfix, nth)    feasibility residual map     (nominal)
+    DevBuf Fnz;    // (1) int        1 when F has a non-zero entry (rank-deficient data); 0 = every window is feasible
     DevBuf lamA, lamS;  // per-controller lamb_alpha*eps_max, lamb_sigma
     std::vector<int> pe_rank, status;
     double bound = 0.0;   // c * eps_max

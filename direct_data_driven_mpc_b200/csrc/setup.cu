@@ -322,6 +322,17 @@ __global__ void k_extract(FillArgs f, int nf, int nb, int Lm, const int *__restr
     }
 }
 
+// Fnz[c] = 1 when the feasibility map F of controller c has an entry above 1e-13 (rank-deficient H: some windows are
+// not trajectories of the data); with noisy data H has full row rank, F vanishes and the per-solve check is skipped.
+__global__ void k_flag_nonzero(long n, const double *__restrict__ F, int *__restrict__ flag) {
+    const int c = blockIdx.x;
+    F += (long)c * n;
+    int nz = 0;
+    for (long e = threadIdx.x; e < n; e += blockDim.x) nz |= fabs(F[e]) > 1e-13;
+    nz = __syncthreads_or(nz);
+    if (threadIdx.x == 0) flag[c] = nz;
+}
+
 __global__ void k_sub_identity(int n, double *__restrict__ A, long bs) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) A[(long)blockIdx.y * bs + (long)i * n + i] -= 1.0;
@@ -591,6 +602,8 @@ static int build_nominal(cudaStream_t st, Plan &pl, const FillArgs &fa, const in
         DDMPC_LAUNCH_CHECK();
     }
     DDMPC_TRY(gemm(st, C, nfix, nth, nfix, 1.0, mat(G10.d(), nfix, 1, sF), Ccm, 0.0, pl.F.d(), nth, 1, (long)nfix * nth));
+    k_flag_nonzero<<<C, 256, 0, st>>>((long)nfix * nth, pl.F.d(), pl.Fnz.i());
+    DDMPC_LAUNCH_CHECK();
     // extract: X0p holds every (permuted) row, so "nf" = nx here
     {
         dim3 g(ceil_div((long)r * nth, 256), C);
@@ -720,6 +733,7 @@ int set_create_device(const ddmpc_params *prm, int count, const double *u_d, siz
         DDMPC_CUDA(pl.Om.alloc(sizeof(double) * CD * d.r * d.r));
     } else {
         DDMPC_CUDA(pl.F.alloc(sizeof(double) * C * d.nfix * d.nth));
+        DDMPC_CUDA(pl.Fnz.alloc(sizeof(int) * C));
     }
     if (d.nb > 0) {
         // box rows: sigma_pred in [-c eps_max, c eps_max] (controller.py:659-675), predicted inputs in [u_min, u_max]

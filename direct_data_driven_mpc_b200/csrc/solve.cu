@@ -22,6 +22,7 @@ struct KArgs {
     int n, m, p, L, nth, nb, Lm, nx, nfix, r, cols, ny, nu;
     int convex, robust;
     const double *Ku, *Z, *Ks, *Phi, *Psi, *Lam, *rho2, *F, *X0, *Yf;
+    const int *Fnz;                  // nominal: per controller, 1 when F is not identically zero
     const double *lo, *hi, *bmax;    // per controller: scaled bounds of the box rows (nb), largest finite |bound|
     const double *umin, *umax;       // input box (m) or NULL
     const double *ymin, *ymax;       // output box (p) or NULL
@@ -148,7 +149,7 @@ __global__ void k_solve_batch(KArgs a, int B, const int *__restrict__ ctrl_idx, 
     }
     int status = finite ? DDMPC_SOLVE_OPTIMAL : DDMPC_SOLVE_NONFINITE;
     int iters = 1;
-    if (a.F) {  // nominal: consistency of the fixed coordinates with range(H)
+    if (a.F && a.Fnz[c]) {  // nominal: consistency of the fixed coordinates with range(H)
         const double *F = a.F + (size_t)c * a.nfix * a.nth;
         double fe = 0.0;
         for (int i = 0; i < a.nfix; ++i) fe = fmax(fe, fabs(dot_theta(F + (size_t)i * a.nth, th, a.nth, TS, tid)));
@@ -262,7 +263,7 @@ k_solve_small(KArgs a, int B, const int *__restrict__ ctrl_idx, const double *__
     const bool finite = block_max(bad, red) == 0.0;
     int status = finite ? DDMPC_SOLVE_OPTIMAL : DDMPC_SOLVE_NONFINITE;
     int iters = 1;
-    if (a.F) {
+    if (a.F && a.Fnz[c]) {
         const double *F = a.F + (size_t)c * a.nfix * a.nth;
         double fe = 0.0;
         for (int i = tid; i < a.nfix; i += T) fe = fmax(fe, fabs(dot_row(F + (size_t)i * a.nth, th, a.nth)));
@@ -471,7 +472,7 @@ __global__ void k_closed_loop(KArgs a, LoopArgs la, int B, const int *__restrict
     const double *Phi = boxed ? a.Phi + (size_t)c * a.nb * a.nb : nullptr;
     const double *Psi = boxed ? a.Psi + (size_t)c * a.Lm * a.nb : nullptr;
     const double *lo = boxed ? a.lo + (size_t)c * a.nb : nullptr, *hi = boxed ? a.hi + (size_t)c * a.nb : nullptr;
-    const double *F = a.F ? a.F + (size_t)c * a.nfix * a.nth : nullptr;
+    const double *F = (a.F && a.Fnz[c]) ? a.F + (size_t)c * a.nfix * a.nth : nullptr;
 
     for (int i = 0; i < nm; ++i) SMV(th, i) = u_past0[(size_t)b * nm + i];
     for (int i = 0; i < npp; ++i) SMV(th, nm + i) = y_past0[(size_t)b * npp + i];
@@ -601,6 +602,7 @@ static KArgs make_kargs(const ddmpc_set *set, double tol, int max_iter) {
     a.Ks = pl.Ks.d(); a.Phi = pl.Phi.d(); a.Psi = pl.Psi.d(); a.Lam = pl.Lam.d(); a.Yf = pl.Yf.d();
     a.rho2 = pl.rho2.d();
     a.F = d.robust ? nullptr : pl.F.d();
+    a.Fnz = d.robust ? nullptr : pl.Fnz.i();
     a.lo = pl.lo.d(); a.hi = pl.hi.d(); a.bmax = pl.bmax.d();
     a.umin = d.nbu > 0 ? pl.umin.d() : nullptr; a.umax = d.nbu > 0 ? pl.umax.d() : nullptr;
     a.ymin = d.nby > 0 ? pl.ymin.d() : nullptr; a.ymax = d.nby > 0 ? pl.ymax.d() : nullptr;
