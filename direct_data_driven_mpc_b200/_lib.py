@@ -55,6 +55,7 @@ def _load() -> C.CDLL:
         "ddmpc_strerror": (C.c_char_p, [i32]),
         "ddmpc_last_error": (C.c_char_p, []),
         "ddmpc_kernel_launches": (u64, []),
+        "ddmpc_trim_memory": (i32, []),
         "ddmpc_hankel": (i32, [vp, i32, i32, i32, vp, vp]),
         "ddmpc_hankel_host": (i32, [vp, i32, i32, i32, vp]),
         "ddmpc_pe_rank_host": (i32, [vp, i32, i32, i32, C.POINTER(C.c_int)]),
@@ -85,7 +86,7 @@ EXPORTED = ["ddmpc_version", "ddmpc_strerror", "ddmpc_last_error", "ddmpc_kernel
             "ddmpc_hankel_host", "ddmpc_pe_rank_host", "ddmpc_set_create", "ddmpc_set_create_host",
             "ddmpc_set_destroy", "ddmpc_set_count", "ddmpc_set_info", "ddmpc_set_get", "ddmpc_solve_batch",
             "ddmpc_solve_batch_host", "ddmpc_solve_full_batch", "ddmpc_closed_loop_batch",
-            "ddmpc_closed_loop_batch_host", "ddmpc_generate_example_data", "ddmpc_pcg64_uniform"]
+            "ddmpc_closed_loop_batch_host", "ddmpc_generate_example_data", "ddmpc_pcg64_uniform", "ddmpc_trim_memory"]
 
 
 def last_error() -> str:
@@ -107,3 +108,8 @@ def check(code: int) -> None:
 
 def kernel_launches() -> int:
     return int(lib.ddmpc_kernel_launches())
+
+
+def trim_memory() -> None:
+    """Return the unused part of the library's device-memory pool to the driver (see ddmpc_trim_memory)."""
+    check(lib.ddmpc_trim_memory())

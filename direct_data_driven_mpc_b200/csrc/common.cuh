@@ -51,7 +51,8 @@ inline int fail(int code, const char *fmt, ...) {
 inline int ceil_div(long a, long b) { return (int)((a + b - 1) / b); }
 
 // RAII device buffer (setup scratch + plan storage).  Memory comes from the device's stream-ordered pool
-// (cudaMallocAsync on the legacy default stream) with a 1 GiB release threshold: a batched controller setup
+// (cudaMallocAsync on the legacy default stream) that keeps what it has been given (release threshold = max;
+// ddmpc_trim_memory() hands it back): a batched controller setup
 // allocates and frees a dozen buffers of up to hundreds of MB, and with cudaMalloc/cudaFree (each a device-wide
 // synchronisation plus page-table work) that cost 80-250 ms of wall time per call against 13 ms of kernels.
 // Every scratch lifetime in this library ends with a stream synchronise before the buffers go out of scope, and
@@ -64,7 +65,7 @@ inline cudaError_t pool_ready() {
         cudaMemPool_t pool;
         e = cudaDeviceGetDefaultMemPool(&pool, dev);
         if (e != cudaSuccess) return e;
-        uint64_t keep = 1ull << 30;
+        uint64_t keep = ~0ull;   // a finite threshold makes every large setup re-map gigabytes (0.4-3 s instead of 0.13 s)
         return cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
     }();
     return state;

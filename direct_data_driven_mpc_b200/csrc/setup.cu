@@ -819,6 +819,16 @@ const char *ddmpc_version(void) { return "ddmpc-b200 0.1 (sm_100a)"; }
 const char *ddmpc_last_error(void) { return g_last_error; }
 uint64_t ddmpc_kernel_launches(void) { return g_launches.load(); }
 
+int ddmpc_trim_memory(void) {
+    int dev = 0;
+    DDMPC_CUDA(cudaGetDevice(&dev));
+    cudaMemPool_t pool;
+    DDMPC_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+    DDMPC_CUDA(cudaDeviceSynchronize());
+    DDMPC_CUDA(cudaMemPoolTrimTo(pool, 0));
+    return DDMPC_OK;
+}
+
 const char *ddmpc_strerror(int s) {
     switch (s) {
         case DDMPC_OK: return "ok";

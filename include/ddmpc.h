@@ -214,6 +214,11 @@ int ddmpc_pcg64_uniform(uint64_t *rng_state, int S, int count, double lo, double
 /* Number of kernels this library has launched since load (bench bookkeeping). */
 uint64_t ddmpc_kernel_launches(void);
 
+/* Plan storage and setup scratch come from the device's stream-ordered memory pool, which keeps freed memory for the
+ * next setup (re-mapping gigabytes per call is what made batched setups slow).  This returns the unused part to the
+ * driver (e.g. before handing the GPU to another allocator).  Synchronises the device. */
+int ddmpc_trim_memory(void);
+
 #ifdef __cplusplus
 }
 #endif

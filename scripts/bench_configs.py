@@ -22,11 +22,12 @@ if "2" in which:
     # config 2: 4096 closed loops over seeds, each loop with its own (u_d, y_d) => its own controller
     B, n_steps = int(os.environ.get("CFG2_B", 4096)), 401
     pl, prm = S.four_tank_plant(), S.four_tank_controller_params()
-    t = time.perf_counter()
-    data = [S.example_data(s) for s in range(B)]
-    t_data = time.perf_counter() - t
-    ud, yd = np.stack([d[2] for d in data]), np.stack([d[3] for d in data])
-    x0 = np.stack([d[4] for d in data])
+    # per-seed data on the device with the reference's NumPy streams (stages 1-3 of the example script for --seed b)
+    torch.cuda.synchronize(); t = time.perf_counter()
+    ds = S.DeviceScenarios(seeds=range(B))
+    w_dev = ds.uniform(n_steps * 2, -1.0, 1.0, 0.002).reshape(B, n_steps, 2)       # controller_operation.py:263
+    torch.cuda.synchronize(); t_data = time.perf_counter() - t
+    ud, yd, x0 = ds.u_d, ds.y_d, ds.x_end
     for name, slack, term, nmpc, ctype in [("ROBUST TEC n-step", 0, True, 4, 1), ("ROBUST TEC 1-step", 0, True, 1, 1),
                                            ("ROBUST UCON 1-step", 0, False, 1, 1), ("ROBUST CONVEX n-step", 1, True, 4, 1),
                                            ("NOMINAL 1-step", 0, True, 1, 0)]:
@@ -35,9 +36,10 @@ if "2" in which:
                            1.0, slack, ctype, nmpc, term)
         torch.cuda.synchronize(); t_setup = time.perf_counter() - t
         ok = int((cs.statuses() == 0).sum())
-        w = np.stack([0.002 * d[0].uniform(-1.0, 1.0, (n_steps, 2)) for d in data]) if name.endswith("n-step") and slack == 0 else None
-        args = (pl, x0, ud[:, -4:].reshape(B, -1), yd[:, -4:].reshape(B, -1), np.tile(prm["u_s"].T, (B, 1)), np.tile(prm["y_s"].T, (B, 1)), n_steps)
-        kw = dict(w=w, noise_seed=0, noise_eps=0.002, ctrl_idx=np.arange(B))
+        td = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+        args = (pl, x0, ud[:, -4:].reshape(B, -1).contiguous(), yd[:, -4:].reshape(B, -1).contiguous(),
+                td(np.tile(prm["u_s"].T, (B, 1))), td(np.tile(prm["y_s"].T, (B, 1))), n_steps)
+        kw = dict(w=w_dev, ctrl_idx=torch.arange(B, device=dev, dtype=torch.int32))
         dt = timed(lambda: cs.closed_loop(*args, **kw))
         u, y, st, it = cs.closed_loop(*args, **kw)
         print(json.dumps({"config": 2, "variant": name, "loops": B, "controllers_ok": ok, "setup_s": t_setup,
