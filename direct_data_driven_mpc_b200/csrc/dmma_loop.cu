@@ -127,10 +127,37 @@ __device__ __forceinline__ void dl_gemm(const double *__restrict__ AF, int ksN, 
     }
 }
 
+// Same product with the A fragments already in registers (small shapes: the block map is loop invariant).
+template <int MT, int KS>
+__device__ __forceinline__ void dl_gemm_reg(const double (&areg)[MT * KS], const int *offtab, const double *tb,
+                                            double2 (&out)[MT]) {
+    constexpr int SK = MT >= 3 ? 1 : 4 / MT;
+#pragma unroll
+    for (int j = 0; j < MT; ++j) out[j] = make_double2(0.0, 0.0);
+    double2 acc[MT][SK];
+#pragma unroll
+    for (int j = 0; j < MT; ++j)
+#pragma unroll
+        for (int s = 0; s < SK; ++s) acc[j][s] = make_double2(0.0, 0.0);
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+        const double bv = tb[offtab[ks]];
+#pragma unroll
+        for (int j = 0; j < MT; ++j) dl_mma(acc[j][ks % SK], areg[j * KS + ks], bv);
+    }
+#pragma unroll
+    for (int j = 0; j < MT; ++j) {
+        double2 v = acc[j][0];
+#pragma unroll
+        for (int s = 1; s < SK; ++s) { v.x += acc[j][s].x; v.y += acc[j][s].y; }
+        out[j] = v;
+    }
+}
+
 constexpr int DL_WARPS = 4;   // warps (n-tiles of 8 loops) per CTA
 
 template <int MTS, int MTP, int KSS, int KSP>
-__global__ void __launch_bounds__(32 * DL_WARPS)
+__global__ void __launch_bounds__(32 * DL_WARPS, 4)
 k_closed_loop_dmma(const DmmaArgs a) {
     extern __shared__ __align__(16) double dl_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, q = lane & 3;
@@ -188,6 +215,13 @@ k_closed_loop_dmma(const DmmaArgs a) {
     const int cps = p >> 2;                                   // Philox calls per step (4 noise words each)
     bool fin[2] = {true, true};
     int base = 0, n_iter = 0;                                 // ring slot of the oldest window entry
+    // small shapes: the A fragments of the block map stay in registers for the whole run
+    constexpr bool PLANT_REG = KSP > 0 && MTP * KSP <= 24;
+    double aP[PLANT_REG ? MTP * KSP : 1];
+    if constexpr (PLANT_REG) {
+#pragma unroll
+        for (int e = 0; e < MTP * KSP; ++e) aP[e] = __ldg(a.MbF + (size_t)e * 32 + lane);
+    }
     __syncwarp();
 
     for (int t0 = 0; t0 < a.n_steps; t0 += nmpc, ++n_iter) {
@@ -243,7 +277,15 @@ k_closed_loop_dmma(const DmmaArgs a) {
         __syncwarp();
         // ---- plant: outputs of the block and the state after it
         double2 yo[MTP];
-        dl_gemm<MTP, KSP>(MF, a.ksP, tabP, tb, lane, yo);
+        if constexpr (PLANT_REG) {
+            if (steps != nmpc) {                              // last, partial block: its own block map
+#pragma unroll
+                for (int e = 0; e < MTP * KSP; ++e) aP[e] = __ldg(a.MtF + (size_t)e * 32 + lane);
+            }
+            dl_gemm_reg<MTP, KSP>(aP, tabP, tb, yo);
+        } else {
+            dl_gemm<MTP, KSP>(MF, a.ksP, tabP, tb, lane, yo);
+        }
         __syncwarp();                                         // every lane has read the old state
 #pragma unroll
         for (int j = 0; j < MTP; ++j) {
