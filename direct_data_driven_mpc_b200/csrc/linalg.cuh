@@ -27,7 +27,10 @@ k_gemm(int M, int N, int K, double alpha,
        const double *__restrict__ A, long rsA, long csA, long bsA,
        const double *__restrict__ Bm, long rsB, long csB, long bsB,
        const double *__restrict__ dvec, long bsd,
-       double beta, double *__restrict__ C, long rsC, long csC, long bsC) {
+       double beta, double *__restrict__ C, long rsC, long csC, long bsC, int sym) {
+    // sym: the product is known to be symmetric (Gram matrices A A^T): tiles above the diagonal are skipped and the
+    // tiles below it are written to both triangles
+    if (sym && blockIdx.x > blockIdx.y) return;
     constexpr int G_LDB = GT + 4;   // Bs[k][n]
     constexpr int WT = GT / 2;      // warp tile edge
     constexpr int NF = WT / 8;      // m8n8 fragments per warp tile edge
@@ -99,6 +102,7 @@ k_gemm(int M, int N, int K, double alpha,
                 double v = alpha * acc[a][c][h];
                 if (beta != 0.0) v += beta * (*cp);
                 *cp = v;
+                if (sym && blockIdx.x != blockIdx.y) C[(long)j * rsC + (long)i * csC] = v;
             }
         }
     }
@@ -113,17 +117,20 @@ inline Mat tr(Mat a) { return Mat{a.p, a.cs, a.rs, a.bs}; }
 
 inline int gemm(cudaStream_t st, int batch, int M, int N, int K, double alpha, Mat A, Mat B,
                 double beta, double *C, long rsC, long csC, long bsC,
-                const double *dvec = nullptr, long bsd = 0) {
+                const double *dvec = nullptr, long bsd = 0, bool symmetric = false) {
     if (M <= 0 || N <= 0 || batch <= 0) return DDMPC_OK;
+    const int sym = (symmetric && M == N && beta == 0.0) ? 1 : 0;
     const long tiles64 = (long)ceil_div(N, 64) * ceil_div(M, 64) * batch;
-    if (tiles64 >= 148) {
+    // executed area with 64- and 32-wide tiles: small matrices (136 rows = 3 x 64 or 5 x 32) waste less with the latter
+    const long area64 = (long)ceil_div(N, 64) * ceil_div(M, 64) * 4096, area32 = (long)ceil_div(N, 32) * ceil_div(M, 32) * 1024;
+    if (tiles64 >= 148 && 4 * area32 > 3 * area64) {
         dim3 grid(ceil_div(N, 64), ceil_div(M, 64), batch);
         k_gemm<64><<<grid, 128, 0, st>>>(M, N, K, alpha, A.p, A.rs, A.cs, A.bs, B.p, B.rs, B.cs, B.bs, dvec, bsd, beta,
-                                         C, rsC, csC, bsC);
-    } else {   // not enough 64x64 tiles for one wave: quarter-size tiles
+                                         C, rsC, csC, bsC, sym);
+    } else {   // not enough 64x64 tiles for one wave, or too much padding in them: quarter-size tiles
         dim3 grid(ceil_div(N, 32), ceil_div(M, 32), batch);
         k_gemm<32><<<grid, 128, 0, st>>>(M, N, K, alpha, A.p, A.rs, A.cs, A.bs, B.p, B.rs, B.cs, B.bs, dvec, bsd, beta,
-                                         C, rsC, csC, bsC);
+                                         C, rsC, csC, bsC, sym);
     }
     DDMPC_LAUNCH_CHECK();
     return DDMPC_OK;

@@ -399,7 +399,7 @@ int pe_rank_device(cudaStream_t st, int batch, const double *X, long bsX, int N,
     DDMPC_CUDA(G.alloc(sizeof(double) * (size_t)batch * rows * rows));
     DDMPC_TRY(launch_hankel(st, batch, X, bsX, N, nch, order, 0, nullptr, Hpe.d(), cols, (long)rows * cols));
     Mat Hm = mat(Hpe.d(), cols, 1, (long)rows * cols);
-    DDMPC_TRY(gemm(st, batch, rows, rows, cols, 1.0, Hm, tr(Hm), 0.0, G.d(), rows, 1, (long)rows * rows));
+    DDMPC_TRY(gemm(st, batch, rows, rows, cols, 1.0, Hm, tr(Hm), 0.0, G.d(), rows, 1, (long)rows * rows, nullptr, 0, true));
     DDMPC_TRY(symmetrize(st, batch, rows, G.d(), rows, (long)rows * rows));
     // Stage 1: number of pivots of a diagonally pivoted elimination of the Gram matrix above 1e-12 x the largest.
     // The Gram matrix squares the singular values, so this proves full rank only for sigma_min/sigma_max > 1e-6 -
@@ -433,7 +433,7 @@ static int build_robust(cudaStream_t st, Plan &pl, const FillArgs &fa, const int
     const int CW = pl.data_count;
     const long sOm = CW == 1 ? 0 : sW;
     Mat Hm = mat(pl.H.d(), d.cols, 1, (long)r * d.cols);
-    DDMPC_TRY(gemm(st, CW, r, r, d.cols, 1.0, Hm, tr(Hm), 0.0, pl.W.d(), r, 1, sW));
+    DDMPC_TRY(gemm(st, CW, r, r, d.cols, 1.0, Hm, tr(Hm), 0.0, pl.W.d(), r, 1, sW, nullptr, 0, true));
     DDMPC_TRY(symmetrize(st, CW, r, pl.W.d(), r, sW));
     DDMPC_TRY(copy_bcast(st, CW, sW, pl.W.d(), sW, Lw.d(), sW));
     DDMPC_TRY(potrf(st, CW, r, Lw.d(), r, sW, info_d));
@@ -529,7 +529,7 @@ static int build_nominal(cudaStream_t st, Plan &pl, const FillArgs &fa, const in
     DDMPC_TRY(launch_hankel(st, C, ud, bs_ud, d.N, d.m, d.Lp, 0, invperm_d, Hp.d(), d.cols, sH));
     DDMPC_TRY(launch_hankel(st, C, yd, bs_yd, d.N, d.p, d.Lp, d.nu, invperm_d, Hp.d(), d.cols, sH));
     Mat Hm = mat(Hp.d(), d.cols, 1, sH);
-    DDMPC_TRY(gemm(st, C, r, r, d.cols, 1.0, Hm, tr(Hm), 0.0, Wp.d(), r, 1, sW));
+    DDMPC_TRY(gemm(st, C, r, r, d.cols, 1.0, Hm, tr(Hm), 0.0, Wp.d(), r, 1, sW, nullptr, 0, true));
     DDMPC_TRY(symmetrize(st, C, r, Wp.d(), r, sW));
     DDMPC_TRY(jacobi_eig(st, C, r, Wp.d(), r, sW, V1.d(), r, sW, l1.d(), r));
     k_spectrum<<<C, 32, 0, st>>>(r, l1.d(), r, 1e-11, 0, d1.d(), r, nullptr);
