@@ -174,8 +174,68 @@ k_potrf(int n, double *__restrict__ A, long ld, long bs, int *__restrict__ info)
     if (tid == 0 && info) info[blockIdx.x] = bad;
 }
 
+// Same factorisation with the lower triangle held in shared memory (packed, row-major: (i, j) at i(i+1)/2 + j) for
+// matrices that fit (n <= 208): the unblocked right-looking update moves n^3/6 elements, which is L2 traffic in
+// k_potrf and shared-memory traffic here.  One CTA of 256 threads per matrix; a warp per row of the trailing update.
+static __global__ void __launch_bounds__(256)
+k_potrf_smem(int n, double *__restrict__ A, long ld, long bs, int *__restrict__ info) {
+    extern __shared__ double sh[];          // Lp[n(n+1)/2], col[n], dg[n]
+    A += (long)blockIdx.x * bs;
+    const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, NW = T >> 5;
+    double *Lp = sh, *col = sh + (size_t)n * (n + 1) / 2, *dg = col + n;
+    __shared__ int bad;
+    if (tid == 0) bad = 0;
+    for (int i = warp; i < n; i += NW) {
+        const double *row = A + (long)i * ld;
+        double *dst = Lp + (size_t)i * (i + 1) / 2;
+        for (int j = lane; j <= i; j += 32) dst[j] = row[j];
+    }
+    __syncthreads();
+    for (int j = 0; j < n; ++j) {
+        double d = Lp[(size_t)j * (j + 1) / 2 + j];      // not written during this column (the square root goes to dg)
+        if (!(d > 0.0) || !isfinite(d)) {
+            if (tid == 0 && !bad) bad = j + 1;
+            d = 1.0;                                     // keep going with finite numbers; the verdict is in info
+        }
+        d = sqrt(d);
+        const double inv = 1.0 / d;
+        if (tid == 0) dg[j] = d;
+        for (int i = j + 1 + tid; i < n; i += T) {
+            const size_t e = (size_t)i * (i + 1) / 2 + j;
+            const double v = Lp[e] * inv;
+            Lp[e] = v;
+            col[i] = v;
+        }
+        __syncthreads();
+        for (int i = j + 1 + warp; i < n; i += NW) {
+            const double ci = col[i];
+            double *row = Lp + (size_t)i * (i + 1) / 2;
+            for (int k = j + 1 + lane; k <= i; k += 32) row[k] = fma(-ci, col[k], row[k]);
+        }
+        __syncthreads();
+    }
+    for (int i = warp; i < n; i += NW) {
+        double *row = A + (long)i * ld;
+        const double *src = Lp + (size_t)i * (i + 1) / 2;
+        for (int j = lane; j < i; j += 32) row[j] = src[j];
+        if (lane == 0) row[i] = dg[i];
+    }
+    if (tid == 0 && info) info[blockIdx.x] = bad;
+}
+
 inline int potrf(cudaStream_t st, int batch, int n, double *A, long ld, long bs, int *info) {
     if (n <= 0 || batch <= 0) return DDMPC_OK;
+    const size_t sh = sizeof(double) * ((size_t)n * (n + 1) / 2 + 2 * (size_t)n);
+    if (sh <= 200 * 1024) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            DDMPC_CUDA(cudaFuncSetAttribute(k_potrf_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            attr_set = true;
+        }
+        k_potrf_smem<<<batch, 256, sh, st>>>(n, A, ld, bs, info);
+        DDMPC_LAUNCH_CHECK();
+        return DDMPC_OK;
+    }
     int threads = n >= 256 ? 1024 : (n >= 96 ? 512 : 256);
     k_potrf<<<batch, threads, 0, st>>>(n, A, ld, bs, info);
     DDMPC_LAUNCH_CHECK();
