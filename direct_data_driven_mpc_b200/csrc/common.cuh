@@ -50,6 +50,14 @@ inline int fail(int code, const char *fmt, ...) {
 
 inline int ceil_div(long a, long b) { return (int)((a + b - 1) / b); }
 
+// True the first time it is called with `mask` on the current device (function attributes are per device).
+inline bool first_time_on_device(std::atomic<unsigned long long> &mask) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return true;
+    const unsigned long long bit = 1ull << (dev & 63);
+    return (mask.fetch_or(bit) & bit) == 0;
+}
+
 // RAII device buffer (setup scratch + plan storage).  Memory comes from the device's stream-ordered pool
 // (cudaMallocAsync on the legacy default stream) that keeps what it has been given (release threshold = max;
 // ddmpc_trim_memory() hands it back): a batched controller setup
@@ -58,17 +66,16 @@ inline int ceil_div(long a, long b) { return (int)((a + b - 1) / b); }
 // Every scratch lifetime in this library ends with a stream synchronise before the buffers go out of scope, and
 // ddmpc_set_destroy synchronises the device, so returning memory to the pool never races with work using it.
 inline cudaError_t pool_ready() {
-    static cudaError_t state = [] {
-        int dev = 0;
-        cudaError_t e = cudaGetDevice(&dev);
-        if (e != cudaSuccess) return e;
-        cudaMemPool_t pool;
-        e = cudaDeviceGetDefaultMemPool(&pool, dev);
-        if (e != cudaSuccess) return e;
-        uint64_t keep = ~0ull;   // a finite threshold makes every large setup re-map gigabytes (0.4-3 s instead of 0.13 s)
-        return cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-    }();
-    return state;
+    static std::atomic<unsigned long long> done{0};
+    if (!first_time_on_device(done)) return cudaSuccess;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    cudaMemPool_t pool;
+    e = cudaDeviceGetDefaultMemPool(&pool, dev);
+    if (e != cudaSuccess) return e;
+    uint64_t keep = ~0ull;   // a finite threshold makes every large setup re-map gigabytes (0.4-3 s instead of 0.13 s)
+    return cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
 }
 
 struct DevBuf {

@@ -1493,13 +1493,12 @@ static int launch_fast(const ddmpc_set *set, const ddmpc_plant *plant, const Fas
                 if (const char *ens = getenv("DDMPC_DEBUG_NOSTORE")) a.dbg_nostore = ens[0] == '1';
                 const char *emw = getenv("DDMPC_WS_MATH_WARPS");
                 const int mw = (emw && emw[0] == '1') ? 1 : 2;
-                static bool carveout_set = false;
-                if (!carveout_set) {
+                static std::atomic<unsigned long long> carveout_done{0};
+                if (first_time_on_device(carveout_done)) {
                     DDMPC_CUDA(cudaFuncSetAttribute(k_closed_loop_ws<N, M, P, NX, NMPC, false, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
                     DDMPC_CUDA(cudaFuncSetAttribute(k_closed_loop_ws<N, M, P, NX, NMPC, true, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
                     DDMPC_CUDA(cudaFuncSetAttribute(k_closed_loop_ws<N, M, P, NX, NMPC, false, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
                     DDMPC_CUDA(cudaFuncSetAttribute(k_closed_loop_ws<N, M, P, NX, NMPC, true, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-                    carveout_set = true;
                 }
                 if (mw == 2) {
                     if (a.w) k_closed_loop_ws<N, M, P, NX, NMPC, false, 2><<<gridw, 96, 0, st>>>(mc, a, n_tail);

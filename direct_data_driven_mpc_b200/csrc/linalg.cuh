@@ -227,11 +227,9 @@ inline int potrf(cudaStream_t st, int batch, int n, double *A, long ld, long bs,
     if (n <= 0 || batch <= 0) return DDMPC_OK;
     const size_t sh = sizeof(double) * ((size_t)n * (n + 1) / 2 + 2 * (size_t)n);
     if (sh <= 200 * 1024) {
-        static bool attr_set = false;
-        if (!attr_set) {
+        static std::atomic<unsigned long long> attr_done{0};
+        if (first_time_on_device(attr_done))
             DDMPC_CUDA(cudaFuncSetAttribute(k_potrf_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            attr_set = true;
-        }
         k_potrf_smem<<<batch, 256, sh, st>>>(n, A, ld, bs, info);
         DDMPC_LAUNCH_CHECK();
         return DDMPC_OK;
