@@ -1355,6 +1355,151 @@ k_closed_loop_ws(const __grid_constant__ MmaCoef<N, M, P, NX, NMPC> cfp, const F
     }
 }
 
+// ===========================================================================
+// Register-chained all-tensor-core variant: no shared memory, no barriers.
+//
+// The products are computed TRANSPOSED, loops along M:   U^T (8 loops x 8) = W^T (8 x 16) Ku^T,
+// [Y; x+]^T (8 loops x 12) = [x; U]^T (8 x 12) Mblk^T.   With the m8n8k4 fragment layouts (lane = 4g + q:
+// A[g][q], B[q][g], C[g][2q..2q+1]) the C fragment of one product - lane (g, q) holds outputs 2q, 2q+1 of loop g -
+// is directly a pair of A fragments of the next one, because the order in which a dot product visits its terms is
+// free: k-step "0" takes entry 2q from lane q and k-step "1" entry 2q+1, and that permutation is folded into the
+// constant B operands (the coefficient matrices, held in registers for the whole run).  So the planned inputs feed
+// the plant product, and both feed the next solve, without ever leaving the register file; only the 4 plant
+// states are re-spread over the lanes with two shuffles.  Lane (g, q) ends up holding step q of the block for loop
+// g: it draws that step's noise (one Philox call, the accumulator of the plant product starts from it), and stores
+// that step's u and y (16 B each; the four lanes of a loop write 64 contiguous bytes).
+// A warp carries NT m-tiles (8 NT loops) as independent DMMA chains.
+// ===========================================================================
+template <int N, int M, int P, int NX, int NMPC, bool PHILOX, int NT>
+__global__ void __launch_bounds__(32, NT >= 8 ? 7 : 14)
+k_closed_loop_reg(const __grid_constant__ MmaCoef<N, M, P, NX, NMPC> cfp, const FastArgs a, const int n_tail) {
+    constexpr int R = NMPC * M, RY = NMPC * P, NU = N * M;
+    static_assert(M == 2 && P == 2 && R == 8 && RY == 8 && NX == 4 && NMPC == N, "shape not supported by the register-chained kernel");
+    const int lane = threadIdx.x, g = lane >> 2, q = lane & 3;
+    const int nblk = (a.n_steps + NMPC - 1) / NMPC;
+    // constant B fragments: lane (g, q) holds B[k = q][n = g] of every k-step
+    double bK[4], bP[2][3];
+    bK[0] = cfp.Ku[g][2 * q];          bK[1] = cfp.Ku[g][2 * q + 1];             // window inputs  2q, 2q+1
+    bK[2] = cfp.Ku[g][NU + 2 * q];     bK[3] = cfp.Ku[g][NU + 2 * q + 1];        // window outputs 2q, 2q+1
+    auto load_plant = [&](const double (&Mb)[NMPC * P + NX][NX + NMPC * M]) {
+#pragma unroll
+        for (int tile = 0; tile < 2; ++tile) {
+            const int row = 8 * tile + g;
+            const bool valid = row < RY + NX;
+            const int rr = valid ? row : 0;
+            bP[tile][0] = valid ? Mb[rr][q] : 0.0;                               // state entry q
+            bP[tile][1] = valid ? Mb[rr][NX + 2 * q] : 0.0;                      // planned inputs 2q, 2q+1
+            bP[tile][2] = valid ? Mb[rr][NX + 2 * q + 1] : 0.0;
+        }
+    };
+    load_plant(cfp.Mb);
+    auto mma = [](double2 &c, double av, double bv) {
+        asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+            : "+d"(c.x), "+d"(c.y)
+            : "d"(av), "d"(bv));
+    };
+    // per m-tile state of loop g: lane (g, q) holds entries 2q, 2q+1 of the window halves, entry q of the state
+    int b[NT];
+    bool live[NT];
+    double2 uC[NT], yC[NT], csp[NT], xC[NT];
+    double xA[NT];
+#pragma unroll
+    for (int mt = 0; mt < NT; ++mt) {
+        b[mt] = (blockIdx.x * NT + mt) * 8 + g;
+        live[mt] = b[mt] < a.B;
+        if (!live[mt]) b[mt] = a.B - 1;                        // dead rows replay the last loop and never store
+        const size_t bb = (size_t)b[mt];
+        uC[mt] = *reinterpret_cast<const double2 *>(a.u_past0 + bb * NU + 2 * q);
+        yC[mt] = *reinterpret_cast<const double2 *>(a.y_past0 + bb * (N * P) + 2 * q);
+        xA[mt] = a.x0[bb * NX + q];
+        xC[mt] = make_double2(0.0, 0.0);
+        double sp[M + P];
+#pragma unroll
+        for (int i = 0; i < M; ++i) sp[i] = a.u_s[bb * M + i];
+#pragma unroll
+        for (int i = 0; i < P; ++i) sp[M + i] = a.y_s[bb * P + i];
+        double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+        for (int j = 0; j < M + P; ++j) {
+            c0 = fma(__ldg(a.Ksp + (2 * q) * (M + P) + j), sp[j], c0);
+            c1 = fma(__ldg(a.Ksp + (2 * q + 1) * (M + P) + j), sp[j], c1);
+        }
+        csp[mt] = make_double2(c0, c1);
+    }
+    for (int t = 0; t < nblk; ++t) {
+        const int steps = (t == nblk - 1 && n_tail != 0) ? n_tail : NMPC;
+        if (t == nblk - 1 && n_tail != 0) load_plant(cfp.Mt);   // last, partial block (controller_operation.py:278)
+        // ---- solve: U^T = csp + W^T Ku^T   (k-steps outermost: consecutive DMMAs hit different accumulators)
+        double2 nu[NT];
+#pragma unroll
+        for (int mt = 0; mt < NT; ++mt) nu[mt] = csp[mt];
+#pragma unroll
+        for (int mt = 0; mt < NT; ++mt) mma(nu[mt], uC[mt].x, bK[0]);
+#pragma unroll
+        for (int mt = 0; mt < NT; ++mt) mma(nu[mt], uC[mt].y, bK[1]);
+#pragma unroll
+        for (int mt = 0; mt < NT; ++mt) mma(nu[mt], yC[mt].x, bK[2]);
+#pragma unroll
+        for (int mt = 0; mt < NT; ++mt) mma(nu[mt], yC[mt].y, bK[3]);
+        // ---- measurement noise of step q of the block (the accumulator of the output product starts from it)
+        const int k = t * NMPC + q;
+        double2 d0[NT], d1[NT];
+#pragma unroll
+        for (int mt = 0; mt < NT; ++mt) {
+            if constexpr (PHILOX) {
+                // noise word qs = q*P + i of the block is word (qs & 3) of Philox call t*RY/4 + (qs >> 2)
+                const unsigned long long sid = a.id0 + (unsigned long long)b[mt];
+                uint32_t c0 = (uint32_t)(((unsigned)t * (unsigned)RY) >> 2) + (uint32_t)(q >> 1), c1 = 0u, c2 = (uint32_t)sid,
+                         c3 = (uint32_t)(sid >> 32);
+#pragma unroll
+                for (int r = 0; r < 10; ++r) philox_round(c0, c1, c2, c3, a.rk[2 * r], a.rk[2 * r + 1]);
+                const uint32_t w0 = (q & 1) ? c2 : c0, w1 = (q & 1) ? c3 : c1;
+                d0[mt] = make_double2(a.eps * (2.0 * unit32_fast(w0) - 3.0), a.eps * (2.0 * unit32_fast(w1) - 3.0));
+            } else {
+                d0[mt] = k < a.n_steps ? *reinterpret_cast<const double2 *>(a.w + ((size_t)b[mt] * a.n_steps + k) * P)
+                                       : make_double2(0.0, 0.0);
+            }
+            d1[mt] = make_double2(0.0, 0.0);
+        }
+        // ---- plant: [Y; x+]^T = w + [x; U]^T Mblk^T
+#pragma unroll
+        for (int mt = 0; mt < NT; ++mt) { mma(d0[mt], xA[mt], bP[0][0]); mma(d1[mt], xA[mt], bP[1][0]); }
+#pragma unroll
+        for (int mt = 0; mt < NT; ++mt) { mma(d0[mt], nu[mt].x, bP[0][1]); mma(d1[mt], nu[mt].x, bP[1][1]); }
+#pragma unroll
+        for (int mt = 0; mt < NT; ++mt) { mma(d0[mt], nu[mt].y, bP[0][2]); mma(d1[mt], nu[mt].y, bP[1][2]); }
+        // ---- record step q, hand the block over to the next one
+#pragma unroll
+        for (int mt = 0; mt < NT; ++mt) {
+            if (live[mt] && q < steps && !a.dbg_nostore) {
+                const size_t f = (size_t)b[mt] * a.n_steps + k;
+                *reinterpret_cast<double2 *>(a.u_sys + f * M) = nu[mt];
+                *reinterpret_cast<double2 *>(a.y_sys + f * P) = d0[mt];
+            }
+            uC[mt] = nu[mt];
+            yC[mt] = d0[mt];
+            xC[mt] = d1[mt];
+            // state entry q of loop g sits in lane (g, q >> 1), component q & 1
+            const int src = (lane & ~3) | (q >> 1);
+            const double v0 = __shfl_sync(0xffffffffu, d1[mt].x, src), v1 = __shfl_sync(0xffffffffu, d1[mt].y, src);
+            xA[mt] = (q & 1) ? v1 : v0;
+        }
+    }
+    // ---- per-loop results (loop g = lanes 4g .. 4g+3)
+#pragma unroll
+    for (int mt = 0; mt < NT; ++mt) {
+        const int sl = (n_tail ? n_tail : NMPC) - 1;             // last recorded step of the last block
+        bool fin = isfinite(xA[mt]) && (q != sl || (isfinite(yC[mt].x) && isfinite(yC[mt].y)));
+        const unsigned badm = __ballot_sync(0xffffffffu, !fin);
+        const bool loop_bad = ((badm >> (4 * g)) & 0xfu) != 0u;
+        if (live[mt] && q == 0) {
+            if (a.status) a.status[b[mt]] = loop_bad ? DDMPC_SOLVE_NONFINITE : DDMPC_SOLVE_OPTIMAL;
+            if (a.iters) a.iters[b[mt]] = nblk;
+        }
+        if (live[mt] && a.x_final) a.x_final[(size_t)b[mt] * NX + q] = xA[mt];
+    }
+}
+
 // s-step block map of the plant into Mout (rows y_0..y_{NMPC-1} (zero beyond s), then x_s; columns x_0, u_0..)
 template <int M, int P, int NX, int NMPC>
 static void host_block_map(const ddmpc_plant *pl, int s, double (&Mout)[NMPC * P + NX][NX + NMPC * M]) {
@@ -1480,6 +1625,38 @@ static int launch_fast(const ddmpc_set *set, const ddmpc_plant *plant, const Fas
         const char *ews = getenv("DDMPC_WS");
         const bool want_ws = ews ? ews[0] == '1' : true;
         if constexpr (MMA_OK) {
+            // register-chained variant: opt-in (DDMPC_REG=1).  Its recurrence never leaves the register file (compute alone:
+            // 0.19 ms on config 3 with NT = 2 against 0.213 ms for the warp-specialised kernel), but a lane then owns ONE
+            // step of a loop, i.e. 16-byte stores, and those cost far more than the shared-memory hand-over they save
+            // (0.33-0.44 ms in total); pairing them into sectors needs the same transposition again.
+            const char *ereg = getenv("DDMPC_REG");
+            const bool want_reg = ereg ? ereg[0] == '1' : false;
+            if constexpr (NX == 4) {
+                if (want_reg && want_ws && !want && pair && lpt == 2 && (reinterpret_cast<uintptr_t>(a.u_past0) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(a.y_past0) & 15) == 0 && (!a.w || (reinterpret_cast<uintptr_t>(a.w) & 15) == 0)) {
+                    MmaCoef<N, M, P, NX, NMPC> mc;
+                    for (int k = 0; k < NMPC * M; ++k)
+                        for (int j = 0; j < NW; ++j) mc.Ku[k][j] = cache[(size_t)k * d.nth + j];
+                    host_block_map<M, P, NX, NMPC>(plant, NMPC, mc.Mb);
+                    const int n_tail = a.n_steps % NMPC;
+                    host_block_map<M, P, NX, NMPC>(plant, n_tail ? n_tail : NMPC, mc.Mt);
+                    if (const char *ens = getenv("DDMPC_DEBUG_NOSTORE")) a.dbg_nostore = ens[0] == '1';
+                    const char *ent = getenv("DDMPC_REG_NT");
+                    const int nt = ent ? atoi(ent) : 4;
+                    if (nt == 2) {
+                        if (a.w) k_closed_loop_reg<N, M, P, NX, NMPC, false, 2><<<ceil_div(a.B, 16), 32, 0, st>>>(mc, a, n_tail);
+                        else k_closed_loop_reg<N, M, P, NX, NMPC, true, 2><<<ceil_div(a.B, 16), 32, 0, st>>>(mc, a, n_tail);
+                    } else if (nt == 8) {
+                        if (a.w) k_closed_loop_reg<N, M, P, NX, NMPC, false, 8><<<ceil_div(a.B, 64), 32, 0, st>>>(mc, a, n_tail);
+                        else k_closed_loop_reg<N, M, P, NX, NMPC, true, 8><<<ceil_div(a.B, 64), 32, 0, st>>>(mc, a, n_tail);
+                    } else {
+                        if (a.w) k_closed_loop_reg<N, M, P, NX, NMPC, false, 4><<<ceil_div(a.B, 32), 32, 0, st>>>(mc, a, n_tail);
+                        else k_closed_loop_reg<N, M, P, NX, NMPC, true, 4><<<ceil_div(a.B, 32), 32, 0, st>>>(mc, a, n_tail);
+                    }
+                    DDMPC_LAUNCH_CHECK();
+                    return DDMPC_OK;
+                }
+            }
             if (want_ws && !want && pair && lpt == 2) {
                 MmaCoef<N, M, P, NX, NMPC> mc;
                 for (int k = 0; k < NMPC * M; ++k)

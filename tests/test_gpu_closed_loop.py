@@ -391,9 +391,10 @@ def test_batched_reproduction_matches_reference_semantics(golden_repro):
 
 
 def test_tensor_core_variants_match_hybrid(monkeypatch):
-    """The warp-specialised kernel (k_closed_loop_ws: math warp + i/o warp, the default for large batches) and the
-    opt-in single-warp k_closed_loop_mma (both: plant through the block map on the FP64 MMA pipe) vs the hybrid
-    fused kernel (DDMPC_WS=0), including a partial last block, uploaded noise and a ragged batch."""
+    """The warp-specialised kernel (k_closed_loop_ws, the default for large batches), the opt-in register-chained kernel
+    (k_closed_loop_reg, DDMPC_REG=1) and the opt-in single-warp k_closed_loop_mma (all three: plant through the block
+    map on the FP64 MMA pipe) vs the hybrid fused kernel (DDMPC_WS=0), including a partial last block, uploaded noise
+    and a ragged batch."""
     plant_o, prm, rng, x0, u_d, y_d = O.example_scenario(0)
     cs, _ = _set(u_d, y_d)
     B = 16384 + 70
@@ -409,19 +410,23 @@ def test_tensor_core_variants_match_hybrid(monkeypatch):
         monkeypatch.setenv("DDMPC_WS", "0")
         monkeypatch.delenv("DDMPC_PLANT_MMA", raising=False)
         u1, y1, s1, i1, x1 = cs.closed_loop(_plant(), xs, up0, yp0, us, ys, n_steps, want_x_final=True, **kw)
-        for env in (dict(DDMPC_WS="1"), dict(DDMPC_WS="0", DDMPC_PLANT_MMA="1")):
+        for env in (dict(DDMPC_WS="1"), dict(DDMPC_REG="1"), dict(DDMPC_REG="1", DDMPC_REG_NT="2"), dict(DDMPC_REG="1", DDMPC_REG_NT="8"),
+                    dict(DDMPC_WS="0", DDMPC_PLANT_MMA="1")):     # warp-specialised (default), register-chained NT = 4 / 2 / 8, single-warp MMA
             for k, v in env.items():
                 monkeypatch.setenv(k, v)
             u2, y2, s2, i2, x2 = cs.closed_loop(_plant(), xs, up0, yp0, us, ys, n_steps, want_x_final=True, **kw)
-            monkeypatch.delenv("DDMPC_PLANT_MMA", raising=False)
-            monkeypatch.delenv("DDMPC_WS", raising=False)
+            for k in ("DDMPC_PLANT_MMA", "DDMPC_WS", "DDMPC_REG", "DDMPC_REG_NT"):
+                monkeypatch.delenv(k, raising=False)
             assert int(s2.max()) == 0 and (i1 == i2).all(), env
             assert _rel(u2.cpu().numpy(), u1.cpu().numpy()) < 1e-9 and _rel(y2.cpu().numpy(), y1.cpu().numpy()) < 1e-9, env
             assert _rel(x2.cpu().numpy(), x1.cpu().numpy()) < 1e-9, env
 
 
-def test_warp_specialised_kernel_vs_oracle():
-    """Default large-batch path (k_closed_loop_ws) against the literal-KKT oracle on whole 401-step loops."""
+@pytest.mark.parametrize("reg", ["0", "1"])
+def test_warp_specialised_kernel_vs_oracle(reg, monkeypatch):
+    """Large-batch paths (k_closed_loop_ws by default, k_closed_loop_reg with DDMPC_REG=1) against the literal-KKT
+    oracle on whole 401-step loops."""
+    monkeypatch.setenv("DDMPC_REG", reg)
     plant_o, prm, rng, x0, u_d, y_d = O.example_scenario(0)
     cs, _ = _set(u_d, y_d)
     B, n_steps = 16384 + 3, 401
