@@ -21,24 +21,47 @@ std::atomic<uint64_t> g_launches{0};
 // ---------------------------------------------------------------------------
 // K1: Hankel gather.  H[row0 + r, col] = X[r + col * nch]   (hankel_matrix.py:47-51:
 // column i is X[i:i+L,:].flatten()).  Pure FP64 copy -> bit-exact.
-// grid: (ceil(cols/128), rows, batch); rowmap (optional) permutes output rows.
+// One CTA writes HK_ROWS consecutive rows of one matrix: the (tiny) data sequence is staged in shared memory once,
+// every output row is then written with unit-stride 8-byte stores, 256 B per warp instruction.  (The first version
+// gave every output element its own thread in 128-thread CTAs: 835,584 CTAs for 4096 four-tank controllers and
+// 1.9 TB/s; this one writes the same 0.76 GB at the HBM write rate.)  rowmap (optional) permutes output rows.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
+constexpr int HK_ROWS = 8;
+__global__ void __launch_bounds__(256)
 k_hankel(const double *__restrict__ X, long bsX, int nch, int rows, int cols, int row0,
-         const int *__restrict__ rowmap, double *__restrict__ H, long ldH, long bsH) {
-    const int col = blockIdx.x * blockDim.x + threadIdx.x;
-    const int r = blockIdx.y;
-    if (col >= cols || r >= rows) return;
-    const double *x = X + (long)blockIdx.z * bsX;
-    const int orow = rowmap ? rowmap[row0 + r] : row0 + r;
-    H[(long)blockIdx.z * bsH + (long)orow * ldH + col] = x[(long)r + (long)col * nch];
+         const int *__restrict__ rowmap, double *__restrict__ H, long ldH, long bsH, int in_smem) {
+    extern __shared__ double xs[];
+    const int nrb = (rows + HK_ROWS - 1) / HK_ROWS;          // 1-D grid: (matrix, row block)
+    const long bz = blockIdx.x / nrb;
+    const double *x = X + bz * bsX;
+    const int r0 = (int)(blockIdx.x % nrb) * HK_ROWS, r1 = min(r0 + HK_ROWS, rows);
+    // the rows r0..r1-1 read x[r0 .. r1-1 + (cols-1)*nch]
+    const int lo = r0, hi = (r1 - 1) + (cols - 1) * nch + 1;
+    if (in_smem) {
+        for (int e = lo + threadIdx.x; e < hi; e += blockDim.x) xs[e - lo] = x[e];
+        __syncthreads();
+    }
+    const double *src = in_smem ? xs - lo : x;
+    double *Hb = H + bz * bsH;
+    for (int r = r0; r < r1; ++r) {
+        const int orow = rowmap ? rowmap[row0 + r] : row0 + r;
+        double *dst = Hb + (long)orow * ldH;
+        for (int col = threadIdx.x; col < cols; col += blockDim.x) dst[col] = src[(long)r + (long)col * nch];
+    }
 }
 
 static int launch_hankel(cudaStream_t st, int batch, const double *X, long bsX, int N, int nch, int L,
                          int row0, const int *rowmap, double *H, long ldH, long bsH) {
     const int rows = L * nch, cols = N - L + 1;
-    dim3 grid(ceil_div(cols, 128), rows, batch);
-    k_hankel<<<grid, 128, 0, st>>>(X, bsX, nch, rows, cols, row0, rowmap, H, ldH, bsH);
+    const size_t sh = sizeof(double) * ((size_t)(HK_ROWS - 1) + (size_t)(cols - 1) * nch + 1);
+    const int in_smem = sh <= 96 * 1024;
+    if (in_smem && sh > 48 * 1024) {
+        static std::atomic<unsigned long long> attr_done{0};
+        if (first_time_on_device(attr_done))
+            DDMPC_CUDA(cudaFuncSetAttribute(k_hankel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    }
+    const long grid = (long)ceil_div(rows, HK_ROWS) * batch;
+    k_hankel<<<(unsigned)grid, 256, in_smem ? sh : 0, st>>>(X, bsX, nch, rows, cols, row0, rowmap, H, ldH, bsH, in_smem);
     DDMPC_LAUNCH_CHECK();
     return DDMPC_OK;
 }
