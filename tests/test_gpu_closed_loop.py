@@ -532,3 +532,37 @@ def test_config2_per_seed_variants_vs_oracle(name, ctype, slack, term, n_mpc, n_
         ctrl = O.make_controller(prm, ud[b], yd[b], n_mpc_step=n_mpc, use_terminal=term, slack_type=slack, ctrl_type=ctype)
         u_ref, y_ref = O.closed_loop(data[b][0], ctrl, n_steps, w[b])
         assert _rel(u[b], u_ref) < tol and _rel(y[b], y_ref) < tol, (name, b, _rel(u[b], u_ref))
+
+
+def test_config4_full_size_properties():
+    """BASELINE config 4 at full size (16,384 loops x 401 steps, n_mpc_step = 20) through the fused DMMA kernel: every
+    loop settles at its set-point, the batch equals the concatenation of two half-batch shards run with id offsets
+    (sharding invariance), and a loop matches the oracle."""
+    import torch
+    from direct_data_driven_mpc_b200 import ControllerSet, scenarios as S
+    B, n_steps = 16384, 401
+    sc = S.config4_batch(B, n_mpc_step=20)
+    prm, pl = sc["params"], sc["plant"]
+    cs = ControllerSet(20, 4, 4, sc["u_d"], sc["y_d"], 40, prm["Q"], prm["R"], prm["eps_max"], prm["lamb_alpha"],
+                       prm["lamb_sigma"], prm["c"], 0, 1, 20, True)
+    r = np.random.default_rng(4)
+    u_s = sc["u_s"] * r.uniform(0.8, 1.2, (B, 1))
+    y_s = u_s @ pl.equilibrium_gain().T
+    args = lambda lo, hi: (pl, sc["x0"][lo:hi], sc["u_past0"][lo:hi], sc["y_past0"][lo:hi], u_s[lo:hi], y_s[lo:hi], n_steps)
+    u, y, st, it = cs.closed_loop(*args(0, B), noise_seed=0, scenario_id0=0, noise_eps=0.002)
+    assert int(st.max()) == 0 and int(it.min()) == 21 and int(it.max()) == 21
+    assert float((y[:, -1] - torch.from_numpy(y_s).to(y.device)).abs().max()) < 0.02
+    half = B // 2
+    ua, ya, _, _ = cs.closed_loop(*args(0, half), noise_seed=0, scenario_id0=0, noise_eps=0.002)
+    ub, yb, _, _ = cs.closed_loop(*args(half, B), noise_seed=0, scenario_id0=half, noise_eps=0.002)
+    assert torch.equal(torch.cat([ua, ub]), u) and torch.equal(torch.cat([ya, yb]), y)
+    b = B - 1
+    w = O.philox_noise(0, np.array([b]), n_steps, 4, 0.002)[0]
+    qp = O.OracleController(20, 4, 4, sc["u_d"], sc["y_d"], 40, prm["Q"], prm["R"], u_s[b].reshape(-1, 1), y_s[b].reshape(-1, 1),
+                            prm["eps_max"], prm["lamb_alpha"], prm["lamb_sigma"], prm["c"], O.SLACK_NONE, O.ROBUST, 20, True,
+                            check_pe=False)
+    qp.set_past_input_output_data(sc["u_past0"][b].reshape(-1, 1), sc["y_past0"][b].reshape(-1, 1))
+    po = O.Plant(pl.A, pl.B, pl.C, pl.D, pl.eps_max)
+    po.x = sc["x0"][b].copy()
+    u_ref, y_ref = O.closed_loop(po, qp, n_steps, w)
+    assert _rel(u[b].cpu().numpy(), u_ref) < 1e-6 and _rel(y[b].cpu().numpy(), y_ref) < 1e-6
