@@ -609,267 +609,10 @@ k_closed_loop_fast(const __grid_constant__ FastCoef<N, M, P, NX, NMPC> cfp, cons
     }
 }
 
-// ===========================================================================
-// Two lanes per loop.  A 65,536-loop batch gives a B200 only 13.8 warps per SM with one thread per
-// loop, and the loop body is a chain of short dependent FP64 sequences: the one-thread kernel above
-// is latency-bound (ncu: 3.3 warps/scheduler, issue slots 40 % busy).  Here lanes (2q, 2q+1) of a warp
-// share loop q: each computes half of the planned-input rows of the solve, half of the state rows
-// and half of the output rows of every plant step, draws half of the block's Philox calls, and one
-// lane records u while the other records y.  Halves are exchanged with __shfl_xor / shared memory.
-// Twice the warps, half the registers, same total instruction count.
-// Requirements: NX, P and NMPC*M even; the unified 32-byte store path needs M == P == 2.
-// ===========================================================================
-template <int N, int M, int P, int NX, int NMPC>
-struct PairCoef {
-    double Kt[N * (M + P)][NMPC * M];   // Kt[j][k] = Ku[k][j]
-    double PA[2][NX / 2][NX];           // lane h: its state rows, columns ordered (own half, other half)
-    double PB[2][NX / 2][M];
-    double PC[2][P / 2][NX];            // lane h: its output rows, same column order
-    double PD[2][P / 2][M];
-};
-
-constexpr int PAIR_TPB = 128;           // 64 loops per block
-constexpr int PAIR_LOOPS = PAIR_TPB / 2;
-
-template <int N, int M, int P, int NX, int NMPC, bool PHILOX, bool PAIR>
-__global__ void __launch_bounds__(PAIR_TPB, 7)
-k_closed_loop_pair(const __grid_constant__ PairCoef<N, M, P, NX, NMPC> cfp, const FastArgs a) {
-    using Coef = PairCoef<N, M, P, NX, NMPC>;
-    constexpr int R = NMPC * M, RH = R / 2, XH = NX / 2, PH = P / 2;
-    constexpr bool ALIGNED = (NMPC % N) == 0;            // every block starts with the ring at slot 0
-    constexpr bool STATIC_NOISE = PHILOX && ((NMPC * P) % 4 == 0);
-    constexpr int NCALL = STATIC_NOISE ? (NMPC * P) / 4 : 1;
-    __shared__ __align__(16) Coef cf;
-    __shared__ double csp_s[R][PAIR_LOOPS];              // set-point term of the planned inputs
-    __shared__ double up_s[R][PAIR_LOOPS];               // planned inputs of the current block
-    __shared__ double wu_s[N * M][PAIR_LOOPS];           // measurement window, ring over N slots
-    __shared__ double wy_s[N * P][PAIR_LOOPS];
-    __shared__ double nz_s[STATIC_NOISE ? NMPC * P : 1][PAIR_LOOPS];   // block noise
-    {
-        const double *src = reinterpret_cast<const double *>(&cfp);
-        double *dst = reinterpret_cast<double *>(&cf);
-        for (int i = threadIdx.x; i < (int)(sizeof(Coef) / sizeof(double)); i += blockDim.x) dst[i] = src[i];
-    }
-    __syncthreads();
-    const int tid = threadIdx.x;
-    const int h = tid & 1;                               // which half of the work this lane does
-    const int sl = tid >> 1;                             // loop slot in the block
-    // loops of equal sector parity share a warp: slots 0..31 take even loops, 32..63 odd loops
-    const int b = blockIdx.x * PAIR_LOOPS + 2 * (sl % (PAIR_LOOPS / 2)) + (sl / (PAIR_LOOPS / 2));
-    const bool live = b < a.B;
-    const int bb = live ? b : 0;                         // dead pairs compute on loop 0 and never store
-    double xo[XH], xt[XH];                               // own / partner half of the plant state
-#pragma unroll
-    for (int i = 0; i < XH; ++i) {
-        xo[i] = a.x0[(size_t)bb * NX + h * XH + i];
-        xt[i] = a.x0[(size_t)bb * NX + (1 - h) * XH + i];
-    }
-    if (h == 0) {
-#pragma unroll
-        for (int i = 0; i < N * M; ++i) wu_s[i][sl] = a.u_past0[(size_t)bb * N * M + i];
-    } else {
-#pragma unroll
-        for (int i = 0; i < N * P; ++i) wy_s[i][sl] = a.y_past0[(size_t)bb * N * P + i];
-    }
-    {
-        double sp[M + P];
-#pragma unroll
-        for (int i = 0; i < M; ++i) sp[i] = a.u_s[(size_t)bb * M + i];
-#pragma unroll
-        for (int i = 0; i < P; ++i) sp[M + i] = a.y_s[(size_t)bb * P + i];
-#pragma unroll
-        for (int k = 0; k < RH; ++k) {
-            double acc = 0.0;
-#pragma unroll
-            for (int j = 0; j < M + P; ++j) acc = fma(__ldg(a.Ksp + (h * RH + k) * (M + P) + j), sp[j], acc);
-            csp_s[h * RH + k][sl] = acc;
-        }
-    }
-    __syncwarp();
-    const size_t f0 = (size_t)bb * a.n_steps;
-    const unsigned long long sid = a.id0 + (unsigned long long)bb;
-    const uint32_t sid_lo = (uint32_t)sid, sid_hi = (uint32_t)(sid >> 32);
-    // recording: lane 0 owns u_sys, lane 1 owns y_sys (element = 2 doubles when M == P == 2)
-    double *const rec = h ? a.y_sys : a.u_sys;
-    double pe0 = 0.0, pe1 = 0.0;                         // previous element of the recorded array
-
-    auto philox_call = [&](uint32_t call, uint32_t (&o)[4]) {
-        uint32_t c0 = call, c1 = 0u, c2 = sid_lo, c3 = sid_hi;
-#pragma unroll
-        for (int r = 0; r < 10; ++r) philox_round(c0, c1, c2, c3, a.rk[2 * r], a.rk[2 * r + 1]);
-        o[0] = c0; o[1] = c1; o[2] = c2; o[3] = c3;
-    };
-
-    auto block = [&](const int t0, auto guard) {
-        constexpr bool GUARD = decltype(guard)::value;
-        // opaque zero: keeps ptxas from hoisting the (loop-invariant) coefficient loads into registers
-        int zoff;
-        asm volatile("mov.u32 %0, 0;" : "=r"(zoff));
-        const Coef *c = &cf + zoff;
-        // ---- noise of the block: calls are split between the two lanes
-        if constexpr (STATIC_NOISE) {
-            const uint32_t call0 = (uint32_t)(((unsigned)t0 * (unsigned)P) >> 2);
-#pragma unroll
-            for (int cc = 0; cc < NCALL; ++cc) {
-                if ((cc & 1) == h || NCALL == 1) {
-                    uint32_t o[4];
-                    philox_call(call0 + (uint32_t)cc, o);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) nz_s[4 * cc + i][sl] = a.eps * (2.0 * unit32_fast(o[i]) - 3.0);
-                }
-            }
-        }
-        // ---- solve: this lane's half of the planned-input rows
-        {
-            double acc[RH];
-#pragma unroll
-            for (int k = 0; k < RH; ++k) acc[k] = csp_s[h * RH + k][sl + zoff];
-            const int base = ALIGNED ? 0 : (t0 % N);
-#pragma unroll
-            for (int jj = 0; jj < N; ++jj) {
-                const int slot = ALIGNED ? jj : ((base + jj) % N);
-#pragma unroll
-                for (int i = 0; i < M; ++i) {
-                    const double wj = wu_s[slot * M + i][sl];
-#pragma unroll
-                    for (int k = 0; k < RH; ++k) acc[k] = fma(c->Kt[jj * M + i][h * RH + k], wj, acc[k]);
-                }
-#pragma unroll
-                for (int i = 0; i < P; ++i) {
-                    const double wj = wy_s[slot * P + i][sl];
-#pragma unroll
-                    for (int k = 0; k < RH; ++k) acc[k] = fma(c->Kt[N * M + jj * P + i][h * RH + k], wj, acc[k]);
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < RH; ++k) up_s[h * RH + k][sl] = acc[k];
-        }
-        __syncwarp();
-        // ---- NMPC plant steps
-#pragma unroll
-        for (int s = 0; s < NMPC; ++s) {
-            const int k = t0 + s;
-            if (GUARD && k >= a.n_steps) break;
-            double u[M], yo[PH];
-#pragma unroll
-            for (int i = 0; i < M; ++i) u[i] = up_s[s * M + i][sl];
-            // measurement noise of this lane's output rows
-            if constexpr (!PHILOX) {
-#pragma unroll
-                for (int i = 0; i < PH; ++i) yo[i] = __ldg(a.w + (f0 + k) * P + h * PH + i);
-            } else if constexpr (STATIC_NOISE) {
-#pragma unroll
-                for (int i = 0; i < PH; ++i) yo[i] = nz_s[s * P + h * PH + i][sl];
-            } else {
-                uint32_t o[4] = {0u, 0u, 0u, 0u};
-                unsigned last = 0xffffffffu;
-#pragma unroll
-                for (int i = 0; i < PH; ++i) {
-                    const unsigned q = (unsigned)k * (unsigned)P + (unsigned)(h * PH + i);
-                    if ((q >> 2) != last) {
-                        last = q >> 2;
-                        philox_call(last, o);
-                    }
-                    const unsigned l = q & 3u;
-                    const uint32_t word = l == 0 ? o[0] : (l == 1 ? o[1] : (l == 2 ? o[2] : o[3]));
-                    yo[i] = a.eps * (2.0 * unit32_fast(word) - 3.0);
-                }
-            }
-            // y = C x + D u + w   (pre-update state; model_simulation.py:94)
-#pragma unroll
-            for (int i = 0; i < PH; ++i) {
-                double acc = 0.0, acd = 0.0;
-#pragma unroll
-                for (int j = 0; j < XH; ++j) acc = fma(c->PC[h][i][j], xo[j], acc);
-#pragma unroll
-                for (int j = 0; j < XH; ++j) acc = fma(c->PC[h][i][XH + j], xt[j], acc);
-#pragma unroll
-                for (int j = 0; j < M; ++j) acd = fma(c->PD[h][i][j], u[j], acd);
-                yo[i] = (acc + acd) + yo[i];
-            }
-            // x <- A x + B u      (model_simulation.py:96), own rows, then swap halves with the partner
-            double xn[XH];
-#pragma unroll
-            for (int i = 0; i < XH; ++i) {
-                double acc = 0.0, acb = 0.0;
-#pragma unroll
-                for (int j = 0; j < XH; ++j) acc = fma(c->PA[h][i][j], xo[j], acc);
-#pragma unroll
-                for (int j = 0; j < XH; ++j) acc = fma(c->PA[h][i][XH + j], xt[j], acc);
-#pragma unroll
-                for (int j = 0; j < M; ++j) acb = fma(c->PB[h][i][j], u[j], acb);
-                xn[i] = acc + acb;
-            }
-#pragma unroll
-            for (int i = 0; i < XH; ++i) {
-                xo[i] = xn[i];
-                xt[i] = __shfl_xor_sync(0xffffffffu, xn[i], 1);
-            }
-            // window update (controller.py:893-895): the oldest slot receives (u, y)
-            const int slot = ALIGNED ? (s % N) : (k % N);
-            if (h == 0) {
-#pragma unroll
-                for (int i = 0; i < M; ++i) wu_s[slot * M + i][sl] = u[i];
-            }
-#pragma unroll
-            for (int i = 0; i < PH; ++i) wy_s[slot * P + h * PH + i][sl] = yo[i];
-            // record
-            const size_t f = f0 + k;
-            if constexpr (M == 2 && P == 2) {
-                // lane 1 needs the partner's y row; lane 0 already holds both inputs
-                const double yp = __shfl_xor_sync(0xffffffffu, yo[0], 1);
-                const double e0 = h ? yp : u[0], e1 = h ? yo[0] : u[1];
-                if (live) {
-                    if constexpr (PAIR) {
-                        if (f & 1) {   // warp-uniform: completes the sector (f-1, f)
-                            if (k == 0) *reinterpret_cast<double2 *>(rec + f * 2) = make_double2(e0, e1);
-                            else
-                                asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(rec + (f - 1) * 2),
-                                             "d"(pe0), "d"(pe1), "d"(e0), "d"(e1)
-                                             : "memory");
-                        }
-                    } else {
-                        *reinterpret_cast<double2 *>(rec + f * 2) = make_double2(e0, e1);
-                    }
-                }
-                pe0 = e0;
-                pe1 = e1;
-            } else {
-                if (live) {
-                    if (h == 0) {
-#pragma unroll
-                        for (int i = 0; i < M; ++i) a.u_sys[f * M + i] = u[i];
-                    }
-#pragma unroll
-                    for (int i = 0; i < PH; ++i) a.y_sys[f * P + h * PH + i] = yo[i];
-                }
-            }
-        }
-        __syncwarp();
-    };
-
-    int t0 = 0;
-    for (; t0 + NMPC <= a.n_steps; t0 += NMPC) block(t0, std::false_type{});
-    if (t0 < a.n_steps) block(t0, std::true_type{});       // last, partial block (controller_operation.py:278)
-
-    if constexpr (PAIR && M == 2 && P == 2) {   // an unpaired final element is still in (pe0, pe1)
-        const size_t fl = f0 + a.n_steps - 1;
-        if (live && (fl & 1) == 0) *reinterpret_cast<double2 *>(rec + fl * 2) = make_double2(pe0, pe1);
-    }
-    bool finite = true;
-#pragma unroll
-    for (int i = 0; i < XH; ++i) finite = finite && isfinite(xo[i]) && isfinite(xt[i]);
-#pragma unroll
-    for (int i = 0; i < N * P; ++i) finite = finite && isfinite(wy_s[i][sl]);
-    if (live && h == 0) {
-        if (a.status) a.status[b] = finite ? DDMPC_SOLVE_OPTIMAL : DDMPC_SOLVE_NONFINITE;
-        if (a.iters) a.iters[b] = (a.n_steps + NMPC - 1) / NMPC;
-    }
-    if (live && a.x_final) {
-#pragma unroll
-        for (int i = 0; i < XH; ++i) a.x_final[(size_t)b * NX + h * XH + i] = xo[i];
-    }
-}
+// (A two-lanes-per-loop variant of the kernel above - each lane computing half of the rows of every product, halves
+// exchanged through shuffles - was measured and removed: twice the warps but also twice the shared-memory
+// instructions per loop, MIO-throttled at 0.49 ms against 0.34 ms on config 3.  Its ncu summary is kept in
+// profiles/r1_k_closed_loop_pair_experiment_ncu_full_summary.txt.)
 
 // ===========================================================================
 // All-tensor-core variant (four-tank n-step shape: 8 planned-input rows, NMPC a multiple of N, M = P = 2).
@@ -1722,59 +1465,6 @@ static int launch_fast(const ddmpc_set *set, const ddmpc_plant *plant, const Fas
 }
 
 
-template <int N, int M, int P, int NX, int NMPC>
-static int launch_pair(const ddmpc_set *set, const ddmpc_plant *plant, const FastArgs &fa, cudaStream_t st) {
-    using Coef = PairCoef<N, M, P, NX, NMPC>;
-    static_assert(sizeof(Coef) <= 3584, "coefficients must fit in the kernel parameter space");
-    static_assert(NX % 2 == 0 && P % 2 == 0 && (NMPC * M) % 2 == 0, "pair kernel needs even NX, P, NMPC*M");
-    const Dims &d = set->plan.d;
-    constexpr int NW = N * (M + P), XH = NX / 2, PH = P / 2;
-    auto &cache = set->fast_host;
-    const size_t need = (size_t)NMPC * M * d.nth;
-    if (cache.size() != need) {
-        cache.resize(need);
-        DDMPC_CUDA(cudaMemcpy(cache.data(), set->plan.Ku.d(), sizeof(double) * need, cudaMemcpyDeviceToHost));
-        DDMPC_CUDA(set->fast_ksp.alloc(sizeof(double) * NMPC * M * (M + P)));
-        k_gather_ksp<<<ceil_div(NMPC * M * (M + P), 128), 128, 0, st>>>(set->plan.Ku.d(), d.nth, NW, NMPC * M,
-                                                                          set->fast_ksp.d());
-        DDMPC_LAUNCH_CHECK();
-    }
-    Coef cf;
-    for (int k = 0; k < NMPC * M; ++k)
-        for (int j = 0; j < NW; ++j) cf.Kt[j][k] = cache[(size_t)k * d.nth + j];
-    for (int h = 0; h < 2; ++h) {
-        auto col = [&](int jj) { return jj < XH ? h * XH + jj : (1 - h) * XH + (jj - XH); };
-        for (int i = 0; i < XH; ++i) {
-            const int row = h * XH + i;
-            for (int jj = 0; jj < NX; ++jj) cf.PA[h][i][jj] = plant->A[row * NX + col(jj)];
-            for (int j = 0; j < M; ++j) cf.PB[h][i][j] = plant->B[row * M + j];
-        }
-        for (int i = 0; i < PH; ++i) {
-            const int row = h * PH + i;
-            for (int jj = 0; jj < NX; ++jj) cf.PC[h][i][jj] = plant->C[row * NX + col(jj)];
-            for (int j = 0; j < M; ++j) cf.PD[h][i][j] = plant->D[row * M + j];
-        }
-    }
-    FastArgs a = fa;
-    a.Ksp = set->fast_ksp.d();
-    for (int r = 0; r < 10; ++r) {
-        a.rk[2 * r] = (uint32_t)a.seed + (uint32_t)r * 0x9E3779B9u;
-        a.rk[2 * r + 1] = (uint32_t)(a.seed >> 32) + (uint32_t)r * 0xBB67AE85u;
-    }
-    const dim3 grid(ceil_div(a.B, PAIR_LOOPS));
-    const bool pair = (M == 2 && P == 2) && ((reinterpret_cast<uintptr_t>(a.u_sys) & 31) == 0) &&
-                      ((reinterpret_cast<uintptr_t>(a.y_sys) & 31) == 0);
-    if (a.w) {
-        if (pair) k_closed_loop_pair<N, M, P, NX, NMPC, false, true><<<grid, PAIR_TPB, 0, st>>>(cf, a);
-        else k_closed_loop_pair<N, M, P, NX, NMPC, false, false><<<grid, PAIR_TPB, 0, st>>>(cf, a);
-    } else {
-        if (pair) k_closed_loop_pair<N, M, P, NX, NMPC, true, true><<<grid, PAIR_TPB, 0, st>>>(cf, a);
-        else k_closed_loop_pair<N, M, P, NX, NMPC, true, false><<<grid, PAIR_TPB, 0, st>>>(cf, a);
-    }
-    DDMPC_LAUNCH_CHECK();
-    return DDMPC_OK;
-}
-
 // Returns DDMPC_OK when the fast kernel handled the call, -1 when it does not apply.
 int closed_loop_fast_try(const ddmpc_set *set, const ddmpc_plant *plant, int B, const int *ctrl_idx, const double *x0,
                          const double *u_past0, const double *y_past0, const double *u_s, const double *y_s,
@@ -1797,19 +1487,6 @@ int closed_loop_fast_try(const ddmpc_set *set, const ddmpc_plant *plant, int B, 
 #define DDMPC_FAST_CASE(N_, M_, P_, NX_, NMPC_)                                                    \
     if (d.n == N_ && d.m == M_ && d.p == P_ && plant->n_x == NX_ && nmpc == NMPC_)                 \
         return launch_fast<N_, M_, P_, NX_, NMPC_>(set, plant, fa, st);
-    // The two-lanes-per-loop kernel is an experiment kept for reference: it doubles
-    // the warps per SM but also doubles the shared-memory instructions per loop and ends up
-    // MIO-throttled (0.49 ms vs 0.34 ms on config 3).  Opt in with DDMPC_TWO_LANES=1.
-    const char *two = getenv("DDMPC_TWO_LANES");
-    if (two && two[0] == '1' && !d.convex) {
-#define DDMPC_PAIR_CASE(N_, M_, P_, NX_, NMPC_)                                                    \
-    if (d.n == N_ && d.m == M_ && d.p == P_ && plant->n_x == NX_ && nmpc == NMPC_)                 \
-        return launch_pair<N_, M_, P_, NX_, NMPC_>(set, plant, fa, st);
-        DDMPC_PAIR_CASE(4, 2, 2, 4, 4)   // four-tank, n-step scheme (configs 1, 3; TEC-n-step)
-        DDMPC_PAIR_CASE(4, 2, 2, 4, 1)   // four-tank, 1-step schemes (TEC, UCON)
-        DDMPC_PAIR_CASE(4, 2, 2, 4, 2)
-#undef DDMPC_PAIR_CASE
-    }
     DDMPC_FAST_CASE(4, 2, 2, 4, 4)
     DDMPC_FAST_CASE(4, 2, 2, 4, 1)
     DDMPC_FAST_CASE(4, 2, 2, 4, 2)
