@@ -1113,10 +1113,17 @@ k_closed_loop_ws(const __grid_constant__ MmaCoef<N, M, P, NX, NMPC> cfp, const F
 // that step's u and y (16 B each; the four lanes of a loop write 64 contiguous bytes).
 // A warp carries NT m-tiles (8 NT loops) as independent DMMA chains.
 // ===========================================================================
-template <int N, int M, int P, int NX, int NMPC, bool PHILOX, int NT>
+// XP (needs NT = 4): the block's results are transposed through 4 KB of shared memory private to the warp, so that
+// lane l records loop l of the warp's 32 as full 32-byte sectors (the pairing rule of emit()) instead of 16-byte pieces.
+template <int N, int M, int P, int NX, int NMPC, bool PHILOX, int NT, bool XP = false>
 __global__ void __launch_bounds__(32, NT >= 8 ? 7 : 14)
 k_closed_loop_reg(const __grid_constant__ MmaCoef<N, M, P, NX, NMPC> cfp, const FastArgs a, const int n_tail) {
     constexpr int R = NMPC * M, RY = NMPC * P, NU = N * M;
+    static_assert(!XP || NT == 4, "the transposing variant carries 32 loops per warp");
+    __shared__ __align__(16) double2 xu_s[XP ? 32 * NMPC : 1], xy_s[XP ? 32 * NMPC : 1];
+    // chunk (loop, step) -> 16-byte slot: conflict-free for the writers (lane (g, q): loop 8mt + g, step q) and the reader
+    // (lane l: loop l, one step at a time); see k_closed_loop_rws
+    auto CH = [](int loop, int s) { return ((loop ^ ((loop >> 3) & 1)) << 2) | (s ^ ((loop >> 1) & 3)); };
     static_assert(M == 2 && P == 2 && R == 8 && RY == 8 && NX == 4 && NMPC == N, "shape not supported by the register-chained kernel");
     const int lane = threadIdx.x, g = lane >> 2, q = lane & 3;
     const int nblk = (a.n_steps + NMPC - 1) / NMPC;
@@ -1136,6 +1143,12 @@ k_closed_loop_reg(const __grid_constant__ MmaCoef<N, M, P, NX, NMPC> cfp, const 
         }
     };
     load_plant(cfp.Mb);
+    // Keep the coefficients in registers: left alone, the compiler re-fetches them inside the loop with LANE-INDEXED
+    // constant loads (c[0x0][R + off]: 32 different addresses per warp = 32 serialised constant-cache accesses each).
+#pragma unroll
+    for (int i = 0; i < 4; ++i) asm volatile("" : "+d"(bK[i]));
+#pragma unroll
+    for (int i = 0; i < 6; ++i) asm volatile("" : "+d"(bP[i / 3][i % 3]));
     auto mma = [](double2 &c, double av, double bv) {
         asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
             : "+d"(c.x), "+d"(c.y)
@@ -1169,6 +1182,11 @@ k_closed_loop_reg(const __grid_constant__ MmaCoef<N, M, P, NX, NMPC> cfp, const 
         }
         csp[mt] = make_double2(c0, c1);
     }
+    // transposing variant: lane records loop `bo`
+    const int bo = blockIdx.x * NT * 8 + lane;
+    const bool olive = bo < a.B;
+    const size_t of0 = (size_t)(olive ? bo : 0) * a.n_steps;
+    double2 pu = make_double2(0.0, 0.0), py = pu;              // previous trajectory element (sector pairing)
     for (int t = 0; t < nblk; ++t) {
         const int steps = (t == nblk - 1 && n_tail != 0) ? n_tail : NMPC;
         if (t == nblk - 1 && n_tail != 0) load_plant(cfp.Mt);   // last, partial block (controller_operation.py:278)
@@ -1212,9 +1230,40 @@ k_closed_loop_reg(const __grid_constant__ MmaCoef<N, M, P, NX, NMPC> cfp, const 
 #pragma unroll
         for (int mt = 0; mt < NT; ++mt) { mma(d0[mt], nu[mt].y, bP[0][2]); mma(d1[mt], nu[mt].y, bP[1][2]); }
         // ---- record step q, hand the block over to the next one
+        if constexpr (XP) {
+            __syncwarp();                                      // the previous block has been read out
+#pragma unroll
+            for (int mt = 0; mt < NT; ++mt) {
+                xu_s[CH(8 * mt + g, q)] = nu[mt];
+                xy_s[CH(8 * mt + g, q)] = d0[mt];
+            }
+            __syncwarp();
+#pragma unroll
+            for (int s = 0; s < NMPC; ++s) {
+                if (s < steps) {
+                    const double2 u = xu_s[CH(lane, s)], y = xy_s[CH(lane, s)];
+                    const size_t f = of0 + (size_t)(t * NMPC + s);
+                    if (olive && (f & 1) && !a.dbg_nostore) {      // completes the sector (f - 1, f)
+                        if (t == 0 && s == 0) {
+                            *reinterpret_cast<double2 *>(a.u_sys + f * 2) = u;
+                            *reinterpret_cast<double2 *>(a.y_sys + f * 2) = y;
+                        } else {
+                            asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(a.u_sys + (f - 1) * 2), "d"(pu.x),
+                                         "d"(pu.y), "d"(u.x), "d"(u.y)
+                                         : "memory");
+                            asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(a.y_sys + (f - 1) * 2), "d"(py.x),
+                                         "d"(py.y), "d"(y.x), "d"(y.y)
+                                         : "memory");
+                        }
+                    }
+                    pu = u;
+                    py = y;
+                }
+            }
+        }
 #pragma unroll
         for (int mt = 0; mt < NT; ++mt) {
-            if (live[mt] && q < steps && !a.dbg_nostore) {
+            if (!XP && live[mt] && q < steps && !a.dbg_nostore) {
                 const size_t f = (size_t)b[mt] * a.n_steps + k;
                 *reinterpret_cast<double2 *>(a.u_sys + f * M) = nu[mt];
                 *reinterpret_cast<double2 *>(a.y_sys + f * P) = d0[mt];
@@ -1226,6 +1275,13 @@ k_closed_loop_reg(const __grid_constant__ MmaCoef<N, M, P, NX, NMPC> cfp, const 
             const int src = (lane & ~3) | (q >> 1);
             const double v0 = __shfl_sync(0xffffffffu, d1[mt].x, src), v1 = __shfl_sync(0xffffffffu, d1[mt].y, src);
             xA[mt] = (q & 1) ? v1 : v0;
+        }
+    }
+    if constexpr (XP) {
+        const size_t fl = of0 + a.n_steps - 1;
+        if (olive && (fl & 1) == 0 && !a.dbg_nostore) {          // an unpaired final element is still in (pu, py)
+            *reinterpret_cast<double2 *>(a.u_sys + fl * 2) = pu;
+            *reinterpret_cast<double2 *>(a.y_sys + fl * 2) = py;
         }
     }
     // ---- per-loop results (loop g = lanes 4g .. 4g+3)
@@ -1240,6 +1296,280 @@ k_closed_loop_reg(const __grid_constant__ MmaCoef<N, M, P, NX, NMPC> cfp, const 
             if (a.iters) a.iters[b[mt]] = nblk;
         }
         if (live[mt] && a.x_final) a.x_final[(size_t)b[mt] * NX + q] = xA[mt];
+    }
+}
+
+// ===========================================================================
+// Register-chained math warps + a DECOUPLED i/o warp (the two ideas above combined).
+//
+// Two math warps run the register-chained recurrence of k_closed_loop_reg on 4 m-tiles (32 loops) each; what
+// they exchange with the i/o warp is only the block's results and its noise, as 16-byte chunks (one step of one
+// loop: lane (g, q) of m-tile mt owns chunk (loop 8mt + g, step q)): per block and m-tile one LDS.128 (the noise,
+// which initialises the output accumulator) and two STS.128 (planned inputs, outputs) instead of the 12 shared-
+// memory accesses per m-tile of k_closed_loop_ws.  The i/o warp is that kernel's: lane tl owns loops 2tl, 2tl+1,
+// draws noise and records results as full 32-byte sectors.
+// Because the window lives in registers, the shared buffers are pure hand-over queues, so the warps need not run
+// in lock-step: instead of one __syncthreads per block there are two rings of mbarriers,
+//     full[t % 3]  "noise of block t is in wy_s[t % 3]"            i/o lane 0 arrives, math warps wait
+//     done[t % 3]  "results of block t are in up_s[t % 3], wy_s[t % 3]"   lane 0 of each math warp arrives, i/o waits
+// and the i/o warp's order   draw(j + 2); wait done[j]; record(j)   lets the math warps run up to two blocks ahead of
+// the trajectory stores (full[t] is signalled after record(t - 3), which is what frees buffer t % 3), and the math
+// warps never wait for each other.
+// Chunk (loop, s) sits at 16-byte slot ((loop ^ bit3(loop)) << 2) | (s ^ ((loop >> 1) & 3)): a quarter-warp of a
+// math warp (loops 2j, 2j+1, all four steps) and a quarter-warp of the i/o warp (8 consecutive even or odd loops,
+// one step) then both touch eight different 16-byte bank groups.
+// ===========================================================================
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+    const unsigned addr = (unsigned)__cvta_generic_to_shared(bar);
+    unsigned ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok)
+                     : "r"(addr), "r"(parity)
+                     : "memory");
+    } while (!ok);
+}
+
+template <int N, int M, int P, int NX, int NMPC, bool PHILOX>
+__global__ void __launch_bounds__(96, 7)   // 7 CTAs = 21 warps per SM = 6 per scheduler -> at most 80 registers (16K per scheduler)
+k_closed_loop_rws(const __grid_constant__ MmaCoef<N, M, P, NX, NMPC> cfp, const FastArgs a, const int n_tail) {
+    constexpr int R = NMPC * M, RY = NMPC * P, NU = N * M, NT = 4, LC = 64, LPT = 2;
+    static_assert(M == 2 && P == 2 && R == 8 && RY == 8 && NX == 4 && NMPC == N && NMPC == 4, "shape not supported by the register-chained kernel");
+    __shared__ __align__(16) double2 wy_s[3][LC * NMPC];       // noise, then outputs, of block t in buffer t % 3
+    __shared__ __align__(16) double2 up_s[3][LC * NMPC];       // planned inputs of block t in buffer t % 3
+    __shared__ __align__(16) double2 csp_s[LC * NMPC];         // set-point term of the planned inputs (same chunk layout)
+    __shared__ __align__(8) uint64_t full_b[3], done_b[3];
+    auto CH = [](int loop, int s) { return ((loop ^ ((loop >> 3) & 1)) << 2) | (s ^ ((loop >> 1) & 3)); };
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nblk = (a.n_steps + NMPC - 1) / NMPC;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            mbar_init(&full_b[i], 1);
+            mbar_init(&done_b[i], 2);
+        }
+    }
+    __syncthreads();
+
+    if (warp == 2) {
+        // ------------------------------------------------------------------ i/o warp: lane owns loops 2 lane, 2 lane + 1
+        int b[LPT];
+        bool live[LPT];
+        size_t f0[LPT];
+        uint32_t sid_lo[LPT], sid_hi[LPT];
+        double2 pu[LPT], py[LPT];                // previous trajectory element (sector pairing)
+#pragma unroll
+        for (int l = 0; l < LPT; ++l) {
+            b[l] = blockIdx.x * LC + 2 * lane + l;
+            live[l] = b[l] < a.B;
+            if (!live[l]) b[l] = a.B - 1;        // dead slots replay the last loop and never store
+            f0[l] = (size_t)b[l] * a.n_steps;
+            const unsigned long long sid = a.id0 + (unsigned long long)b[l];
+            sid_lo[l] = (uint32_t)sid;
+            sid_hi[l] = (uint32_t)(sid >> 32);
+            pu[l] = py[l] = make_double2(0.0, 0.0);
+        }
+        // noise of block tb into wy_s[tb & 3] (word qs & 3 of Philox call tb*NMPC*P/4 + (qs >> 2), qs = s*P + i), then signal
+        auto draw = [&](const int tb, const int buf) {
+#pragma unroll
+            for (int l = 0; l < LPT; ++l) {
+                const int loop = 2 * lane + l;
+                if constexpr (PHILOX) {
+#pragma unroll
+                    for (int cc = 0; cc < RY / 4; ++cc) {
+                        uint32_t c0 = (uint32_t)(((unsigned)tb * (unsigned)RY) >> 2) + (uint32_t)cc, c1 = 0u,
+                                 c2 = sid_lo[l], c3 = sid_hi[l];
+#pragma unroll
+                        for (int r = 0; r < 10; ++r) philox_round(c0, c1, c2, c3, a.rk[2 * r], a.rk[2 * r + 1]);
+                        wy_s[buf][CH(loop, 2 * cc)] =
+                            make_double2(a.eps * (2.0 * unit32_fast(c0) - 3.0), a.eps * (2.0 * unit32_fast(c1) - 3.0));
+                        wy_s[buf][CH(loop, 2 * cc + 1)] =
+                            make_double2(a.eps * (2.0 * unit32_fast(c2) - 3.0), a.eps * (2.0 * unit32_fast(c3) - 3.0));
+                    }
+                } else {
+#pragma unroll
+                    for (int s = 0; s < NMPC; ++s) {
+                        const int k = tb * NMPC + s;
+                        wy_s[buf][CH(loop, s)] = k < a.n_steps ? __ldg(reinterpret_cast<const double2 *>(a.w + (f0[l] + k) * P))
+                                                               : make_double2(0.0, 0.0);
+                    }
+                }
+            }
+            __syncwarp();                                  // every lane's chunks are written before lane 0 signals
+            if (lane == 0) mbar_arrive(&full_b[buf]);
+        };
+        // record the `steps` trajectory elements of block tb (full 32-byte sectors, see emit())
+        auto record = [&](const int tb, const int ub, const int steps) {
+            const int yb = ub;
+#pragma unroll
+            for (int l = 0; l < LPT; ++l) {
+                const int loop = 2 * lane + l;
+#pragma unroll
+                for (int s = 0; s < NMPC; ++s) {
+                    if (s < steps) {
+                        const int k = tb * NMPC + s;
+                        const double2 u = up_s[ub][CH(loop, s)], y = wy_s[yb][CH(loop, s)];
+                        const size_t f = f0[l] + k;
+                        if (live[l] && (f & 1) && !a.dbg_nostore) {   // warp-uniform: completes the sector (f-1, f)
+                            if (k == 0) {
+                                *reinterpret_cast<double2 *>(a.u_sys + f * 2) = u;
+                                *reinterpret_cast<double2 *>(a.y_sys + f * 2) = y;
+                            } else {
+                                asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(a.u_sys + (f - 1) * 2),
+                                             "d"(pu[l].x), "d"(pu[l].y), "d"(u.x), "d"(u.y)
+                                             : "memory");
+                                asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(a.y_sys + (f - 1) * 2),
+                                             "d"(py[l].x), "d"(py[l].y), "d"(y.x), "d"(y.y)
+                                             : "memory");
+                            }
+                        }
+                        pu[l] = u;
+                        py[l] = y;
+                    }
+                }
+            }
+        };
+        draw(0, 0);
+        if (nblk > 1) draw(1, 1);
+        int ub = 0;                                        // j % 3
+        unsigned ph = 0u;                                  // (j / 3) & 1
+        for (int j = 0; j < nblk; ++j) {
+            if (j + 2 < nblk) draw(j + 2, ub == 0 ? 2 : ub - 1);   // (j + 2) % 3: that buffer was last read by record(j - 1)
+            mbar_wait(&done_b[ub], ph);
+            record(j, ub, (j == nblk - 1 && n_tail) ? n_tail : NMPC);
+            if (ub == 2) { ub = 0; ph ^= 1u; } else ++ub;
+        }
+#pragma unroll
+        for (int l = 0; l < LPT; ++l) {
+            const size_t fl = f0[l] + a.n_steps - 1;
+            if (live[l] && (fl & 1) == 0 && !a.dbg_nostore) {   // an unpaired final element is still in (pu, py)
+                *reinterpret_cast<double2 *>(a.u_sys + fl * 2) = pu[l];
+                *reinterpret_cast<double2 *>(a.y_sys + fl * 2) = py[l];
+            }
+        }
+        return;
+    }
+
+    // ---------------------------------------------------------------------- math warps (see k_closed_loop_reg)
+    const int g = lane >> 2, q = lane & 3;
+    double bK[4], bP[2][3];
+    bK[0] = cfp.Ku[g][2 * q];          bK[1] = cfp.Ku[g][2 * q + 1];
+    bK[2] = cfp.Ku[g][NU + 2 * q];     bK[3] = cfp.Ku[g][NU + 2 * q + 1];
+    auto load_plant = [&](const double (&Mb)[NMPC * P + NX][NX + NMPC * M]) {
+#pragma unroll
+        for (int tile = 0; tile < 2; ++tile) {
+            const int row = 8 * tile + g;
+            const bool valid = row < RY + NX;
+            const int rr = valid ? row : 0;
+            bP[tile][0] = valid ? Mb[rr][q] : 0.0;
+            bP[tile][1] = valid ? Mb[rr][NX + 2 * q] : 0.0;
+            bP[tile][2] = valid ? Mb[rr][NX + 2 * q + 1] : 0.0;
+        }
+    };
+    load_plant(cfp.Mb);
+    // Keep the coefficients in registers: left alone, the compiler re-fetches them inside the loop with LANE-INDEXED
+    // constant loads (c[0x0][R + off], 32 different addresses per warp = 32 serialised constant-cache accesses each).
+#pragma unroll
+    for (int i = 0; i < 4; ++i) asm volatile("" : "+d"(bK[i]));
+#pragma unroll
+    for (int i = 0; i < 6; ++i) asm volatile("" : "+d"(bP[i / 3][i % 3]));
+    auto mma = [](double2 &c, double av, double bv) {
+        asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+            : "+d"(c.x), "+d"(c.y)
+            : "d"(av), "d"(bv));
+    };
+    // chunk of m-tile mt: CH(32 warp + 8 mt + g, q) = ((mt & 1) ? chO : chE) + 32 mt
+    const int chE = CH(32 * warp + g, q), chO = CH(32 * warp + (g ^ 1), q);
+    const int b0 = blockIdx.x * LC + 32 * warp + g;
+    double2 uC[NT], yC[NT];
+    double xA[NT];
+#pragma unroll
+    for (int mt = 0; mt < NT; ++mt) {
+        const size_t bb = (size_t)min(b0 + 8 * mt, a.B - 1);    // dead rows replay the last loop and never store
+        uC[mt] = *reinterpret_cast<const double2 *>(a.u_past0 + bb * NU + 2 * q);
+        yC[mt] = *reinterpret_cast<const double2 *>(a.y_past0 + bb * (N * P) + 2 * q);
+        xA[mt] = a.x0[bb * NX + q];
+        double sp[M + P];
+#pragma unroll
+        for (int i = 0; i < M; ++i) sp[i] = a.u_s[bb * M + i];
+#pragma unroll
+        for (int i = 0; i < P; ++i) sp[M + i] = a.y_s[bb * P + i];
+        double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+        for (int j = 0; j < M + P; ++j) {
+            c0 = fma(__ldg(a.Ksp + (2 * q) * (M + P) + j), sp[j], c0);
+            c1 = fma(__ldg(a.Ksp + (2 * q + 1) * (M + P) + j), sp[j], c1);
+        }
+        csp_s[((mt & 1) ? chO : chE) + 32 * mt] = make_double2(c0, c1);   // read back by the same lane only
+    }
+    int cu = 0;                                            // t % 3
+    unsigned ph = 0u;                                      // (t / 3) & 1
+    for (int t = 0; t < nblk; ++t) {
+        if (t == nblk - 1 && n_tail != 0) {                // last, partial block (controller_operation.py:278)
+            load_plant(cfp.Mt);
+#pragma unroll
+            for (int i = 0; i < 6; ++i) asm volatile("" : "+d"(bP[i / 3][i % 3]));
+        }
+        // two m-tiles at a time: 80 registers hold the windows of all four but the accumulators of only two
+#pragma unroll
+        for (int h = 0; h < NT; h += 2) {
+            double2 nu[2], d0[2], d1[2];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                d1[i] = make_double2(0.0, 0.0);
+                nu[i] = csp_s[(((h + i) & 1) ? chO : chE) + 32 * (h + i)];
+            }
+            // the input half of the solve does not need the noise: start it before waiting
+#pragma unroll
+            for (int i = 0; i < 2; ++i) { mma(nu[i], uC[h + i].x, bK[0]); mma(d1[i], xA[h + i], bP[1][0]); }
+#pragma unroll
+            for (int i = 0; i < 2; ++i) mma(nu[i], uC[h + i].y, bK[1]);
+            if (h == 0) mbar_wait(&full_b[cu], ph);        // noise of block t is there, and buffer cu has been recorded
+#pragma unroll
+            for (int i = 0; i < 2; ++i) d0[i] = wy_s[cu][(((h + i) & 1) ? chO : chE) + 32 * (h + i)];   // accumulator starts from the noise
+#pragma unroll
+            for (int i = 0; i < 2; ++i) { mma(nu[i], yC[h + i].x, bK[2]); mma(d0[i], xA[h + i], bP[0][0]); }
+#pragma unroll
+            for (int i = 0; i < 2; ++i) mma(nu[i], yC[h + i].y, bK[3]);
+#pragma unroll
+            for (int i = 0; i < 2; ++i) { mma(d0[i], nu[i].x, bP[0][1]); mma(d1[i], nu[i].x, bP[1][1]); }
+#pragma unroll
+            for (int i = 0; i < 2; ++i) { mma(d0[i], nu[i].y, bP[0][2]); mma(d1[i], nu[i].y, bP[1][2]); }
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int mt = h + i;
+                up_s[cu][((mt & 1) ? chO : chE) + 32 * mt] = nu[i];
+                wy_s[cu][((mt & 1) ? chO : chE) + 32 * mt] = d0[i];
+                uC[mt] = nu[i];
+                yC[mt] = d0[i];
+                const int src = (lane & ~3) | (q >> 1);          // state entry q of loop g: lane (g, q >> 1), component q & 1
+                const double v0 = __shfl_sync(0xffffffffu, d1[i].x, src), v1 = __shfl_sync(0xffffffffu, d1[i].y, src);
+                xA[mt] = (q & 1) ? v1 : v0;
+            }
+        }
+        __syncwarp();                                      // every lane's chunks are written before lane 0 signals
+        if (lane == 0) mbar_arrive(&done_b[cu]);
+        if (cu == 2) { cu = 0; ph ^= 1u; } else ++cu;
+    }
+#pragma unroll
+    for (int mt = 0; mt < NT; ++mt) {
+        const int bm = b0 + 8 * mt;
+        const bool live = bm < a.B;
+        const int sl = (n_tail ? n_tail : NMPC) - 1;             // last recorded step of the last block
+        const bool fin = isfinite(xA[mt]) && (q != sl || (isfinite(yC[mt].x) && isfinite(yC[mt].y)));
+        const unsigned badm = __ballot_sync(0xffffffffu, !fin);
+        const bool loop_bad = ((badm >> (4 * g)) & 0xfu) != 0u;
+        if (live && q == 0) {
+            if (a.status) a.status[bm] = loop_bad ? DDMPC_SOLVE_NONFINITE : DDMPC_SOLVE_OPTIMAL;
+            if (a.iters) a.iters[bm] = nblk;
+        }
+        if (live && a.x_final) a.x_final[(size_t)bm * NX + q] = xA[mt];
     }
 }
 
@@ -1373,7 +1703,7 @@ static int launch_fast(const ddmpc_set *set, const ddmpc_plant *plant, const Fas
             // step of a loop, i.e. 16-byte stores, and those cost far more than the shared-memory hand-over they save
             // (0.33-0.44 ms in total); pairing them into sectors needs the same transposition again.
             const char *ereg = getenv("DDMPC_REG");
-            const bool want_reg = ereg ? ereg[0] == '1' : false;
+            const bool want_reg = ereg ? (ereg[0] >= '1' && ereg[0] <= '3') : false;
             if constexpr (NX == 4) {
                 if (want_reg && want_ws && !want && pair && lpt == 2 && (reinterpret_cast<uintptr_t>(a.u_past0) & 15) == 0 &&
                     (reinterpret_cast<uintptr_t>(a.y_past0) & 15) == 0 && (!a.w || (reinterpret_cast<uintptr_t>(a.w) & 15) == 0)) {
@@ -1386,7 +1716,18 @@ static int launch_fast(const ddmpc_set *set, const ddmpc_plant *plant, const Fas
                     if (const char *ens = getenv("DDMPC_DEBUG_NOSTORE")) a.dbg_nostore = ens[0] == '1';
                     const char *ent = getenv("DDMPC_REG_NT");
                     const int nt = ent ? atoi(ent) : 4;
-                    if (nt == 2) {
+                    if (ereg[0] == '2') {                            // register-chained math warps + decoupled i/o warp
+                        auto go = [&](auto kern) -> int {
+                            DDMPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+                            kern<<<ceil_div(a.B, 64), 96, 0, st>>>(mc, a, n_tail);
+                            return DDMPC_OK;
+                        };
+                        const int rc = a.w ? go(k_closed_loop_rws<N, M, P, NX, NMPC, false>) : go(k_closed_loop_rws<N, M, P, NX, NMPC, true>);
+                        if (rc != DDMPC_OK) return rc;
+                    } else if (ereg[0] == '3') {                     // register-chained, results transposed per warp (sector stores)
+                        if (a.w) k_closed_loop_reg<N, M, P, NX, NMPC, false, 4, true><<<ceil_div(a.B, 32), 32, 0, st>>>(mc, a, n_tail);
+                        else k_closed_loop_reg<N, M, P, NX, NMPC, true, 4, true><<<ceil_div(a.B, 32), 32, 0, st>>>(mc, a, n_tail);
+                    } else if (nt == 2) {
                         if (a.w) k_closed_loop_reg<N, M, P, NX, NMPC, false, 2><<<ceil_div(a.B, 16), 32, 0, st>>>(mc, a, n_tail);
                         else k_closed_loop_reg<N, M, P, NX, NMPC, true, 2><<<ceil_div(a.B, 16), 32, 0, st>>>(mc, a, n_tail);
                     } else if (nt == 8) {
