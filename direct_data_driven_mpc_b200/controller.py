@@ -291,8 +291,10 @@ class DirectDataDrivenMPCController:
             raise ValueError(f"Incorrect dimensions. Expected dimensions are {expected_u0_dim} for u_current and "
                              f"{expected_y0_dim} for y_current, but got {u_current.shape} and {y_current.shape} "
                              "instead.")
-        self.u_past = np.vstack([self.u_past[self.m:], u_current])     # controller.py:893
-        self.y_past = np.vstack([self.y_past[self.p:], y_current])     # controller.py:895
+        # controller.py:893-895 (np.vstack there; both operands are 2-D columns here, so concatenate is the same array
+        # without vstack's atleast_2d pass: 1 us less per call on the per-step path)
+        self.u_past = np.concatenate((self.u_past[self.m:], u_current))
+        self.y_past = np.concatenate((self.y_past[self.p:], y_current))
 
     def set_past_input_output_data(self, u_past: np.ndarray, y_past: np.ndarray) -> None:
         expected_u_dim, expected_y_dim = (self.n * self.m, 1), (self.n * self.p, 1)
