@@ -566,3 +566,47 @@ def test_config4_full_size_properties():
     po.x = sc["x0"][b].copy()
     u_ref, y_ref = O.closed_loop(po, qp, n_steps, w)
     assert _rel(u[b].cpu().numpy(), u_ref) < 1e-6 and _rel(y[b].cpu().numpy(), y_ref) < 1e-6
+
+
+def test_set_lifecycle_returns_device_memory():
+    """Create / use / destroy a controller set many times (batched solve, B = 1 staged host path with its mapped buffer
+    and private stream, large fused closed loop): after ddmpc_trim_memory() the device's free memory is back where it
+    started, i.e. nothing the library allocates outlives the set that owns it."""
+    import torch
+    from direct_data_driven_mpc_b200 import _lib
+    plant_o, prm, rng, x0, u_d, y_d = O.example_scenario(0)
+    B = 20000
+    xs = np.tile(plant_o.x, (B, 1))
+    us, ys = np.tile(prm["u_s"].T, (B, 1)), np.tile(prm["y_s"].T, (B, 1))
+    up0, yp0 = np.tile(u_d[-4:].reshape(1, -1), (B, 1)), np.tile(y_d[-4:].reshape(1, -1), (B, 1))
+
+    from direct_data_driven_mpc_b200 import (DataDrivenMPCType, DirectDataDrivenMPCController,
+                                             SlackVarConstraintTypes)
+
+    def cycle():
+        ctrl = DirectDataDrivenMPCController(                            # B = 1: staged host path (solve #0 + one more)
+            n=4, m=2, p=2, u_d=u_d, y_d=y_d, L=30, Q=prm["Q"], R=prm["R"], u_s=prm["u_s"], y_s=prm["y_s"],
+            eps_max=0.002, lamb_alpha=prm["lamb_alpha"], lamb_sigma=1000, c=1.0,
+            slack_var_constraint_type=SlackVarConstraintTypes.NONE, controller_type=DataDrivenMPCType.ROBUST,
+            n_mpc_step=4, use_terminal_constraint=True)
+        ctrl.update_and_solve_data_driven_mpc()
+        del ctrl
+        cs, _ = _set(u_d, y_d)
+        cs.solve_batch(up0[:300], yp0[:300], us[:300], ys[:300])
+        u, y, st, it = cs.closed_loop(_plant(), xs, up0, yp0, us, ys, 41, noise_seed=1, noise_eps=0.002)
+        assert int(st.max()) == 0
+        del u, y, st, it
+        cs.close()
+
+    cycle()                                                              # first use: module load, pool creation
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    _lib.trim_memory()
+    free0, _ = torch.cuda.mem_get_info()
+    for _ in range(12):
+        cycle()
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    _lib.trim_memory()
+    free1, _ = torch.cuda.mem_get_info()
+    assert free0 - free1 < 32 * 2**20, (free0, free1)
