@@ -215,6 +215,9 @@ k_closed_loop_dmma(const DmmaArgs a) {
     const int cps = p >> 2;                                   // Philox calls per step (4 noise words each)
     bool fin[2] = {true, true};
     int base = 0, n_iter = 0;                                 // ring slot of the oldest window entry
+    // (slot within the block, channel) of the plant-table entry this lane rotates: no division inside the loop
+    const bool pRot = lane < a.ksP && 4 * lane >= nx;
+    const int pj = pRot ? (4 * lane - nx) / m : 0, pi = pRot ? (4 * lane - nx) % m : 0;
     // small shapes: the A fragments of the block map stay in registers for the whole run
     constexpr bool PLANT_REG = KSP > 0 && MTP * KSP <= 24;
     double aP[PLANT_REG ? MTP * KSP : 1];
@@ -227,6 +230,9 @@ k_closed_loop_dmma(const DmmaArgs a) {
     for (int t0 = 0; t0 < a.n_steps; t0 += nmpc, ++n_iter) {
         const int steps = min(nmpc, a.n_steps - t0);
         const double *MF = steps == nmpc ? a.MbF : a.MtF;
+        // a non-finite input or output turns the state non-finite for good (x+ = A x + B u, the window feeds u), so
+        // looking at the outputs and the state of the last block is enough
+        const bool last = t0 + nmpc >= a.n_steps;
         // ---- solve: planned inputs of the block
         double2 uo[MTS];
         dl_gemm<MTS, KSS>(a.KuF, a.ksS, tabS, tb, lane, uo);
@@ -246,7 +252,7 @@ k_closed_loop_dmma(const DmmaArgs a) {
         // ---- measurement noise of the block, parked in the output slots of the ring (the old outputs there have
         // been consumed by the solve): word qw = k*p + i is word (qw & 3) of Philox call (qw >> 2)
         for (int c = lane >> 3; c < steps * cps; c += 4) {
-            const int s = c / cps, i0 = 4 * (c - s * cps), k = t0 + s;
+            const int s = cps == 1 ? c : c / cps, i0 = 4 * (c - s * cps), k = t0 + s;
             double nz[4];
             if (a.w) {
 #pragma unroll
@@ -266,13 +272,16 @@ k_closed_loop_dmma(const DmmaArgs a) {
             for (int i = 0; i < 4; ++i) tile[(r + i) * 8 + SW(r + i, lane & 7)] = nz[i];
         }
         // rotate the U entries of the plant table to this block's slots, then the plant GEMM
-        for (int ks = lane; ks < a.ksP; ks += 32) {
+        if (pRot) {
+            int slot = base + pj;
+            if (slot >= n) slot -= n;
+            tabP[lane] = 8 * (slot * m + pi);
+        }
+        for (int ks = lane + 32; ks < a.ksP; ks += 32) {
             const int e0 = 4 * ks;
-            if (e0 >= nx) {
-                int slot = base + (e0 - nx) / m;
-                if (slot >= n) slot -= n;
-                tabP[ks] = 8 * (slot * m + (e0 - nx) % m);
-            }
+            int slot = base + (e0 - nx) / m;
+            if (slot >= n) slot -= n;
+            tabP[ks] = 8 * (slot * m + (e0 - nx) % m);
         }
         __syncwarp();
         // ---- plant: outputs of the block and the state after it
@@ -302,14 +311,18 @@ k_closed_loop_dmma(const DmmaArgs a) {
                     const size_t f = (size_t)(t0 + sY[j]) * p + iY[j];
                     if (live[0]) yrow[0][f] = y.x;
                     if (live[1]) yrow[1][f] = y.y;
-                    fin[0] = fin[0] && isfinite(y.x);
-                    fin[1] = fin[1] && isfinite(y.y);
+                    if (last) {
+                        fin[0] = fin[0] && isfinite(y.x);
+                        fin[1] = fin[1] && isfinite(y.y);
+                    }
                 }
             } else if (row < RY + nx) {
                 const int r = oX + (row - RY);
                 *reinterpret_cast<double2 *>(&tile[r * 8 + SW(r, 2 * q)]) = yo[j];
-                fin[0] = fin[0] && isfinite(yo[j].x);
-                fin[1] = fin[1] && isfinite(yo[j].y);
+                if (last) {
+                    fin[0] = fin[0] && isfinite(yo[j].x);
+                    fin[1] = fin[1] && isfinite(yo[j].y);
+                }
             }
         }
         // ---- rotate the ring entries of the solve table by `steps` slots

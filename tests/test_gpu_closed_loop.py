@@ -610,3 +610,57 @@ def test_set_lifecycle_returns_device_memory():
     _lib.trim_memory()
     free1, _ = torch.cuda.mem_get_info()
     assert free0 - free1 < 32 * 2**20, (free0, free1)
+
+
+def test_nonfinite_inputs_flag_only_their_own_loops(monkeypatch):
+    """Status DDMPC_SOLVE_NONFINITE (3) for exactly the loops that were given a NaN / Inf initial state, set-point or
+    window, on every closed-loop kernel: generic, hybrid, warp-specialised and the register-chained variants (four-tank),
+    the fused FP64 tensor-core kernel and the generic one (config 4)."""
+    from direct_data_driven_mpc_b200 import ControllerSet, scenarios as S
+    plant_o, prm, rng, x0, u_d, y_d = O.example_scenario(0)
+    cs, _ = _set(u_d, y_d)
+    bad = {5: "x0", 77: "u_s", 4100: "y_past", 16390: "x0"}
+    for B, envs in ((300, (dict(DDMPC_FORCE_GENERIC="1"), dict())),
+                    (16384 + 9, (dict(), dict(DDMPC_WS="0"), dict(DDMPC_REG="1"), dict(DDMPC_REG="2"), dict(DDMPC_REG="3")))):
+        xs = np.tile(plant_o.x, (B, 1))
+        us, ys = np.tile(prm["u_s"].T, (B, 1)), np.tile(prm["y_s"].T, (B, 1))
+        up0, yp0 = np.tile(u_d[-4:].reshape(1, -1), (B, 1)), np.tile(y_d[-4:].reshape(1, -1), (B, 1))
+        expect = np.zeros(B, dtype=np.int32)
+        for b, what in bad.items():
+            if b >= B:
+                continue
+            expect[b] = 3
+            if what == "x0":
+                xs[b, 2] = np.nan
+            elif what == "u_s":
+                us[b, 0] = np.inf
+            else:
+                yp0[b, 3] = np.nan
+        for env in envs:
+            for k, v in env.items():
+                monkeypatch.setenv(k, v)
+            u, y, st, it = cs.closed_loop(_plant(), xs, up0, yp0, us, ys, 41, noise_seed=2, noise_eps=0.002)
+            for k in env:
+                monkeypatch.delenv(k, raising=False)
+            assert np.array_equal(st.cpu().numpy(), expect), (B, env, np.nonzero(st.cpu().numpy() != expect)[0][:8])
+            good = expect == 0
+            assert np.isfinite(u.cpu().numpy()[good]).all() and np.isfinite(y.cpu().numpy()[good]).all()
+    for n_mpc in (1, 20):
+        B = 520
+        sc = S.config4_batch(B, n_mpc_step=n_mpc)
+        p4, pl = sc["params"], sc["plant"]
+        c4 = ControllerSet(p4["n"], 4, 4, sc["u_d"], sc["y_d"], p4["L"], p4["Q"], p4["R"], p4["eps_max"],
+                           p4["lamb_alpha"], p4["lamb_sigma"], p4["c"], 0, 1, n_mpc, True)
+        xs, us, up0 = sc["x0"].copy(), sc["u_s"].copy(), sc["u_past0"].copy()
+        expect = np.zeros(B, dtype=np.int32)
+        xs[3, 7] = np.nan
+        us[258, 1] = -np.inf
+        up0[519, 11] = np.nan
+        expect[[3, 258, 519]] = 3
+        for env in (dict(), dict(DDMPC_FORCE_GENERIC="1")):
+            for k, v in env.items():
+                monkeypatch.setenv(k, v)
+            u, y, st, it = c4.closed_loop(pl, xs, up0, sc["y_past0"], us, sc["y_s"], 45, noise_seed=2, noise_eps=0.002)
+            for k in env:
+                monkeypatch.delenv(k, raising=False)
+            assert np.array_equal(st.cpu().numpy(), expect), (n_mpc, env, np.nonzero(st.cpu().numpy() != expect)[0][:8])
