@@ -156,9 +156,16 @@ __device__ __forceinline__ void dl_gemm_reg(const double (&areg)[MT * KS], const
 
 // DL_WARPS warps (n-tiles of 8 loops) per CTA.  The warps are independent (no block-level barrier), so the CTA size only
 // sets the granularity with which the batch is dealt to the SMs.
-template <int MTS, int MTP, int KSS, int KSP, int DL_WARPS>
+// KU, KY > 0 (small shapes, one m-tile of planned inputs): k-steps of the input and output halves of the window.  The solve
+// then walks the ring in PHYSICAL slot order - the order of the terms of a dot product is free - so its B operands sit at
+// compile-time offsets of the tile, and the rotation moves to the A side: the gain fragments of each half are stored
+// twice in a row, and the fragment of physical k-step j is entry j + (K - base * k-steps-per-slot) of that doubled run.
+// No row table, no table rotation, no address arithmetic per DMMA.
+template <int MTS, int MTP, int KSS, int KSP, int DL_WARPS, int KU = 0, int KY = 0>
 __global__ void __launch_bounds__(32 * DL_WARPS, 16 / DL_WARPS)
 k_closed_loop_dmma(const DmmaArgs a) {
+    constexpr bool PHYS = KU > 0 && KY > 0;
+    static_assert(!PHYS || (MTS == 1 && KSS > KU + KY), "physical-order solve: one m-tile, compile-time k-step counts");
     extern __shared__ __align__(16) double dl_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, q = lane & 3;
     const int n = a.n, m = a.m, p = a.p, nx = a.nx, nmpc = a.nmpc;
@@ -188,9 +195,11 @@ k_closed_loop_dmma(const DmmaArgs a) {
         tile[r * 8 + SW(r, col)] = v;
     }
     // ---- offset tables for ring base 0 (entries of ring rows rotate by `steps` slots after every block)
-    for (int ks = lane; ks < a.ksS; ks += 32) {
-        const int e0 = 4 * ks;                                // theta order: window_u, window_y, set-points
-        tabS[ks] = 8 * (e0 < nm + npp ? e0 : oSP + (e0 - nm - npp));
+    if constexpr (!PHYS) {
+        for (int ks = lane; ks < a.ksS; ks += 32) {
+            const int e0 = 4 * ks;                            // theta order: window_u, window_y, set-points
+            tabS[ks] = 8 * (e0 < nm + npp ? e0 : oSP + (e0 - nm - npp));
+        }
     }
     for (int ks = lane; ks < a.ksP; ks += 32) {
         const int e0 = 4 * ks;                                // [x; U]: U of step s sits in ring slot (base + s) % n
@@ -233,9 +242,46 @@ k_closed_loop_dmma(const DmmaArgs a) {
         // a non-finite input or output turns the state non-finite for good (x+ = A x + B u, the window feeds u), so
         // looking at the outputs and the state of the last block is enough
         const bool last = t0 + nmpc >= a.n_steps;
+        // noise words 4c .. 4c+3 of the block (word qw = k*p + i is word (qw & 3) of Philox call (qw >> 2)) for loop lane % 8
+        auto draw = [&](const int c, double (&nz)[4]) {
+            const int s = cps == 1 ? c : c / cps, i0 = 4 * (c - s * cps), k = t0 + s;
+            if (a.w) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) nz[i] = __ldg(a.w + ((size_t)nb_ * a.n_steps + k) * p + i0 + i);
+            } else {
+                uint32_t o[4];
+                dl_philox((unsigned)k * (unsigned)cps + (unsigned)(c - s * cps), (uint32_t)(nsid & 0xffffffffu),
+                          (uint32_t)(nsid >> 32), (uint32_t)(a.seed & 0xffffffffu), (uint32_t)(a.seed >> 32), o);
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    nz[i] = a.eps * (2.0 * __hiloint2double((int)(0x3FF00000u | (o[i] >> 12)), (int)(o[i] << 20)) - 3.0);
+            }
+        };
         // ---- solve: planned inputs of the block
         double2 uo[MTS];
-        dl_gemm<MTS, KSS>(a.KuF, a.ksS, tabS, tb, lane, uo);
+        if constexpr (PHYS) {
+            constexpr int KP = KSS - KU - KY;                  // k-steps of the set-point rows
+            const double *apU = a.KuF + (size_t)(KU - base * (m >> 2)) * 32 + lane;
+            const double *apY = a.KuF + (size_t)(2 * KU + KY - base * (p >> 2)) * 32 + lane;
+            const double *apS = a.KuF + (size_t)(2 * KU + 2 * KY) * 32 + lane;
+            constexpr int NA = 8;                              // independent accumulator chains (a 2048-warp batch gives a
+            double2 acc[NA];                                   // scheduler only 3-4 warps to hide the DMMA latency with)
+#pragma unroll
+            for (int i = 0; i < NA; ++i) acc[i] = make_double2(0.0, 0.0);
+#pragma unroll
+            for (int ks = 0; ks < KU; ++ks) dl_mma(acc[ks % NA], __ldg(apU + 32 * ks), tb[32 * ks]);
+#pragma unroll
+            for (int ks = 0; ks < KY; ++ks) dl_mma(acc[(KU + ks) % NA], __ldg(apY + 32 * ks), tb[32 * (KU + ks)]);
+#pragma unroll
+            for (int ks = 0; ks < KP; ++ks) dl_mma(acc[(KU + KY + ks) % NA], __ldg(apS + 32 * ks), tb[32 * (KU + KY + ks)]);
+#pragma unroll
+            for (int w = NA / 2; w >= 1; w >>= 1)
+#pragma unroll
+                for (int i = 0; i < w; ++i) { acc[i].x += acc[i + w].x; acc[i].y += acc[i + w].y; }
+            uo[0] = acc[0];
+        } else {
+            dl_gemm<MTS, KSS>(a.KuF, a.ksS, tabS, tb, lane, uo);
+        }
         __syncwarp();                                         // every lane has read the old window
 #pragma unroll
         for (int j = 0; j < MTS; ++j) {
@@ -250,21 +296,11 @@ k_closed_loop_dmma(const DmmaArgs a) {
             }
         }
         // ---- measurement noise of the block, parked in the output slots of the ring (the old outputs there have
-        // been consumed by the solve): word qw = k*p + i is word (qw & 3) of Philox call (qw >> 2)
+        // been consumed by the solve)
         for (int c = lane >> 3; c < steps * cps; c += 4) {
-            const int s = cps == 1 ? c : c / cps, i0 = 4 * (c - s * cps), k = t0 + s;
+            const int s = cps == 1 ? c : c / cps, i0 = 4 * (c - s * cps);
             double nz[4];
-            if (a.w) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) nz[i] = __ldg(a.w + ((size_t)nb_ * a.n_steps + k) * p + i0 + i);
-            } else {
-                uint32_t o[4];
-                dl_philox((unsigned)k * (unsigned)cps + (unsigned)(c - s * cps), (uint32_t)(nsid & 0xffffffffu),
-                          (uint32_t)(nsid >> 32), (uint32_t)(a.seed & 0xffffffffu), (uint32_t)(a.seed >> 32), o);
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    nz[i] = a.eps * (2.0 * __hiloint2double((int)(0x3FF00000u | (o[i] >> 12)), (int)(o[i] << 20)) - 3.0);
-            }
+            draw(c, nz);
             int slot = base + s;
             if (slot >= n) slot -= n;
             const int r = oWY + slot * p + i0;
@@ -328,11 +364,13 @@ k_closed_loop_dmma(const DmmaArgs a) {
         // ---- rotate the ring entries of the solve table by `steps` slots
         base += steps;
         if (base >= n) base -= n;
-        for (int ks = lane; ks < a.ksS; ks += 32) {
-            int o = tabS[ks];
-            if (o < 8 * oWY) { o += 8 * steps * m; if (o >= 8 * oWY) o -= 8 * nm; }
-            else if (o < 8 * oSP) { o += 8 * steps * p; if (o >= 8 * oSP) o -= 8 * npp; }
-            tabS[ks] = o;
+        if constexpr (!PHYS) {
+            for (int ks = lane; ks < a.ksS; ks += 32) {
+                int o = tabS[ks];
+                if (o < 8 * oWY) { o += 8 * steps * m; if (o >= 8 * oWY) o -= 8 * nm; }
+                else if (o < 8 * oSP) { o += 8 * steps * p; if (o >= 8 * oSP) o -= 8 * npp; }
+                tabS[ks] = o;
+            }
         }
         __syncwarp();
     }
@@ -369,12 +407,13 @@ static void pack_fragments(const double *M, int ld, int rows, int cols, int mt, 
             }
 }
 
-template <int MTS, int MTP, int KSS, int KSP, int DL_WARPS>
+template <int MTS, int MTP, int KSS, int KSP, int DL_WARPS, int KU, int KY>
 static int launch_dmma_w(const DmmaArgs &a, size_t smem_per_warp, cudaStream_t st) {
     const size_t smem = smem_per_warp * DL_WARPS;
-    DDMPC_CUDA(cudaFuncSetAttribute(k_closed_loop_dmma<MTS, MTP, KSS, KSP, DL_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    DDMPC_CUDA(cudaFuncSetAttribute(k_closed_loop_dmma<MTS, MTP, KSS, KSP, DL_WARPS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    k_closed_loop_dmma<MTS, MTP, KSS, KSP, DL_WARPS><<<ceil_div(a.B, 8 * DL_WARPS), 32 * DL_WARPS, smem, st>>>(a);
+    auto kern = k_closed_loop_dmma<MTS, MTP, KSS, KSP, DL_WARPS, KU, KY>;
+    DDMPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DDMPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    kern<<<ceil_div(a.B, 8 * DL_WARPS), 32 * DL_WARPS, smem, st>>>(a);
     DDMPC_LAUNCH_CHECK();
     return DDMPC_OK;
 }
@@ -383,16 +422,16 @@ static int launch_dmma_w(const DmmaArgs &a, size_t smem_per_warp, cudaStream_t s
 // 13 per SM instead of 16 or 12 with CTAs of four) and measured 6 % faster than CTAs of 2 or 4 on config 4
 // (1.455 vs 1.541 / 1.553 ms per 401-step pass, 0.903 vs 0.953 / 0.951 ms with n_mpc_step = 20);
 // DDMPC_DMMA_WARPS=2|4 selects the larger ones.
-template <int MTS, int MTP, int KSS, int KSP>
+template <int MTS, int MTP, int KSS, int KSP, int KU = 0, int KY = 0>
 static int launch_dmma(const DmmaArgs &a, size_t smem_per_warp, cudaStream_t st) {
     int best = 1;
     if (const char *e = getenv("DDMPC_DMMA_WARPS")) {
         const int v = atoi(e);
         if (v == 1 || v == 2 || v == 4) best = v;
     }
-    if (best == 4) return launch_dmma_w<MTS, MTP, KSS, KSP, 4>(a, smem_per_warp, st);
-    if (best == 2) return launch_dmma_w<MTS, MTP, KSS, KSP, 2>(a, smem_per_warp, st);
-    return launch_dmma_w<MTS, MTP, KSS, KSP, 1>(a, smem_per_warp, st);
+    if (best == 4) return launch_dmma_w<MTS, MTP, KSS, KSP, 4, KU, KY>(a, smem_per_warp, st);
+    if (best == 2) return launch_dmma_w<MTS, MTP, KSS, KSP, 2, KU, KY>(a, smem_per_warp, st);
+    return launch_dmma_w<MTS, MTP, KSS, KSP, 1, KU, KY>(a, smem_per_warp, st);
 }
 
 // Returns DDMPC_OK when handled, -1 when this path does not apply.
@@ -411,7 +450,8 @@ int closed_loop_dmma_try(const ddmpc_set *set, const ddmpc_plant *plant, int B, 
     const int R = nmpc * m, rowsP = nmpc * p + nx, colsP = nx + R;
     const int mtS = ceil_div(R, 8), mtP = ceil_div(rowsP, 8), ksS = nth / 4, ksP = colsP / 4;
     // compiled shapes: config 4 (n = 20, m = p = 4, n_x = 20) with n_mpc = 1 (straight-line products) and n_mpc = 20
-    const bool shape1 = mtS == 1 && mtP == 3 && ksS == 42 && ksP == 6, shape20 = mtS == 10 && mtP == 13;
+    const bool shape1 = mtS == 1 && mtP == 3 && ksS == 42 && ksP == 6 && n * m == 80 && n * p == 80,
+               shape20 = mtS == 10 && mtP == 13;
     if (!shape1 && !shape20) return -1;
     const int rows = n * (m + p) + m + p + nx;
     const size_t smem = sizeof(double) * ((size_t)rows * 8 + (((((ksS + 3) & ~3) + ((ksP + 3) & ~3)) / 2 + 1) & ~1));   // per warp
@@ -424,12 +464,27 @@ int closed_loop_dmma_try(const ddmpc_set *set, const ddmpc_plant *plant, int B, 
     key.insert(key.end(), plant->C, plant->C + (size_t)p * nx);
     key.insert(key.end(), plant->D, plant->D + (size_t)p * m);
     key.push_back((double)rem);
-    const size_t nKu = (size_t)mtS * ksS * 32, nMb = (size_t)mtP * ksP * 32;
+    // shape 1 walks the window in physical slot order: each half of the gain is stored twice in a row (see the kernel)
+    const int ksKu = shape1 ? (2 * n * m + 2 * n * p + m + p) / 4 : ksS;
+    const size_t nKu = (size_t)mtS * ksKu * 32, nMb = (size_t)mtP * ksP * 32;
     if (set->dmma_key != key || set->dmma_ws.bytes < sizeof(double) * (nKu + 2 * nMb)) {
         DDMPC_CUDA(cudaDeviceSynchronize());                  // loops still reading the previous operands
         std::vector<double> hKu((size_t)R * nth), fKu, fMb, fMt;
         DDMPC_CUDA(cudaMemcpy(hKu.data(), set->plan.Ku.d(), sizeof(double) * hKu.size(), cudaMemcpyDeviceToHost));
-        pack_fragments(hKu.data(), nth, R, nth, mtS, ksS, fKu);
+        if (shape1) {
+            const int nm = n * m, npp = n * p, c2 = 2 * nm + 2 * npp + m + p;
+            std::vector<double> K2((size_t)R * c2);
+            for (int r = 0; r < R; ++r) {
+                const double *src = hKu.data() + (size_t)r * nth;
+                double *dst = K2.data() + (size_t)r * c2;
+                for (int c = 0; c < nm; ++c) dst[c] = dst[nm + c] = src[c];
+                for (int c = 0; c < npp; ++c) dst[2 * nm + c] = dst[2 * nm + npp + c] = src[nm + c];
+                for (int c = 0; c < m + p; ++c) dst[2 * nm + 2 * npp + c] = src[nm + npp + c];
+            }
+            pack_fragments(K2.data(), c2, R, c2, mtS, ksKu, fKu);
+        } else {
+            pack_fragments(hKu.data(), nth, R, nth, mtS, ksS, fKu);
+        }
         const std::vector<double> Mb = block_map(plant, nmpc);
         pack_fragments(Mb.data(), colsP, rowsP, colsP, mtP, ksP, fMb);
         // last, partial block (controller_operation.py:278): its block map in the layout of the full one
@@ -456,7 +511,7 @@ int closed_loop_dmma_try(const ddmpc_set *set, const ddmpc_plant *plant, int B, 
     a.x0 = x0; a.u_past0 = u_past0; a.y_past0 = y_past0; a.u_s = u_s; a.y_s = y_s; a.w = w;
     a.seed = seed; a.id0 = id0; a.eps = eps;
     a.u_sys = u_sys; a.y_sys = y_sys; a.x_final = x_final; a.status = status; a.iters = iters;
-    if (shape1) return launch_dmma<1, 3, 42, 6>(a, smem, st);
+    if (shape1) return launch_dmma<1, 3, 42, 6, 20, 20>(a, smem, st);
     return launch_dmma<10, 13, 0, 0>(a, smem, st);
 }
 

@@ -14,5 +14,6 @@ for w in (None, "4", "2", "1") if "--all" in sys.argv else (None,):
         os.environ.pop("DDMPC_DMMA_WARPS", None)
     else:
         os.environ["DDMPC_DMMA_WARPS"] = w
-    r = bench.secondary_config4(torch.device("cuda", 0))
-    print("warps/CTA", w or "auto", json.dumps({k: {kk: round(vv, 4) for kk, vv in v.items()} for k, v in r.items() if k.startswith("n_mpc")}), flush=True)
+    B = int(os.environ.get("CONFIG4_LOOPS", "16384"))
+    r = bench.secondary_config4(torch.device("cuda", 0), B)
+    print("loops", B, "warps/CTA", w or "auto", json.dumps({k: {kk: round(vv, 4) for kk, vv in v.items()} for k, v in r.items() if k.startswith("n_mpc")}), flush=True)
