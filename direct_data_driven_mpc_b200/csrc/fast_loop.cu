@@ -852,13 +852,19 @@ k_closed_loop_mma(const __grid_constant__ MmaCoef<N, M, P, NX, NMPC> cfp, const 
 // same buffer in the same iteration except to read.  Same arithmetic as k_closed_loop_mma except that the noise
 // is the first instead of the last summand of y.
 // ===========================================================================
-template <int N, int M, int P, int NX, int NMPC, bool PHILOX, int MW>
+template <int N, int M, int P, int NX, int NMPC, bool PHILOX, int MW, bool MD = (MW == 4)>
 __global__ void __launch_bounds__(32 * (MW + 1), 7)
 k_closed_loop_ws(const __grid_constant__ MmaCoef<N, M, P, NX, NMPC> cfp, const FastArgs a, const int n_tail) {
     constexpr int R = NMPC * M, NW = N * (M + P), LPT = 2, TP = 36, NT = 4;
     constexpr int KB = NX + R, RB = NMPC * P + NX, RY = NMPC * P;
-    constexpr int LM = LPT / MW;                               // loop groups (of 32 loops) per math warp
-    static_assert(MW == 1 || MW == 2, "one or two math warps");
+    constexpr int LM = MW == 1 ? LPT : 1;                      // loop groups (of 32 loops) per math warp
+    constexpr int WPG = MW == 4 ? 2 : 1;                       // math warps per loop group (they split its n-tiles)
+    constexpr int NTW = NT / WPG;                              // n-tiles (of 8 loops) per math warp and loop group
+    static_assert(MW == 1 || MW == 2 || MW == 4, "one, two or four math warps");
+    // MD: every math warp draws the Philox noise of its own loops (32 / WPG calls per block) and the i/o warp only
+    // records: a single warp doing both is as long a dependency chain as the math of a block.
+    constexpr bool MATH_DRAWS = MD && PHILOX;
+    static_assert(!MD || MW >= 2, "math warps draw their own noise only with one loop group per warp");
     static_assert(M == 2 && P == 2 && R == 8 && NMPC == N, "shape not supported by the warp-specialised kernel");
     static_assert(NW % 4 == 0 && (N * M) % 4 == 0 && KB % 4 == 0 && NX % 4 == 0 && RB <= 16 && RY == 8, "fragment tiling");
     __shared__ __align__(16) double csp_s[R][LPT][TP];         // set-point term of the planned inputs
@@ -885,7 +891,8 @@ k_closed_loop_ws(const __grid_constant__ MmaCoef<N, M, P, NX, NMPC> cfp, const F
     }
     __syncthreads();
     const int warp = (threadIdx.x >> 5) ^ swap_s;
-    const int l0 = MW == 2 ? warp : 0;             // first loop group of this math warp
+    const int l0 = MW == 1 ? 0 : warp / WPG;       // first loop group of this math warp
+    const int t80 = (warp % WPG) * NTW;            // its first n-tile inside the group
     const int cb = g ^ (((q >> 1) & 1) << 2);      // swizzled column of a B-fragment element (row = 4ks + q)
     const int cc2 = (2 * q) ^ (((g >> 1) & 1) << 2);  // swizzled column of a C-fragment pair (row = g)
 
@@ -985,11 +992,11 @@ k_closed_loop_ws(const __grid_constant__ MmaCoef<N, M, P, NX, NMPC> cfp, const F
                 }
             }
         };
-        draw(0, 0);
+        if (!MATH_DRAWS) draw(0, 0);
         __syncthreads();                                   // window, state and noise of block 0 are in place
         for (int t = 0; t < nblk; ++t) {
             if (t > 0) record(t - 1, NMPC);
-            if (t + 1 < nblk) draw(t + 1, (t + 1) % 3);
+            if (!MATH_DRAWS && t + 1 < nblk) draw(t + 1, (t + 1) % 3);
             __syncthreads();                               // block t is complete
         }
         record(nblk - 1, n_tail ? n_tail : NMPC);
@@ -1028,10 +1035,30 @@ k_closed_loop_ws(const __grid_constant__ MmaCoef<N, M, P, NX, NMPC> cfp, const F
             : "+d"(c.x), "+d"(c.y)
             : "d"(av), "d"(bv));
     };
+    // noise of block tb for the warp's own loops: lane = (column, Philox call); see the i/o warp's draw()
+    constexpr int CPL = RY / 4 / WPG;                      // Philox calls per lane and block
+    const int ncol = WPG == 2 ? 8 * t80 + (tl >> 1) : tl, ncc0 = WPG == 2 ? (tl & 1) : 0;
+    const unsigned long long nsid = a.id0 + (unsigned long long)min(blockIdx.x * 64 + 2 * ncol + l0, a.B - 1);
+    auto mdraw = [&](const int tb, const int buf) {
+#pragma unroll
+        for (int ci = 0; ci < CPL; ++ci) {
+            const int ncc = ncc0 + ci;
+            uint32_t c0 = (uint32_t)(((unsigned)tb * (unsigned)RY) >> 2) + (uint32_t)ncc, c1 = 0u, c2 = (uint32_t)nsid,
+                     c3 = (uint32_t)(nsid >> 32);
+#pragma unroll
+            for (int r = 0; r < 10; ++r) philox_round(c0, c1, c2, c3, a.rk[2 * r], a.rk[2 * r + 1]);
+            wy_s[buf][4 * ncc + 0][l0][SW(4 * ncc + 0, ncol)] = a.eps * (2.0 * unit32_fast(c0) - 3.0);
+            wy_s[buf][4 * ncc + 1][l0][SW(4 * ncc + 1, ncol)] = a.eps * (2.0 * unit32_fast(c1) - 3.0);
+            wy_s[buf][4 * ncc + 2][l0][SW(4 * ncc + 2, ncol)] = a.eps * (2.0 * unit32_fast(c2) - 3.0);
+            wy_s[buf][4 * ncc + 3][l0][SW(4 * ncc + 3, ncol)] = a.eps * (2.0 * unit32_fast(c3) - 3.0);
+        }
+    };
+    if (MATH_DRAWS) mdraw(0, 0);
     __syncthreads();
     int cy = 0, py_ = 2;                                   // output buffers: current block, previous block
     for (int t = 0; t < nblk; ++t) {
         const int cu = t & 1, pu_ = cu ^ 1;
+        if (MATH_DRAWS && t + 1 < nblk) mdraw(t + 1, cy == 2 ? 0 : cy + 1);   // that buffer was recorded during block t - 1
         if (t == nblk - 1 && n_tail != 0) {                // last, partial block (controller_operation.py:278)
 #pragma unroll
             for (int rt = 0; rt < 2; ++rt)
@@ -1040,35 +1067,35 @@ k_closed_loop_ws(const __grid_constant__ MmaCoef<N, M, P, NX, NMPC> cfp, const F
                     aP[rt][ks] = (8 * rt + g < RB) ? cfp.Mt[(8 * rt + g) % RB][4 * ks + q] : 0.0;
         }
         // ---- solve: U (8 x loops) = csp + Ku [window_u; window_y]
-        double2 c[LM][NT];
+        double2 c[LM][NTW];
 #pragma unroll
         for (int li = 0; li < LM; ++li)
 #pragma unroll
-            for (int t8 = 0; t8 < NT; ++t8) c[li][t8] = *reinterpret_cast<const double2 *>(&csp_s[g][l0 + li][8 * t8 + cc2]);
+            for (int t8 = 0; t8 < NTW; ++t8) c[li][t8] = *reinterpret_cast<const double2 *>(&csp_s[g][l0 + li][8 * (t80 + t8) + cc2]);
 #pragma unroll
         for (int ks = 0; ks < NW / 4; ++ks) {
             const int e = 4 * ks + q;
 #pragma unroll
             for (int li = 0; li < LM; ++li)
 #pragma unroll
-                for (int t8 = 0; t8 < NT; ++t8) {
-                    const double bv = (4 * ks < N * M) ? up_s[pu_][e < N * M ? e : 0][l0 + li][8 * t8 + cb]
-                                                       : wy_s[py_][e >= N * M ? e - N * M : 0][l0 + li][8 * t8 + cb];
+                for (int t8 = 0; t8 < NTW; ++t8) {
+                    const double bv = (4 * ks < N * M) ? up_s[pu_][e < N * M ? e : 0][l0 + li][8 * (t80 + t8) + cb]
+                                                       : wy_s[py_][e >= N * M ? e - N * M : 0][l0 + li][8 * (t80 + t8) + cb];
                     mma(c[li][t8], aK[ks], bv);
                 }
         }
 #pragma unroll
         for (int li = 0; li < LM; ++li)
 #pragma unroll
-            for (int t8 = 0; t8 < NT; ++t8) *reinterpret_cast<double2 *>(&up_s[cu][g][l0 + li][8 * t8 + cc2]) = c[li][t8];
+            for (int t8 = 0; t8 < NTW; ++t8) *reinterpret_cast<double2 *>(&up_s[cu][g][l0 + li][8 * (t80 + t8) + cc2]) = c[li][t8];
         __syncwarp();
         // ---- plant: [Y; x+] = Mblk [x; U] (+ the noise waiting in the output buffer)
-        double2 d[2][LM][NT];
+        double2 d[2][LM][NTW];
 #pragma unroll
         for (int li = 0; li < LM; ++li)
 #pragma unroll
-            for (int t8 = 0; t8 < NT; ++t8) {
-                d[0][li][t8] = *reinterpret_cast<const double2 *>(&wy_s[cy][g][l0 + li][8 * t8 + cc2]);
+            for (int t8 = 0; t8 < NTW; ++t8) {
+                d[0][li][t8] = *reinterpret_cast<const double2 *>(&wy_s[cy][g][l0 + li][8 * (t80 + t8) + cc2]);
                 d[1][li][t8] = make_double2(0.0, 0.0);
             }
 #pragma unroll
@@ -1077,9 +1104,9 @@ k_closed_loop_ws(const __grid_constant__ MmaCoef<N, M, P, NX, NMPC> cfp, const F
 #pragma unroll
             for (int li = 0; li < LM; ++li)
 #pragma unroll
-                for (int t8 = 0; t8 < NT; ++t8) {
-                    const double bv = (4 * ks < NX) ? x_s[e < NX ? e : 0][l0 + li][8 * t8 + cb]
-                                                    : up_s[cu][e >= NX ? e - NX : 0][l0 + li][8 * t8 + cb];
+                for (int t8 = 0; t8 < NTW; ++t8) {
+                    const double bv = (4 * ks < NX) ? x_s[e < NX ? e : 0][l0 + li][8 * (t80 + t8) + cb]
+                                                    : up_s[cu][e >= NX ? e - NX : 0][l0 + li][8 * (t80 + t8) + cb];
 #pragma unroll
                     for (int rt = 0; rt < 2; ++rt) mma(d[rt][li][t8], aP[rt][ks], bv);
                 }
@@ -1088,9 +1115,9 @@ k_closed_loop_ws(const __grid_constant__ MmaCoef<N, M, P, NX, NMPC> cfp, const F
 #pragma unroll
         for (int li = 0; li < LM; ++li)
 #pragma unroll
-            for (int t8 = 0; t8 < NT; ++t8) {
-                *reinterpret_cast<double2 *>(&wy_s[cy][g][l0 + li][8 * t8 + cc2]) = d[0][li][t8];
-                if (g < NX) *reinterpret_cast<double2 *>(&x_s[g][l0 + li][8 * t8 + cc2]) = d[1][li][t8];
+            for (int t8 = 0; t8 < NTW; ++t8) {
+                *reinterpret_cast<double2 *>(&wy_s[cy][g][l0 + li][8 * (t80 + t8) + cc2]) = d[0][li][t8];
+                if (g < NX) *reinterpret_cast<double2 *>(&x_s[g][l0 + li][8 * (t80 + t8) + cc2]) = d[1][li][t8];
             }
         py_ = cy;
         cy = cy == 2 ? 0 : cy + 1;
@@ -1753,7 +1780,7 @@ static int launch_fast(const ddmpc_set *set, const ddmpc_plant *plant, const Fas
                 // on 148 SMs: ask for the largest shared-memory carveout instead of trusting the default
                 if (const char *ens = getenv("DDMPC_DEBUG_NOSTORE")) a.dbg_nostore = ens[0] == '1';
                 const char *emw = getenv("DDMPC_WS_MATH_WARPS");
-                const int mw = (emw && emw[0] == '1') ? 1 : 2;
+                const int mw = (emw && emw[0] == '1') ? 1 : ((emw && emw[0] == '4') ? 4 : 2);
                 static std::atomic<unsigned long long> carveout_done{0};
                 if (first_time_on_device(carveout_done)) {
                     DDMPC_CUDA(cudaFuncSetAttribute(k_closed_loop_ws<N, M, P, NX, NMPC, false, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -1761,8 +1788,23 @@ static int launch_fast(const ddmpc_set *set, const ddmpc_plant *plant, const Fas
                     DDMPC_CUDA(cudaFuncSetAttribute(k_closed_loop_ws<N, M, P, NX, NMPC, false, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
                     DDMPC_CUDA(cudaFuncSetAttribute(k_closed_loop_ws<N, M, P, NX, NMPC, true, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
                 }
-                if (mw == 2) {
+                if (mw == 4) {
+                    static std::atomic<unsigned long long> carveout4_done{0};
+                    if (first_time_on_device(carveout4_done)) {
+                        DDMPC_CUDA(cudaFuncSetAttribute(k_closed_loop_ws<N, M, P, NX, NMPC, false, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+                        DDMPC_CUDA(cudaFuncSetAttribute(k_closed_loop_ws<N, M, P, NX, NMPC, true, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+                    }
+                    if (a.w) k_closed_loop_ws<N, M, P, NX, NMPC, false, 4><<<gridw, 160, 0, st>>>(mc, a, n_tail);
+                    else k_closed_loop_ws<N, M, P, NX, NMPC, true, 4><<<gridw, 160, 0, st>>>(mc, a, n_tail);
+                } else if (mw == 2) {
+                    const char *emd = getenv("DDMPC_WS_MATH_DRAWS");
                     if (a.w) k_closed_loop_ws<N, M, P, NX, NMPC, false, 2><<<gridw, 96, 0, st>>>(mc, a, n_tail);
+                    else if (emd && emd[0] == '1') {
+                        static std::atomic<unsigned long long> carveout_md{0};
+                        if (first_time_on_device(carveout_md))
+                            DDMPC_CUDA(cudaFuncSetAttribute(k_closed_loop_ws<N, M, P, NX, NMPC, true, 2, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+                        k_closed_loop_ws<N, M, P, NX, NMPC, true, 2, true><<<gridw, 96, 0, st>>>(mc, a, n_tail);
+                    }
                     else k_closed_loop_ws<N, M, P, NX, NMPC, true, 2><<<gridw, 96, 0, st>>>(mc, a, n_tail);
                 } else {
                     if (a.w) k_closed_loop_ws<N, M, P, NX, NMPC, false, 1><<<gridw, 64, 0, st>>>(mc, a, n_tail);

@@ -19,6 +19,10 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 VARIANTS = [
     ("ws (default)", {}),
     ("ws, no stores", {"DDMPC_DEBUG_NOSTORE": "1"}),
+    ("ws, 4 math warps", {"DDMPC_WS_MATH_WARPS": "4"}),
+    ("ws, 4 math warps, no stores", {"DDMPC_WS_MATH_WARPS": "4", "DDMPC_DEBUG_NOSTORE": "1"}),
+    ("ws, math warps draw", {"DDMPC_WS_MATH_DRAWS": "1"}),
+    ("ws, math warps draw, no stores", {"DDMPC_WS_MATH_DRAWS": "1", "DDMPC_DEBUG_NOSTORE": "1"}),
     ("rws (DDMPC_REG=2)", {"DDMPC_REG": "2"}),
     ("rws, no stores", {"DDMPC_REG": "2", "DDMPC_DEBUG_NOSTORE": "1"}),
     ("regx (DDMPC_REG=3)", {"DDMPC_REG": "3"}),
@@ -26,7 +30,7 @@ VARIANTS = [
     ("reg NT=4 (DDMPC_REG=1)", {"DDMPC_REG": "1"}),
     ("hybrid (DDMPC_WS=0)", {"DDMPC_WS": "0"}),
 ]
-SWITCHES = ("DDMPC_WS", "DDMPC_REG", "DDMPC_REG_NT", "DDMPC_DEBUG_NOSTORE", "DDMPC_PLANT_MMA")
+SWITCHES = ("DDMPC_WS", "DDMPC_WS_MATH_WARPS", "DDMPC_WS_MATH_DRAWS", "DDMPC_REG", "DDMPC_REG_NT", "DDMPC_DEBUG_NOSTORE", "DDMPC_PLANT_MMA")
 
 
 def main() -> None:

@@ -410,12 +410,12 @@ def test_tensor_core_variants_match_hybrid(monkeypatch):
         monkeypatch.setenv("DDMPC_WS", "0")
         monkeypatch.delenv("DDMPC_PLANT_MMA", raising=False)
         u1, y1, s1, i1, x1 = cs.closed_loop(_plant(), xs, up0, yp0, us, ys, n_steps, want_x_final=True, **kw)
-        for env in (dict(DDMPC_WS="1"), dict(DDMPC_REG="2"), dict(DDMPC_REG="3"), dict(DDMPC_REG="1"), dict(DDMPC_REG="1", DDMPC_REG_NT="2"), dict(DDMPC_REG="1", DDMPC_REG_NT="8"),
+        for env in (dict(DDMPC_WS="1"), dict(DDMPC_WS_MATH_WARPS="1"), dict(DDMPC_REG="2"), dict(DDMPC_REG="3"), dict(DDMPC_REG="1"), dict(DDMPC_REG="1", DDMPC_REG_NT="2"), dict(DDMPC_REG="1", DDMPC_REG_NT="8"),
                     dict(DDMPC_WS="0", DDMPC_PLANT_MMA="1")):     # warp-specialised (default), register-chained NT = 4 / 2 / 8, single-warp MMA
             for k, v in env.items():
                 monkeypatch.setenv(k, v)
             u2, y2, s2, i2, x2 = cs.closed_loop(_plant(), xs, up0, yp0, us, ys, n_steps, want_x_final=True, **kw)
-            for k in ("DDMPC_PLANT_MMA", "DDMPC_WS", "DDMPC_REG", "DDMPC_REG_NT"):
+            for k in ("DDMPC_PLANT_MMA", "DDMPC_WS", "DDMPC_WS_MATH_WARPS", "DDMPC_WS_MATH_DRAWS", "DDMPC_REG", "DDMPC_REG_NT"):
                 monkeypatch.delenv(k, raising=False)
             assert int(s2.max()) == 0 and (i1 == i2).all(), env
             assert _rel(u2.cpu().numpy(), u1.cpu().numpy()) < 1e-9 and _rel(y2.cpu().numpy(), y1.cpu().numpy()) < 1e-9, env
