@@ -852,7 +852,7 @@ k_closed_loop_mma(const __grid_constant__ MmaCoef<N, M, P, NX, NMPC> cfp, const 
 // same buffer in the same iteration except to read.  Same arithmetic as k_closed_loop_mma except that the noise
 // is the first instead of the last summand of y.
 // ===========================================================================
-template <int N, int M, int P, int NX, int NMPC, bool PHILOX, int MW, bool MD = (MW == 4)>
+template <int N, int M, int P, int NX, int NMPC, bool PHILOX, int MW, bool MD = false>
 __global__ void __launch_bounds__(32 * (MW + 1), 7)
 k_closed_loop_ws(const __grid_constant__ MmaCoef<N, M, P, NX, NMPC> cfp, const FastArgs a, const int n_tail) {
     constexpr int R = NMPC * M, NW = N * (M + P), LPT = 2, TP = 36, NT = 4;
@@ -861,8 +861,8 @@ k_closed_loop_ws(const __grid_constant__ MmaCoef<N, M, P, NX, NMPC> cfp, const F
     constexpr int WPG = MW == 4 ? 2 : 1;                       // math warps per loop group (they split its n-tiles)
     constexpr int NTW = NT / WPG;                              // n-tiles (of 8 loops) per math warp and loop group
     static_assert(MW == 1 || MW == 2 || MW == 4, "one, two or four math warps");
-    // MD: every math warp draws the Philox noise of its own loops (32 / WPG calls per block) and the i/o warp only
-    // records: a single warp doing both is as long a dependency chain as the math of a block.
+    // MD (opt-in, DDMPC_WS_MATH_DRAWS=1): every math warp draws the Philox noise of its own loops and the i/o warp only
+    // records.  Measured slower (0.263 vs 0.240 ms): the math warps, not the i/o warp, are the critical path.
     constexpr bool MATH_DRAWS = MD && PHILOX;
     static_assert(!MD || MW >= 2, "math warps draw their own noise only with one loop group per warp");
     static_assert(M == 2 && P == 2 && R == 8 && NMPC == N, "shape not supported by the warp-specialised kernel");

@@ -410,7 +410,7 @@ def test_tensor_core_variants_match_hybrid(monkeypatch):
         monkeypatch.setenv("DDMPC_WS", "0")
         monkeypatch.delenv("DDMPC_PLANT_MMA", raising=False)
         u1, y1, s1, i1, x1 = cs.closed_loop(_plant(), xs, up0, yp0, us, ys, n_steps, want_x_final=True, **kw)
-        for env in (dict(DDMPC_WS="1"), dict(DDMPC_WS_MATH_WARPS="1"), dict(DDMPC_REG="2"), dict(DDMPC_REG="3"), dict(DDMPC_REG="1"), dict(DDMPC_REG="1", DDMPC_REG_NT="2"), dict(DDMPC_REG="1", DDMPC_REG_NT="8"),
+        for env in (dict(DDMPC_WS="1"), dict(DDMPC_WS_MATH_WARPS="4"), dict(DDMPC_WS_MATH_WARPS="1"), dict(DDMPC_WS_MATH_DRAWS="1"), dict(DDMPC_REG="2"), dict(DDMPC_REG="3"), dict(DDMPC_REG="1"), dict(DDMPC_REG="1", DDMPC_REG_NT="2"), dict(DDMPC_REG="1", DDMPC_REG_NT="8"),
                     dict(DDMPC_WS="0", DDMPC_PLANT_MMA="1")):     # warp-specialised (default), register-chained NT = 4 / 2 / 8, single-warp MMA
             for k, v in env.items():
                 monkeypatch.setenv(k, v)
