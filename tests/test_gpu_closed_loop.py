@@ -664,3 +664,25 @@ def test_nonfinite_inputs_flag_only_their_own_loops(monkeypatch):
             for k in env:
                 monkeypatch.delenv(k, raising=False)
             assert np.array_equal(st.cpu().numpy(), expect), (n_mpc, env, np.nonzero(st.cpu().numpy() != expect)[0][:8])
+
+
+@pytest.mark.parametrize("n_mpc", [1, 20])
+def test_dmma_kernel_cta_sizes_agree_bitwise(n_mpc, monkeypatch):
+    """k_closed_loop_dmma with CTAs of 1 (default), 2 and 4 warps (DDMPC_DMMA_WARPS): the warps are independent, so the
+    results must be identical bit for bit, ragged batch included."""
+    from direct_data_driven_mpc_b200 import ControllerSet, scenarios as S
+    B, n_steps = 8 * 67 + 3, 45
+    sc = S.config4_batch(B, n_mpc_step=n_mpc)
+    prm, pl = sc["params"], sc["plant"]
+    cs = ControllerSet(prm["n"], 4, 4, sc["u_d"], sc["y_d"], prm["L"], prm["Q"], prm["R"], prm["eps_max"],
+                       prm["lamb_alpha"], prm["lamb_sigma"], prm["c"], 0, 1, n_mpc, True)
+    outs = []
+    for w in ("1", "2", "4"):
+        monkeypatch.setenv("DDMPC_DMMA_WARPS", w)
+        u, y, st, it, xf = cs.closed_loop(pl, sc["x0"], sc["u_past0"], sc["y_past0"], sc["u_s"], sc["y_s"], n_steps,
+                                          want_x_final=True, noise_seed=9, scenario_id0=77, noise_eps=0.002)
+        assert int(st.max()) == 0
+        outs.append((u.cpu().numpy(), y.cpu().numpy(), xf.cpu().numpy()))
+    monkeypatch.delenv("DDMPC_DMMA_WARPS", raising=False)
+    for o in outs[1:]:
+        assert all(np.array_equal(a, b) for a, b in zip(o, outs[0]))
