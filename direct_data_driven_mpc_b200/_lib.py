@@ -18,6 +18,8 @@ ERR_N_TOO_SMALL, ERR_NOT_PE, ERR_HORIZON, ERR_NOT_IMPLEMENTED, ERR_FACTORIZATION
 NOMINAL, ROBUST = 0, 1
 SLACK_NONE, SLACK_CONVEX, SLACK_NON_CONVEX = 0, 1, 2
 SOLVE_OPTIMAL, SOLVE_OPTIMAL_INACCURATE, SOLVE_INFEASIBLE, SOLVE_NONFINITE = range(4)
+# kernel selection of ddmpc_closed_loop_batch (ddmpc_set_option "closed_loop_path")
+PATHS = {"auto": 0, "generic": 1, "fast": 2, "ws": 3, "perloop": 4, "dmma": 5, "gemm": 6}
 STATUS_STRINGS = {SOLVE_OPTIMAL: "optimal", SOLVE_OPTIMAL_INACCURATE: "optimal_inaccurate",
                   SOLVE_INFEASIBLE: "infeasible", SOLVE_NONFINITE: "solver_error"}
 
@@ -56,6 +58,8 @@ def _load() -> C.CDLL:
         "ddmpc_last_error": (C.c_char_p, []),
         "ddmpc_kernel_launches": (u64, []),
         "ddmpc_trim_memory": (i32, []),
+        "ddmpc_probe_fp64_tflops": (i32, [i32, C.POINTER(f64), vp]),
+        "ddmpc_probe_store_ms": (i32, [i32, i32, i32, vp, vp, C.POINTER(f64), vp]),
         "ddmpc_hankel": (i32, [vp, i32, i32, i32, vp, vp]),
         "ddmpc_hankel_host": (i32, [vp, i32, i32, i32, vp]),
         "ddmpc_pe_rank_host": (i32, [vp, i32, i32, i32, C.POINTER(C.c_int)]),
@@ -63,6 +67,8 @@ def _load() -> C.CDLL:
         "ddmpc_set_create_host": (i32, [PP, i32, vp, sz, vp, sz, vp, vp, vp, vp, C.POINTER(vp)]),
         "ddmpc_set_destroy": (None, [vp]),
         "ddmpc_set_count": (i32, [vp]),
+        "ddmpc_set_failed_count": (i32, [vp]),
+        "ddmpc_set_option": (i32, [vp, C.c_char_p, i32]),
         "ddmpc_set_info": (i32, [vp, i32, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
         "ddmpc_set_get": (i32, [vp, C.c_char_p, i32, vp, sz, C.POINTER(sz)]),
         "ddmpc_solve_batch": (i32, [vp, i32, vp, vp, vp, vp, vp, f64, i32, vp, vp, vp, vp, vp]),
@@ -84,9 +90,10 @@ def _load() -> C.CDLL:
 lib = _load()
 EXPORTED = ["ddmpc_version", "ddmpc_strerror", "ddmpc_last_error", "ddmpc_kernel_launches", "ddmpc_hankel",
             "ddmpc_hankel_host", "ddmpc_pe_rank_host", "ddmpc_set_create", "ddmpc_set_create_host",
-            "ddmpc_set_destroy", "ddmpc_set_count", "ddmpc_set_info", "ddmpc_set_get", "ddmpc_solve_batch",
+            "ddmpc_set_destroy", "ddmpc_set_count", "ddmpc_set_failed_count", "ddmpc_set_option", "ddmpc_set_info", "ddmpc_set_get", "ddmpc_solve_batch",
             "ddmpc_solve_batch_host", "ddmpc_solve_full_batch", "ddmpc_closed_loop_batch",
-            "ddmpc_closed_loop_batch_host", "ddmpc_generate_example_data", "ddmpc_pcg64_uniform", "ddmpc_trim_memory"]
+            "ddmpc_closed_loop_batch_host", "ddmpc_generate_example_data", "ddmpc_pcg64_uniform", "ddmpc_trim_memory", "ddmpc_probe_fp64_tflops",
+            "ddmpc_probe_store_ms"]
 
 
 def last_error() -> str:
@@ -108,6 +115,20 @@ def check(code: int) -> None:
 
 def kernel_launches() -> int:
     return int(lib.ddmpc_kernel_launches())
+
+
+def probe_fp64_tflops(use_dmma: bool, stream: int = 0) -> float:
+    """Sustained FP64 TFLOP/s of the current device issued as DFMA or as DMMA m8n8k4 (csrc/probes.cu)."""
+    out = C.c_double()
+    check(lib.ddmpc_probe_fp64_tflops(1 if use_dmma else 0, C.byref(out), stream))
+    return out.value
+
+
+def probe_store_ms(B: int, n_steps: int, coalesced: bool, u_ptr: int, y_ptr: int, stream: int = 0) -> float:
+    """Time (ms) to write the (B, n_steps, 2) x 2 trajectory arrays with no compute (csrc/probes.cu)."""
+    out = C.c_double()
+    check(lib.ddmpc_probe_store_ms(B, n_steps, 1 if coalesced else 0, u_ptr, y_ptr, C.byref(out), stream))
+    return out.value
 
 
 def trim_memory() -> None:

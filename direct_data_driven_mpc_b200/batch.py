@@ -84,14 +84,24 @@ class ControllerSet:
         self.n_mpc_step = n_mpc_step
         ud = _dev_f64(u_d, self.device)
         yd = _dev_f64(y_d, self.device)
-        shared = ud.dim() == 2
+        if ud.dim() not in (2, 3) or yd.dim() not in (2, 3):
+            raise ValueError("u_d must be (N, m) or (count, N, m) and y_d (N, p) or (count, N, p)")
+        # each data array is either shared by the set (2-D, stride 0) or per controller (3-D); the two are independent
+        u_shared, y_shared = ud.dim() == 2, yd.dim() == 2
+        lead = {t.shape[0] for t, sh in ((ud, u_shared), (yd, y_shared)) if not sh}
+        if len(lead) > 1:
+            raise ValueError(f"u_d and y_d hold different numbers of data sets: {sorted(lead)}")
         if count is None:
-            count = 1 if shared else ud.shape[0]
+            count = lead.pop() if lead else 1
+        elif lead and lead.pop() != count:
+            raise ValueError(f"per-controller data must have `count` = {count} leading entries")
         self.count = count
         self.N = ud.shape[-2]
         if ud.shape[-1] != m:
             raise ValueError(f"The length of the elements of the data sequence ({ud.shape[-1]}) should match the "
                              f"number of inputs of the system ({m}).")
+        if tuple(yd.shape[-2:]) != (self.N, p):
+            raise ValueError(f"y_d must hold N = {self.N} rows of p = {p} outputs, got {tuple(yd.shape[-2:])}")
         Qd = _dev_f64(Q, self.device)
         Rd = _dev_f64(R, self.device)
         if tuple(Qd.shape) != (p * L, p * L):
@@ -140,11 +150,44 @@ class ControllerSet:
         with torch.cuda.device(self.device):
             stream = torch.cuda.current_stream().cuda_stream
             _lib.check(_lib.lib.ddmpc_set_create(
-                C.byref(prm), count, ud.data_ptr(), 0 if shared else self.N * m, yd.data_ptr(),
-                0 if shared else self.N * p, Qd.data_ptr(), Rd.data_ptr(),
+                C.byref(prm), count, ud.data_ptr(), 0 if u_shared else self.N * m, yd.data_ptr(),
+                0 if y_shared else self.N * p, Qd.data_ptr(), Rd.data_ptr(),
                 None if la_arr is None else la_arr.ctypes.data, None if ls_arr is None else ls_arr.ctypes.data,
                 stream, C.byref(handle)))
         self._h = handle
+        # Controllers that could not be set up (not persistently exciting / factorisation failed).  A single controller
+        # raises at construction like the reference (controller.py:285-296); in a larger set the failed ones return NaN
+        # and status 3 from every solve, and are listed here.
+        self.n_failed = int(_lib.lib.ddmpc_set_failed_count(self._h))
+        if self.n_failed:
+            import warnings
+            self.failed_mask = self.statuses() != 0
+            warnings.warn(f"{self.n_failed} of {count} controllers could not be set up (ControllerSet.failed_mask, "
+                          "ControllerSet.info(i)); solves that use them return NaN and status 3", RuntimeWarning)
+        else:
+            self.failed_mask = np.zeros(count, dtype=bool)
+
+    def set_option(self, name: str, value) -> None:
+        """Per-set options of the C ABI (ddmpc_set_option): "closed_loop_path" ("auto", "generic", "fast", "ws",
+        "perloop", "dmma", "gemm" - forces one closed-loop kernel where it applies), "dmma_warps", "loops_per_thread"."""
+        if name == "closed_loop_path" and isinstance(value, str):
+            value = _lib.PATHS[value]
+        _lib.check(_lib.lib.ddmpc_set_option(self._h, name.encode(), int(value)))
+
+    def _ctrl_idx(self, ctrl_idx, B: int, dev, check: bool = True):
+        """ctrl_idx as an int32 device tensor of B entries within [0, count) (checked: the kernels index with it)."""
+        if ctrl_idx is None:
+            return None
+        on_dev = isinstance(ctrl_idx, torch.Tensor) and ctrl_idx.is_cuda
+        ci = torch.as_tensor(ctrl_idx, device=dev).to(torch.int32).contiguous().reshape(-1)
+        if ci.numel() != B:
+            raise ValueError(f"ctrl_idx must have one entry per solve ({B}), got {ci.numel()}")
+        if check and B and not (on_dev and torch.cuda.is_current_stream_capturing()):
+            src = ci if on_dev else torch.as_tensor(ctrl_idx).reshape(-1)
+            lo, hi = int(src.min()), int(src.max())
+            if lo < 0 or hi >= self.count:
+                raise ValueError(f"ctrl_idx entries must lie in [0, {self.count}), got [{lo}, {hi}]")
+        return ci
 
     # ---- introspection ---------------------------------------------------------
     def info(self, index: int = 0) -> Tuple[int, int]:
@@ -173,7 +216,7 @@ class ControllerSet:
         yp = _dev_f64(y_past, dev, (B, self.n * self.p))
         us = _dev_f64(u_s, dev, (B, self.m))
         ys = _dev_f64(y_s, dev, (B, self.p))
-        ci = None if ctrl_idx is None else torch.as_tensor(ctrl_idx, device=dev).to(torch.int32).contiguous()
+        ci = self._ctrl_idx(ctrl_idx, B, dev)
         out = torch.empty(B, self.L * self.m, dtype=torch.float64, device=dev)
         cost = torch.empty(B, dtype=torch.float64, device=dev) if want_cost else None
         status = torch.empty(B, dtype=torch.int32, device=dev)
@@ -195,7 +238,7 @@ class ControllerSet:
         yp = _dev_f64(y_past, dev, (B, self.n * self.p))
         us = _dev_f64(u_s, dev, (B, self.m))
         ys = _dev_f64(y_s, dev, (B, self.p))
-        ci = None if ctrl_idx is None else torch.as_tensor(ctrl_idx, device=dev).to(torch.int32).contiguous()
+        ci = self._ctrl_idx(ctrl_idx, B, dev)
         Lp = self.L + self.n
         robust = self.robust
         ub = torch.empty(B, Lp * self.m, dtype=torch.float64, device=dev)
@@ -228,7 +271,7 @@ class ControllerSet:
         us = _dev_f64(u_s, dev, (B, self.m))
         ys = _dev_f64(y_s, dev, (B, self.p))
         wt = None if w is None else _dev_f64(w, dev, (B, n_steps, self.p))
-        ci = None if ctrl_idx is None else torch.as_tensor(ctrl_idx, device=dev).to(torch.int32).contiguous()
+        ci = self._ctrl_idx(ctrl_idx, B, dev, check_idx)
         if out is None:
             u_sys = torch.empty(B, n_steps, self.m, dtype=torch.float64, device=dev)
             y_sys = torch.empty(B, n_steps, self.p, dtype=torch.float64, device=dev)
@@ -270,6 +313,8 @@ class ControllerSet:
         B = x0h.shape[0]
         wh = None if w is None else (w if isinstance(w, torch.Tensor) else torch.from_numpy(_f64(w))).reshape(B, n_steps, self.p)
         cih = None if ctrl_idx is None else torch.as_tensor(ctrl_idx).to(torch.int32).reshape(B)
+        if cih is not None and B and (int(cih.min()) < 0 or int(cih.max()) >= self.count):
+            raise ValueError(f"ctrl_idx entries must lie in [0, {self.count})")
         if out is None:
             u_out = torch.empty(B, n_steps, self.m, dtype=torch.float64, pin_memory=True)
             y_out = torch.empty(B, n_steps, self.p, dtype=torch.float64, pin_memory=True)
@@ -304,7 +349,8 @@ class ControllerSet:
                     _, _, st_, _ = self.closed_loop(
                         plant, x0d[lo:hi], upd[lo:hi], ypd[lo:hi], usd[lo:hi], ysd[lo:hi], n_steps,
                         w=None if wd is None else wd[lo:hi], noise_seed=noise_seed, scenario_id0=scenario_id0 + lo,
-                        noise_eps=noise_eps, ctrl_idx=None if cid is None else cid[lo:hi], tol=tol, max_iter=max_iter,
+                        noise_eps=noise_eps, ctrl_idx=None if cid is None else cid[lo:hi], check_idx=False, tol=tol,
+                        max_iter=max_iter,
                         out=(st["u"][lo:hi], st["y"][lo:hi]))
                     st["status"][lo:hi].copy_(st_)
                     u_out[lo:hi].copy_(st["u"][lo:hi], non_blocking=True)

@@ -59,12 +59,12 @@ inline bool first_time_on_device(std::atomic<unsigned long long> &mask) {
 }
 
 // RAII device buffer (setup scratch + plan storage).  Memory comes from the device's stream-ordered pool
-// (cudaMallocAsync on the legacy default stream) that keeps what it has been given (release threshold = max;
+// (cudaMallocAsync, ordered on the stream of the calling entry point) that keeps what it has been given (release threshold = max;
 // ddmpc_trim_memory() hands it back): a batched controller setup
 // allocates and frees a dozen buffers of up to hundreds of MB, and with cudaMalloc/cudaFree (each a device-wide
 // synchronisation plus page-table work) that cost 80-250 ms of wall time per call against 13 ms of kernels.
-// Every scratch lifetime in this library ends with a stream synchronise before the buffers go out of scope, and
-// ddmpc_set_destroy synchronises the device, so returning memory to the pool never races with work using it.
+// Scratch is freed in the order of the stream its kernels ran on (ScratchStreamScope below), and ddmpc_set_destroy
+// synchronises the device, so returning memory to the pool never races with work using it.
 inline cudaError_t pool_ready() {
     static std::atomic<unsigned long long> done{0};
     if (!first_time_on_device(done)) return cudaSuccess;
@@ -78,24 +78,39 @@ inline cudaError_t pool_ready() {
     return cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
 }
 
+// Stream that DevBuf allocations made by the calling thread are ordered on.  Entry points that enqueue work on a
+// caller stream open a ScratchStreamScope for it, so scratch is allocated AND freed in that stream's order: an early
+// error return then cannot hand memory that kernels on the stream are still using back to the pool.
+extern thread_local cudaStream_t g_scratch_stream;
+struct ScratchStreamScope {
+    cudaStream_t prev;
+    explicit ScratchStreamScope(cudaStream_t s) : prev(g_scratch_stream) { g_scratch_stream = s; }
+    ~ScratchStreamScope() { g_scratch_stream = prev; }
+};
+
 struct DevBuf {
     void *p = nullptr;
     size_t bytes = 0;
+    cudaStream_t stream = nullptr;   // the stream the allocation is ordered on
     DevBuf() = default;
     DevBuf(const DevBuf &) = delete;
     DevBuf &operator=(const DevBuf &) = delete;
     ~DevBuf() { release(); }
     void release() {
-        if (p) cudaFreeAsync(p, (cudaStream_t)0);
+        if (p) cudaFreeAsync(p, stream);
         p = nullptr;
         bytes = 0;
     }
+    // long-lived buffers (plan storage) outlive the stream they were created on: ddmpc_set_destroy synchronises the
+    // device and frees them on the legacy stream
+    void detach_stream() { stream = nullptr; }
     cudaError_t alloc(size_t n) {
         release();
         if (n == 0) n = 8;
         cudaError_t e = pool_ready();
         if (e != cudaSuccess) return e;
-        e = cudaMallocAsync(&p, n, (cudaStream_t)0);
+        stream = g_scratch_stream;
+        e = cudaMallocAsync(&p, n, stream);
         if (e == cudaSuccess) bytes = n;
         else p = nullptr;
         return e;

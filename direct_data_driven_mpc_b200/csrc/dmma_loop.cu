@@ -421,14 +421,9 @@ static int launch_dmma_w(const DmmaArgs &a, size_t smem_per_warp, cudaStream_t s
 // Warps per CTA.  One-warp CTAs deal the batch to the SMs at the finest grain (16,384 loops = 2048 warps on 148 SMs: 14 or
 // 13 per SM instead of 16 or 12 with CTAs of four) and measured 6 % faster than CTAs of 2 or 4 on config 4
 // (1.455 vs 1.541 / 1.553 ms per 401-step pass, 0.903 vs 0.953 / 0.951 ms with n_mpc_step = 20);
-// DDMPC_DMMA_WARPS=2|4 selects the larger ones.
+// ddmpc_set_option("dmma_warps", 2 | 4) selects the larger ones.
 template <int MTS, int MTP, int KSS, int KSP, int KU = 0, int KY = 0>
-static int launch_dmma(const DmmaArgs &a, size_t smem_per_warp, cudaStream_t st) {
-    int best = 1;
-    if (const char *e = getenv("DDMPC_DMMA_WARPS")) {
-        const int v = atoi(e);
-        if (v == 1 || v == 2 || v == 4) best = v;
-    }
+static int launch_dmma(const DmmaArgs &a, size_t smem_per_warp, int best, cudaStream_t st) {
     if (best == 4) return launch_dmma_w<MTS, MTP, KSS, KSP, 4, KU, KY>(a, smem_per_warp, st);
     if (best == 2) return launch_dmma_w<MTS, MTP, KSS, KSP, 2, KU, KY>(a, smem_per_warp, st);
     return launch_dmma_w<MTS, MTP, KSS, KSP, 1, KU, KY>(a, smem_per_warp, st);
@@ -441,10 +436,7 @@ int closed_loop_dmma_try(const ddmpc_set *set, const ddmpc_plant *plant, int B, 
                          double *y_sys, int *status, int *iters, double *x_final, cudaStream_t st) {
     const Dims &d = set->plan.d;
     if (ctrl_idx || set->plan.count != 1 || d.nb > 0 || !d.robust) return -1;
-    const char *force = getenv("DDMPC_FORCE_GENERIC");
-    if (force && force[0] == '1') return -1;
-    const char *off = getenv("DDMPC_NO_FUSED_DMMA");
-    if (off && off[0] == '1') return -1;
+    if (set->opt_path != DDMPC_PATH_AUTO && set->opt_path != DDMPC_PATH_DMMA) return -1;
     const int n = d.n, m = d.m, p = d.p, nx = plant->n_x, nth = d.nth, nmpc = set->prm.n_mpc_step;
     if ((m % 4) || (p % 4) || (nx % 4) || nmpc > n || nth < 64 || B < 256) return -1;
     const int R = nmpc * m, rowsP = nmpc * p + nx, colsP = nx + R;
@@ -511,8 +503,8 @@ int closed_loop_dmma_try(const ddmpc_set *set, const ddmpc_plant *plant, int B, 
     a.x0 = x0; a.u_past0 = u_past0; a.y_past0 = y_past0; a.u_s = u_s; a.y_s = y_s; a.w = w;
     a.seed = seed; a.id0 = id0; a.eps = eps;
     a.u_sys = u_sys; a.y_sys = y_sys; a.x_final = x_final; a.status = status; a.iters = iters;
-    if (shape1) return launch_dmma<1, 3, 42, 6, 20, 20>(a, smem, st);
-    return launch_dmma<10, 13, 0, 0>(a, smem, st);
+    if (shape1) return launch_dmma<1, 3, 42, 6, 20, 20>(a, smem, set->opt_dmma_warps, st);
+    return launch_dmma<10, 13, 0, 0>(a, smem, set->opt_dmma_warps, st);
 }
 
 }  // namespace ddmpc

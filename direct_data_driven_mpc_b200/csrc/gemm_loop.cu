@@ -193,8 +193,7 @@ int closed_loop_gemm_try(const ddmpc_set *set, const ddmpc_plant *plant, int B, 
                          double *y_sys, int *status, int *iters, double *x_final, cudaStream_t st) {
     const Dims &d = set->plan.d;
     if (ctrl_idx || set->plan.count != 1 || d.nb > 0 || !d.robust) return -1;
-    const char *force = getenv("DDMPC_FORCE_GENERIC");
-    if (force && force[0] == '1') return -1;
+    if (set->opt_path != DDMPC_PATH_AUTO && set->opt_path != DDMPC_PATH_GEMM) return -1;
     const int n = d.n, m = d.m, p = d.p, nxp = plant->n_x, nth = d.nth;
     const int nmpc = set->prm.n_mpc_step;
     // worth it only when the per-loop state is too large for the thread-per-loop kernels and the
@@ -203,23 +202,32 @@ int closed_loop_gemm_try(const ddmpc_set *set, const ddmpc_plant *plant, int B, 
     const int rem = n_steps % nmpc;
     const int rows_full = nmpc * p + nxp, cols_full = nxp + nmpc * m;
 
-    // workspace (cached in the set): block maps, ThetaT, V, O
+    // block maps of the plant: constant per (plant, n_mpc), cached in the set.  The loop state (ThetaT, V, O) is
+    // per-call scratch, allocated and freed in stream order on the caller's stream: closed loops of one set may run
+    // on several streams at once (ControllerSet.closed_loop_host alternates its chunks between two streams).
     const size_t nMf = (size_t)rows_full * cols_full;
     const size_t nMr = rem ? (size_t)(rem * p + nxp) * (nxp + rem * m) : 0;
-    const size_t need = nMf + nMr + (size_t)B * (nth + cols_full + rows_full);
     std::vector<double> hM = block_map(plant, nmpc);
     if (rem) {
         std::vector<double> hr = block_map(plant, rem);
         hM.insert(hM.end(), hr.begin(), hr.end());
     }
-    if (set->gemm_ws.bytes < need * sizeof(double) || set->gemm_host != hM) {
-        DDMPC_CUDA(cudaDeviceSynchronize());   // loops still using the previous workspace
-        if (set->gemm_ws.bytes < need * sizeof(double)) DDMPC_CUDA(set->gemm_ws.alloc(need * sizeof(double)));
+    if (set->gemm_host != hM) {
+        DDMPC_CUDA(cudaDeviceSynchronize());   // loops still reading the previous maps
+        DDMPC_CUDA(set->gemm_ws.alloc((nMf + nMr) * sizeof(double)));
         DDMPC_CUDA(cudaMemcpy(set->gemm_ws.p, hM.data(), sizeof(double) * hM.size(), cudaMemcpyHostToDevice));
         set->gemm_host = hM;
     }
-    double *Mf = set->gemm_ws.d(), *Mr = Mf + nMf;
-    double *ThetaT = Mr + nMr, *V = ThetaT + (size_t)B * nth, *O = V + (size_t)B * cols_full;
+    const double *Mf = set->gemm_ws.d(), *Mr = Mf + nMf;
+    DDMPC_CUDA(pool_ready());
+    double *scratch = nullptr;
+    DDMPC_CUDA(cudaMallocAsync((void **)&scratch, sizeof(double) * (size_t)B * (nth + cols_full + rows_full), st));
+    struct ScratchFree {
+        double *p;
+        cudaStream_t s;
+        ~ScratchFree() { cudaFreeAsync(p, s); }           // stream-ordered: after the last kernel enqueued below
+    } scratch_free{scratch, st};
+    double *ThetaT = scratch, *V = ThetaT + (size_t)B * nth, *O = V + (size_t)B * cols_full;
 
     const int T = 128, G = ceil_div(B, T);
     k_gl_final<<<G, T, 0, st>>>(B, nxp, 0, V, status, nullptr, nullptr, 0);

@@ -1,0 +1,360 @@
+// Fused closed loop for PER-LOOP controllers (BASELINE config 2: every closed loop has its own (u_d, y_d), hence
+// its own gains; config 5: a grid of controllers x a few loops each) and for small batches of a shared controller.
+//
+// When every loop has its own gain block there is no shared matrix, hence no GEMM: a solve is a private
+// (n_mpc*m x n_theta) matrix-vector product.  A batch of 4096 such loops offers a B200 far fewer independent chains
+// than it has FP64 lanes, so the design goal is LATENCY of the serial chain solve -> plant -> window, not throughput:
+//
+//   * EIGHT LANES PER LOOP (4 loops per warp).  Lane k of a loop owns planned-input row k of the gain (its window
+//     coefficients live in REGISTERS for the whole run; the set-point part is folded into one constant per row) and
+//     rows k, k + 8 of the plant's n_mpc-step block map  [Y; x+] = Mblk [x; U]  (model_simulation.py:93-98 unrolled;
+//     measurement noise enters y only).  A solve is therefore ONE 16-term dot product deep instead of 8 of them, and
+//     the n_mpc plant steps of a block are ONE 12-term dot product deep instead of n_mpc * 2 matrix-vector products.
+//   * the loop state (window, plant state) is replicated in the registers of the 8 lanes; what a lane produces (one
+//     planned input, one or two outputs / next-state entries) reaches the other seven through 160 bytes of shared
+//     memory per loop: two __syncwarp per MPC iteration, no block-level barrier, no atomics.
+//   * measurement noise: Philox4x32-10 in-kernel (lane = one output of the block) or the caller's array (parity mode);
+//   * trajectories in the reference layout (B, n_steps, m|p): the 8 lanes of a loop write 64 contiguous bytes per
+//     block and array (the thread-per-loop kernel wrote 8-byte pieces 3.2 KB apart: 1.49x DRAM traffic).
+//
+// Replaces, per loop, the same reference code as k_closed_loop (solve.cu): update_and_solve_data_driven_mpc
+// (direct_data_driven_mpc_controller.py:389-407), get_optimal_control_input_at_step (:810-842),
+// store_input_output_measurement (:844-895), LTIModel.simulate_step (utilities/model_simulation.py:93-98) and the loop
+// of simulate_data_driven_mpc_control_loop (utilities/controller/controller_operation.py:263-305), for equality-only
+// controllers (ROBUST / slack NONE, NOMINAL) of the compiled shapes.
+#include <vector>
+
+#include "common.cuh"
+#include "plan.cuh"
+
+namespace ddmpc {
+
+std::vector<double> block_map(const ddmpc_plant *pl, int s);   // gemm_loop.cu
+
+template <int RB, int KB>
+struct PlMaps {
+    double Mb[RB][KB];   // block map of a full n_mpc-step block: rows y_0..y_{n_mpc-1}, x_{n_mpc}; columns x_0, u_0..
+    double Mt[RB][KB];   // block map of the last, partial block (controller_operation.py:278), same layout, zero padded
+};
+
+struct PerLoopArgs {
+    int B, n_steps, nth, Lm, nfix;
+    const int *ctrl_idx;               // (B) controller of each loop, NULL = controller 0
+    const double *Ku;                  // (count, Lm, nth)
+    const double *F;                   // (count, nfix, nth) nominal feasibility map, NULL for ROBUST
+    const int *Fnz;                    // (count) 1 when F of that controller is not identically zero
+    const double *x0, *u_past0, *y_past0, *u_s, *y_s, *w;
+    unsigned long long id0;
+    double eps;
+    double *u_sys, *y_sys, *x_final;
+    int *status, *iters;
+    uint32_t rk[20];                   // Philox round keys (key + r * Weyl), filled on the host
+};
+
+__device__ __forceinline__ void pl_philox_round(uint32_t &c0, uint32_t &c1, uint32_t &c2, uint32_t &c3, uint32_t k0,
+                                                uint32_t k1) {
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+    c1 = (uint32_t)p1;
+    c3 = (uint32_t)p0;
+    c0 = n0;
+    c2 = n2;
+}
+
+template <int N, int M, int P, int NX, int NMPC, bool PHILOX>
+__global__ void __launch_bounds__(128)
+k_closed_loop_perloop(const __grid_constant__ PlMaps<NMPC * P + NX, NX + NMPC * M> maps, const PerLoopArgs a) {
+    constexpr int G = 8;                                   // lanes per loop
+    constexpr int R = NMPC * M, RY = NMPC * P, RB = RY + NX, KB = NX + R;
+    constexpr int NWU = N * M, NWY = N * P, NW = NWU + NWY, NSP = M + P;
+    constexpr int RU = (R + G - 1) / G, RP = (RB + G - 1) / G;   // solve rows / plant rows per lane
+    constexpr int EX = R + RB;                             // exchange buffer of a loop: [U (R); Y (RY); x+ (NX)]
+    constexpr int S = ((EX + 11) / 16) * 16 + 4;           // stride = 4 (mod 16) doubles: the 4 loops of a warp read
+                                                           // their (broadcast) 16-byte pieces from disjoint banks
+    __shared__ __align__(16) double ex_s[16][S];
+    const int lane = threadIdx.x & 31, k = lane & (G - 1);
+    const int slot = threadIdx.x >> 3;                     // loop slot in the CTA
+    double *ex = ex_s[slot];
+    int b = blockIdx.x * (blockDim.x >> 3) + slot;
+    const bool live = b < a.B;
+    if (!live) b = a.B - 1;                                // dead slots replay the last loop and never store
+    const int c = a.ctrl_idx ? a.ctrl_idx[b] : 0;
+    const size_t f0 = (size_t)b * a.n_steps;
+    const unsigned long long sid = a.id0 + (unsigned long long)b;
+    const uint32_t sid_lo = (uint32_t)sid, sid_hi = (uint32_t)(sid >> 32);
+
+    // ---- per-loop constants: gain rows on the window (registers), set-point term, plant block-map rows
+    double sp[NSP];
+#pragma unroll
+    for (int i = 0; i < M; ++i) sp[i] = a.u_s[(size_t)b * M + i];
+#pragma unroll
+    for (int i = 0; i < P; ++i) sp[M + i] = a.y_s[(size_t)b * P + i];
+    double Kw[RU][NW], csp[RU];
+#pragma unroll
+    for (int i = 0; i < RU; ++i) {
+        const int r = k + G * i;
+        const double *row = a.Ku + ((size_t)c * a.Lm + (r < R ? r : 0)) * a.nth;
+        const double on = r < R ? 1.0 : 0.0;
+#pragma unroll
+        for (int j = 0; j < NW; ++j) Kw[i][j] = on * __ldg(row + j);
+        double acc = 0.0;
+#pragma unroll
+        for (int j = 0; j < NSP; ++j) acc = fma(__ldg(row + NW + j), sp[j], acc);
+        csp[i] = on * acc;
+    }
+    double Mc[RP][KB];
+    auto load_map = [&](const double (&Mm)[RB][KB]) {
+#pragma unroll
+        for (int i = 0; i < RP; ++i) {
+            const int r = k + G * i;
+#pragma unroll
+            for (int j = 0; j < KB; ++j) Mc[i][j] = r < RB ? Mm[r < RB ? r : 0][j] : 0.0;
+        }
+    };
+    load_map(maps.Mb);
+
+    // ---- loop state, replicated in the 8 lanes: measurement window (oldest first) and plant state
+    double win[NW], x[NX];
+#pragma unroll
+    for (int j = 0; j < NWU; ++j) win[j] = a.u_past0[(size_t)b * NWU + j];
+#pragma unroll
+    for (int j = 0; j < NWY; ++j) win[NWU + j] = a.y_past0[(size_t)b * NWY + j];
+#pragma unroll
+    for (int j = 0; j < NX; ++j) x[j] = a.x0[(size_t)b * NX + j];
+
+    const double *Fc = nullptr;
+    int fnz = 0;
+    if (a.F) {
+        fnz = a.Fnz[c];
+        Fc = a.F + (size_t)c * a.nfix * a.nth;
+    }
+    const bool any_f = a.F && __any_sync(0xffffffffu, fnz != 0);
+
+    int status = DDMPC_SOLVE_OPTIMAL;
+    const int nblk = (a.n_steps + NMPC - 1) / NMPC;
+    double Y[RY];
+#pragma unroll
+    for (int j = 0; j < RY; ++j) Y[j] = 0.0;
+    for (int blk = 0, t0 = 0; blk < nblk; ++blk, t0 += NMPC) {
+        const int steps = min(NMPC, a.n_steps - t0);
+        if (steps < NMPC) load_map(maps.Mt);
+        // ---- measurement noise of this lane's output rows (independent of the solve: issued first)
+        double nz[RP];
+#pragma unroll
+        for (int i = 0; i < RP; ++i) {
+            const int r = k + G * i;
+            nz[i] = 0.0;
+            if (G * i < RY) {
+                if constexpr (PHILOX) {
+                    // noise word q = step * P + output is word (q & 3) of Philox call (q >> 2)  (solve.cu)
+                    const unsigned q = (unsigned)t0 * (unsigned)P + (unsigned)(r < RY ? r : 0);
+                    uint32_t c0 = q >> 2, c1 = 0u, c2 = sid_lo, c3 = sid_hi;
+#pragma unroll
+                    for (int rr = 0; rr < 10; ++rr) pl_philox_round(c0, c1, c2, c3, a.rk[2 * rr], a.rk[2 * rr + 1]);
+                    const unsigned w4 = q & 3u;
+                    const uint32_t word = w4 == 0 ? c0 : (w4 == 1 ? c1 : (w4 == 2 ? c2 : c3));
+                    const double v = a.eps * (2.0 * __hiloint2double((int)(0x3FF00000u | (word >> 12)), (int)(word << 20)) - 3.0);
+                    nz[i] = r < RY ? v : 0.0;
+                } else {
+                    if (r < RY && t0 + r / P < a.n_steps) nz[i] = __ldg(a.w + (f0 + t0) * P + r);
+                }
+            }
+        }
+        // ---- NOMINAL with rank-deficient data: consistency of the window with range(H) (solve.cu, k_closed_loop)
+        if (any_f) {
+            double fe = 0.0, thmax = 0.0;
+#pragma unroll
+            for (int j = 0; j < NW; ++j) thmax = fmax(thmax, fabs(win[j]));
+#pragma unroll
+            for (int j = 0; j < NSP; ++j) thmax = fmax(thmax, fabs(sp[j]));
+            if (fnz) {
+                for (int i = k; i < a.nfix; i += G) {
+                    const double *row = Fc + (size_t)i * a.nth;
+                    double acc = 0.0;
+#pragma unroll
+                    for (int j = 0; j < NW; ++j) acc = fma(__ldg(row + j), win[j], acc);
+#pragma unroll
+                    for (int j = 0; j < NSP; ++j) acc = fma(__ldg(row + NW + j), sp[j], acc);
+                    fe = fmax(fe, fabs(acc));
+                }
+            }
+#pragma unroll
+            for (int o = 1; o < G; o <<= 1) fe = fmax(fe, __shfl_xor_sync(0xffffffffu, fe, o));
+            if (fnz && fe > 1e-6 * (1.0 + thmax)) status = max(status, (int)DDMPC_SOLVE_INFEASIBLE);
+        }
+        // ---- solve (equality-only => affine in the window): planned input r = csp_r + Kw_r . window
+        double u_own[RU];
+#pragma unroll
+        for (int i = 0; i < RU; ++i) {
+            double acc[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+            for (int j = 0; j < NW; ++j) acc[j & 3] = fma(Kw[i][j], win[j], acc[j & 3]);
+            u_own[i] = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + csp[i];
+            const int r = k + G * i;
+            if (r < R) ex[r] = u_own[i];
+        }
+        __syncwarp();
+        double U[R];
+        if constexpr (R % 2 == 0) {
+#pragma unroll
+            for (int j = 0; j < R; j += 2) {
+                const double2 v = *reinterpret_cast<const double2 *>(ex + j);
+                U[j] = v.x;
+                U[j + 1] = v.y;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < R; ++j) U[j] = ex[j];
+        }
+        // ---- plant: the n_mpc steps of the block at once, row r of [Y; x+] = Mblk [x; U] (+ noise on the y rows)
+        double v_own[RP];
+#pragma unroll
+        for (int i = 0; i < RP; ++i) {
+            double acc[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+            for (int j = 0; j < NX; ++j) acc[j & 3] = fma(Mc[i][j], x[j], acc[j & 3]);
+#pragma unroll
+            for (int j = 0; j < R; ++j) acc[(NX + j) & 3] = fma(Mc[i][NX + j], U[j], acc[(NX + j) & 3]);
+            v_own[i] = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + nz[i];
+            const int r = k + G * i;
+            if (r < RB) ex[R + r] = v_own[i];
+        }
+        // ---- record (controller_operation.py:290-300): the lanes of a loop write one contiguous run per array
+        if (live) {
+#pragma unroll
+            for (int i = 0; i < RU; ++i) {
+                const int r = k + G * i;
+                if (r < steps * M) a.u_sys[(f0 + t0) * M + r] = u_own[i];
+            }
+#pragma unroll
+            for (int i = 0; i < RP; ++i) {
+                const int r = k + G * i;
+                if (G * i < RY && r < steps * P) a.y_sys[(f0 + t0) * P + r] = v_own[i];
+            }
+        }
+        __syncwarp();
+        if constexpr (RY % 2 == 0 && R % 2 == 0) {
+#pragma unroll
+            for (int j = 0; j < RY; j += 2) {
+                const double2 v = *reinterpret_cast<const double2 *>(ex + R + j);
+                Y[j] = v.x;
+                Y[j + 1] = v.y;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < RY; ++j) Y[j] = ex[R + j];
+        }
+#pragma unroll
+        for (int j = 0; j < NX; ++j) x[j] = ex[R + RY + j];
+        // ---- window update (controller.py:893-895), n_mpc steps at once; a partial block is the last one
+        if constexpr (NMPC >= N) {
+#pragma unroll
+            for (int j = 0; j < NWU; ++j) win[j] = U[(NMPC - N) * M + j];
+#pragma unroll
+            for (int j = 0; j < NWY; ++j) win[NWU + j] = Y[(NMPC - N) * P + j];
+        } else {
+#pragma unroll
+            for (int j = 0; j < NWU - R; ++j) win[j] = win[j + R];
+#pragma unroll
+            for (int j = 0; j < R; ++j) win[NWU - R + j] = U[j];
+#pragma unroll
+            for (int j = 0; j < NWY - RY; ++j) win[NWU + j] = win[NWU + j + RY];
+#pragma unroll
+            for (int j = 0; j < RY; ++j) win[NWU + NWY - RY + j] = Y[j];
+        }
+    }
+    // ---- per-loop verdict: a non-finite input or output turns the state non-finite for good
+    bool finite = true;
+#pragma unroll
+    for (int j = 0; j < NX; ++j) finite = finite && isfinite(x[j]);
+    const int last_steps = a.n_steps - (nblk - 1) * NMPC;
+#pragma unroll
+    for (int j = 0; j < RY; ++j)
+        if (j < last_steps * P) finite = finite && isfinite(Y[j]);
+    if (!finite) status = max(status, (int)DDMPC_SOLVE_NONFINITE);
+    if (live) {
+        if (k == 0) {
+            if (a.status) a.status[b] = status;
+            if (a.iters) a.iters[b] = nblk;
+        }
+        if (a.x_final) {
+#pragma unroll
+            for (int j = 0; j < NX; ++j)
+                if ((j & (G - 1)) == k) a.x_final[(size_t)b * NX + j] = x[j];
+        }
+    }
+}
+
+template <int N, int M, int P, int NX, int NMPC>
+static int launch_perloop(const ddmpc_plant *plant, PerLoopArgs a, uint64_t seed, cudaStream_t st) {
+    constexpr int R = NMPC * M, RY = NMPC * P, RB = RY + NX, KB = NX + R;
+    using Maps = PlMaps<RB, KB>;
+    static_assert(sizeof(Maps) + sizeof(PerLoopArgs) <= 4000, "block maps must fit in the kernel parameter space");
+    Maps maps;
+    const std::vector<double> Mb = block_map(plant, NMPC);
+    for (int r = 0; r < RB; ++r)
+        for (int j = 0; j < KB; ++j) maps.Mb[r][j] = maps.Mt[r][j] = Mb[(size_t)r * KB + j];
+    const int rem = a.n_steps % NMPC;
+    if (rem) {
+        const std::vector<double> Mr = block_map(plant, rem);
+        const int cr = NX + rem * M;
+        for (int r = 0; r < RB; ++r)
+            for (int j = 0; j < KB; ++j) maps.Mt[r][j] = 0.0;
+        for (int r = 0; r < rem * P; ++r)
+            for (int j = 0; j < cr; ++j) maps.Mt[r][j] = Mr[(size_t)r * cr + j];
+        for (int i = 0; i < NX; ++i)
+            for (int j = 0; j < cr; ++j) maps.Mt[RY + i][j] = Mr[(size_t)(rem * P + i) * cr + j];
+    }
+    for (int r = 0; r < 10; ++r) {
+        a.rk[2 * r] = (uint32_t)seed + (uint32_t)r * 0x9E3779B9u;
+        a.rk[2 * r + 1] = (uint32_t)(seed >> 32) + (uint32_t)r * 0xBB67AE85u;
+    }
+    // one-warp CTAs deal a small batch to the SMs at the finest grain; larger CTAs once the batch fills the machine
+    const int wpc = a.B > 65536 ? 4 : (a.B > 16384 ? 2 : 1);
+    const int grid = ceil_div(a.B, 4 * wpc);
+    if (a.w) k_closed_loop_perloop<N, M, P, NX, NMPC, false><<<grid, 32 * wpc, 0, st>>>(maps, a);
+    else k_closed_loop_perloop<N, M, P, NX, NMPC, true><<<grid, 32 * wpc, 0, st>>>(maps, a);
+    DDMPC_LAUNCH_CHECK();
+    return DDMPC_OK;
+}
+
+// Largest batch of a SHARED equality-only controller that still takes this kernel: below it the thread-per-loop
+// kernels (fast_loop.cu) leave most of the machine idle and are bound by their serial chain (0.25 ms for ANY batch up
+// to 65,536 four-tank loops); from 16,384 loops on the warp-specialised tensor-core kernel takes over.
+static constexpr int kPerLoopSharedMaxB = 16383;
+
+// Returns DDMPC_OK when handled, -1 when this path does not apply.
+int closed_loop_perloop_try(const ddmpc_set *set, const ddmpc_plant *plant, int B, const int *ctrl_idx, const double *x0,
+                            const double *u_past0, const double *y_past0, const double *u_s, const double *y_s,
+                            const double *w, uint64_t seed, uint64_t id0, double eps, int n_steps, double *u_sys,
+                            double *y_sys, int *status, int *iters, double *x_final, cudaStream_t st) {
+    const Plan &pl = set->plan;
+    const Dims &d = pl.d;
+    if (d.nb > 0) return -1;                               // box rows: other kernels
+    const int path = set->opt_path;
+    if (path != DDMPC_PATH_AUTO && path != DDMPC_PATH_PERLOOP) return -1;
+    const bool per_loop = ctrl_idx != nullptr || pl.count != 1 || !d.robust;
+    if (path == DDMPC_PATH_AUTO && !per_loop && B > kPerLoopSharedMaxB) return -1;
+    PerLoopArgs a{};
+    a.B = B; a.n_steps = n_steps; a.nth = d.nth; a.Lm = d.Lm; a.nfix = d.nfix;
+    a.ctrl_idx = ctrl_idx;
+    a.Ku = pl.Ku.d();
+    a.F = d.robust ? nullptr : pl.F.d();
+    a.Fnz = d.robust ? nullptr : pl.Fnz.i();
+    a.x0 = x0; a.u_past0 = u_past0; a.y_past0 = y_past0; a.u_s = u_s; a.y_s = y_s; a.w = w;
+    a.id0 = id0; a.eps = eps;
+    a.u_sys = u_sys; a.y_sys = y_sys; a.x_final = x_final; a.status = status; a.iters = iters;
+    const int nmpc = set->prm.n_mpc_step;
+#define DDMPC_PERLOOP_CASE(N_, M_, P_, NX_, NMPC_)                                                   \
+    if (d.n == N_ && d.m == M_ && d.p == P_ && plant->n_x == NX_ && nmpc == NMPC_)                   \
+        return launch_perloop<N_, M_, P_, NX_, NMPC_>(plant, a, seed, st);
+    DDMPC_PERLOOP_CASE(4, 2, 2, 4, 4)
+    DDMPC_PERLOOP_CASE(4, 2, 2, 4, 1)
+    DDMPC_PERLOOP_CASE(4, 2, 2, 4, 2)
+    DDMPC_PERLOOP_CASE(2, 1, 1, 2, 1)
+    DDMPC_PERLOOP_CASE(2, 1, 1, 2, 2)
+#undef DDMPC_PERLOOP_CASE
+    return -1;
+}
+
+}  // namespace ddmpc

@@ -2,6 +2,7 @@
 // condensed solve operators produced by the setup pipeline (setup.cu) and
 // consumed by the batched solver / fused closed loop (solve.cu).
 #pragma once
+#include <initializer_list>
 #include <vector>
 
 #include "common.cuh"
@@ -49,6 +50,11 @@ struct Plan {
     DevBuf Fnz;    // (1) int        1 when F has a non-zero entry (rank-deficient data); 0 = every window is feasible
     DevBuf lamA, lamS;  // per-controller lamb_alpha*eps_max, lamb_sigma
     std::vector<int> pe_rank, status;
+    void detach_streams() {
+        for (DevBuf *b : {&H, &Om, &W, &Ku, &Z, &X0, &Ks, &Phi, &Psi, &Lam, &Yf, &rho2, &rs, &lo, &hi, &bmax, &blo, &bhi,
+                          &umin, &umax, &ymin, &ymax, &F, &Fnz, &lamA, &lamS})
+            b->detach_stream();
+    }
     double bound = 0.0;   // c * eps_max
     std::vector<double> u_min, u_max;   // host copy of the input box (empty = none)
 };
@@ -58,6 +64,13 @@ struct Plan {
 struct ddmpc_set {
     ddmpc_params prm;
     ddmpc::Plan plan;
+    // ddmpc_set_option(): kernel selection of ddmpc_closed_loop_batch (DDMPC_PATH_*), CTA size of the config-4 kernel,
+    // loops per thread of the hybrid kernel (0 = automatic)
+    int opt_path = 0, opt_dmma_warps = 1, opt_lpt = 0;
+    // per-controller setup verdicts on the device (count ints, DDMPC_OK or the error): kernels report failed
+    // controllers as DDMPC_SOLVE_NONFINITE with NaN outputs instead of finite garbage
+    ddmpc::DevBuf ctrl_status;
+    int n_failed = 0;
     // last plant uploaded by ddmpc_closed_loop_batch (re-used while unchanged, so the
     // launch path stays asynchronous)
     mutable std::vector<double> plant_host;
@@ -65,7 +78,8 @@ struct ddmpc_set {
     // fast_loop.cu: host copy of the applied gain rows + device copy of their set-point block
     mutable std::vector<double> fast_host;
     mutable ddmpc::DevBuf fast_ksp;
-    // gemm_loop.cu: workspace (block maps of the plant + value-major loop state) and its host key
+    // gemm_loop.cu: block maps of the plant and their host key (the per-call loop state is allocated per call,
+    // stream-ordered: two streams may run closed loops of one set at the same time)
     mutable ddmpc::DevBuf gemm_ws;
     mutable std::vector<double> gemm_host;
     // dmma_loop.cu: packed A fragments (gain rows + block maps of the plant) and their host key
@@ -75,6 +89,10 @@ struct ddmpc_set {
     mutable void *stage_host = nullptr;
     mutable ddmpc::DevBuf stage_dev;
     mutable cudaStream_t stage_stream = nullptr;
+    void detach_streams() {
+        plan.detach_streams();
+        for (ddmpc::DevBuf *b : {&ctrl_status, &plant_dev, &fast_ksp, &gemm_ws, &dmma_ws, &stage_dev}) b->detach_stream();
+    }
     ~ddmpc_set() {
         if (stage_host) cudaFreeHost(stage_host);
         if (stage_stream) cudaStreamDestroy(stage_stream);

@@ -17,6 +17,7 @@ namespace ddmpc {
 
 thread_local char g_last_error[512] = "";
 std::atomic<uint64_t> g_launches{0};
+thread_local cudaStream_t g_scratch_stream = nullptr;
 
 // ---------------------------------------------------------------------------
 // K1: Hankel gather.  H[row0 + r, col] = X[r + col * nch]   (hankel_matrix.py:47-51:
@@ -364,6 +365,14 @@ __global__ void k_sub_identity(int n, double *__restrict__ A, long bs) {
 // ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
+// gains of controllers whose setup failed -> NaN
+__global__ void k_poison(int count, long per, const int *__restrict__ cstat, double *__restrict__ M) {
+    const long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < (long)count * per && cstat[e / per] != 0) M[e] = __longlong_as_double(0x7ff8000000000000LL);
+}
+
+int closed_loop_fast_prepare(ddmpc_set *set, cudaStream_t st);   // fast_loop.cu
+
 static Dims make_dims(const ddmpc_params &q) {
     Dims d{};
     d.n = q.n; d.m = q.m; d.p = q.p; d.N = q.N; d.L = q.L; d.Lp = q.L + q.n;
@@ -645,6 +654,7 @@ int set_create_device(const ddmpc_params *prm, int count, const double *u_d, siz
     *out = nullptr;
     const ddmpc_params &q = *prm;
     DDMPC_TRY(validate(q));
+    ScratchStreamScope scratch_scope(st);   // every DevBuf below is allocated and freed in the order of `st`
     // Remark 1 of the paper / controller.py:275-283
     const long N_min = (long)q.m * (q.L + 2 * q.n) + q.L + 2 * q.n - 1;
     if (q.check_pe && q.N < N_min)
@@ -825,6 +835,30 @@ int set_create_device(const ddmpc_params *prm, int count, const double *u_d, siz
     } else {
         DDMPC_TRY(build_nominal(st, pl, fa, perm_d.i(), invperm_d.i(), u_d, (long)ud_stride, y_d, (long)yd_stride, R, Q));
     }
+    // Per-controller verdicts.  A single controller that cannot be set up is an error, as in the reference
+    // (controller.py:285-296 raises at construction).  In a larger set the failed controllers are poisoned: their gains
+    // become NaN, so every solve / closed loop that uses one returns NaN and DDMPC_SOLVE_NONFINITE instead of finite
+    // garbage under status "optimal"; ddmpc_set_failed_count / ddmpc_set_info report which ones.
+    for (int c = 0; c < count; ++c) set->n_failed += pl.status[c] != DDMPC_OK;
+    if (count == 1 && pl.status[0] == DDMPC_ERR_FACTORIZATION)
+        return fail(DDMPC_ERR_FACTORIZATION,
+                    "The Gram matrix of the data or the reduced Hessian is not positive definite: the data are too "
+                    "ill-conditioned for the robust setup.");
+    if (set->n_failed > 0) {
+        DDMPC_CUDA(set->ctrl_status.alloc(sizeof(int) * count));
+        DDMPC_CUDA(cudaMemcpyAsync(set->ctrl_status.p, pl.status.data(), sizeof(int) * count, cudaMemcpyHostToDevice, st));
+        const int T = 256;
+        k_poison<<<ceil_div((long)count * d.Lm * d.nth, T), T, 0, st>>>(count, (long)d.Lm * d.nth, set->ctrl_status.i(), pl.Ku.d());
+        DDMPC_LAUNCH_CHECK();
+        if (d.nb > 0) {
+            k_poison<<<ceil_div((long)count * d.nb * d.nth, T), T, 0, st>>>(count, (long)d.nb * d.nth, set->ctrl_status.i(), pl.Ks.d());
+            DDMPC_LAUNCH_CHECK();
+        }
+        DDMPC_CUDA(cudaStreamSynchronize(st));
+    }
+    DDMPC_TRY(closed_loop_fast_prepare(set.get(), st));
+    DDMPC_CUDA(cudaStreamSynchronize(st));
+    set->detach_streams();                  // the set may outlive `st`: it is freed on the legacy stream after a device sync
     *out = set.release();
     return DDMPC_OK;
 }
@@ -938,6 +972,25 @@ void ddmpc_set_destroy(ddmpc_set *set) {
 }
 
 int ddmpc_set_count(const ddmpc_set *set) { return set ? set->plan.count : 0; }
+int ddmpc_set_failed_count(const ddmpc_set *set) { return set ? set->n_failed : 0; }
+
+int ddmpc_set_option(ddmpc_set *set, const char *name, int value) {
+    if (!set || !name) return fail(DDMPC_ERR_INVALID_ARG, "set_option: null argument");
+    const std::string nm(name);
+    if (nm == "closed_loop_path") {
+        if (value < DDMPC_PATH_AUTO || value > DDMPC_PATH_GEMM) return fail(DDMPC_ERR_INVALID_ARG, "set_option: unknown path %d", value);
+        set->opt_path = value;
+    } else if (nm == "dmma_warps") {
+        if (value != 1 && value != 2 && value != 4) return fail(DDMPC_ERR_INVALID_ARG, "set_option: dmma_warps must be 1, 2 or 4");
+        set->opt_dmma_warps = value;
+    } else if (nm == "loops_per_thread") {
+        if (value < 0 || value > 2) return fail(DDMPC_ERR_INVALID_ARG, "set_option: loops_per_thread must be 0, 1 or 2");
+        set->opt_lpt = value;
+    } else {
+        return fail(DDMPC_ERR_INVALID_ARG, "set_option: unknown option '%s'", name);
+    }
+    return DDMPC_OK;
+}
 
 int ddmpc_set_info(const ddmpc_set *set, int index, int *pe_rank, int *status) {
     if (!set || index < 0 || index >= set->plan.count) return fail(DDMPC_ERR_INVALID_ARG, "set_info: bad index");

@@ -156,7 +156,13 @@ __global__ void k_solve_batch(KArgs a, int B, const int *__restrict__ ctrl_idx, 
         if (fe > 1e-6 * (1.0 + thmax)) status = max(status, (int)DDMPC_SOLVE_INFEASIBLE);
     }
     const double *Ku = a.Ku + (size_t)c * a.Lm * a.nth;
-    for (int k = 0; k < a.Lm; ++k) optimal_u[(size_t)b * a.Lm + k] = dot_theta(Ku + (size_t)k * a.nth, th, a.nth, TS, tid);
+    bool ofinite = true;       // a controller whose setup failed has NaN gains (setup.cu, k_poison)
+    for (int k = 0; k < a.Lm; ++k) {
+        const double v = dot_theta(Ku + (size_t)k * a.nth, th, a.nth, TS, tid);
+        ofinite = ofinite && isfinite(v);
+        optimal_u[(size_t)b * a.Lm + k] = v;
+    }
+    if (finite && !ofinite) status = max(status, (int)DDMPC_SOLVE_NONFINITE);
     double J = 0.0;
     if (cost) {
         const double *Z = a.Z + (size_t)c * a.nth * a.nth;
@@ -272,7 +278,12 @@ k_solve_small(KArgs a, int B, const int *__restrict__ ctrl_idx, const double *__
     }
     const double *Ku = a.Ku + (size_t)c * a.Lm * a.nth;
     // (the result is staged in shared memory and written once: optimal_u may be mapped host memory)
-    for (int k = tid; k < a.Lm; k += T) uo[k] = dot_row(Ku + (size_t)k * a.nth, th, a.nth);
+    double obad = 0.0;         // a controller whose setup failed has NaN gains (setup.cu, k_poison)
+    for (int k = tid; k < a.Lm; k += T) {
+        uo[k] = dot_row(Ku + (size_t)k * a.nth, th, a.nth);
+        if (!isfinite(uo[k])) obad = 1.0;
+    }
+    if (block_max(obad, red) != 0.0) status = max(status, (int)DDMPC_SOLVE_NONFINITE);
     double J = 0.0;
     if (cost) {
         const double *Z = a.Z + (size_t)c * a.nth * a.nth;
@@ -581,6 +592,11 @@ int closed_loop_fast_try(const ddmpc_set *set, const ddmpc_plant *plant, int B, 
                          double *y_sys, int *status, int *iters, double *x_final, double tol, int max_iter,
                          cudaStream_t st);
 
+int closed_loop_perloop_try(const ddmpc_set *set, const ddmpc_plant *plant, int B, const int *ctrl_idx, const double *x0,
+                            const double *u_past0, const double *y_past0, const double *u_s, const double *y_s,
+                            const double *w, uint64_t seed, uint64_t id0, double eps, int n_steps, double *u_sys,
+                            double *y_sys, int *status, int *iters, double *x_final, cudaStream_t st);
+
 int closed_loop_gemm_try(const ddmpc_set *set, const ddmpc_plant *plant, int B, const int *ctrl_idx, const double *x0,
                          const double *u_past0, const double *y_past0, const double *u_s, const double *y_s,
                          const double *w, uint64_t seed, uint64_t id0, double eps, int n_steps, double *u_sys,
@@ -760,6 +776,7 @@ int ddmpc_solve_full_batch(const ddmpc_set *set, int B, const int32_t *ctrl_idx,
                            double *ubar, double *ybar, double *sigma, double *alpha, void *stream) {
     if (!set || B <= 0) return fail(DDMPC_ERR_INVALID_ARG, "solve_full_batch: bad argument");
     cudaStream_t st = (cudaStream_t)stream;
+    ScratchStreamScope scratch_scope(st);   // scratch below is allocated and freed in the order of `st`
     const Plan &pl = set->plan;
     const Dims &d = pl.d;
     if (alpha && !d.robust) return fail(DDMPC_ERR_INVALID_ARG, "alpha is only defined (unique) for ROBUST controllers");
@@ -783,8 +800,7 @@ int ddmpc_solve_full_batch(const ddmpc_set *set, int B, const int32_t *ctrl_idx,
         k_full_alpha<<<ceil_div((long)B * d.cols, T), T, 0, st>>>(a, B, ctrl_idx, shared_data, pl.H.d(), gb.d(), alpha);
         DDMPC_LAUNCH_CHECK();
     }
-    DDMPC_CUDA(cudaStreamSynchronize(st));  // scratch lifetime
-    return DDMPC_OK;
+    return DDMPC_OK;                        // (scratch is released in stream order, no synchronise needed)
 }
 
 int ddmpc_closed_loop_batch(const ddmpc_set *set, const ddmpc_plant *plant, int B, const int32_t *ctrl_idx,
@@ -804,21 +820,29 @@ int ddmpc_closed_loop_batch(const ddmpc_set *set, const ddmpc_plant *plant, int 
     if (B == 0 || n_steps == 0) return DDMPC_OK;
     cudaStream_t st = (cudaStream_t)stream;
     const int nxp = plant->n_x;
-    {   // register-resident specialisation (shared equality-only controller, small system)
-        const int rc = closed_loop_fast_try(set, plant, B, ctrl_idx, x0, u_past0, y_past0, u_s, y_s, w, noise_seed,
-                                            scenario_id0, noise_eps, n_steps, u_sys, y_sys, status, iters, x_final, tol,
-                                            max_iter, st);
-        if (rc != -1) return rc;
-    }
-    {   // large systems, compiled shapes: one fused launch, a warp per 8 loops, both products on the FP64 tensor cores
-        const int rc = closed_loop_dmma_try(set, plant, B, ctrl_idx, x0, u_past0, y_past0, u_s, y_s, w, noise_seed,
-                                            scenario_id0, noise_eps, n_steps, u_sys, y_sys, status, iters, x_final, st);
-        if (rc != -1) return rc;
-    }
-    {   // large systems: the batch as the N dimension of FP64 tensor-core GEMMs
-        const int rc = closed_loop_gemm_try(set, plant, B, ctrl_idx, x0, u_past0, y_past0, u_s, y_s, w, noise_seed,
-                                            scenario_id0, noise_eps, n_steps, u_sys, y_sys, status, iters, x_final, st);
-        if (rc != -1) return rc;
+    const int path = set->opt_path;
+    if (path != DDMPC_PATH_GENERIC) {
+        {   // 8 lanes per loop: per-loop controllers (any batch), NOMINAL, small batches of a shared controller
+            const int rc = closed_loop_perloop_try(set, plant, B, ctrl_idx, x0, u_past0, y_past0, u_s, y_s, w, noise_seed,
+                                                   scenario_id0, noise_eps, n_steps, u_sys, y_sys, status, iters, x_final, st);
+            if (rc != -1) return rc;
+        }
+        {   // register-resident / warp-specialised kernels (shared ROBUST controller, four-tank-size system)
+            const int rc = closed_loop_fast_try(set, plant, B, ctrl_idx, x0, u_past0, y_past0, u_s, y_s, w, noise_seed,
+                                                scenario_id0, noise_eps, n_steps, u_sys, y_sys, status, iters, x_final, tol,
+                                                max_iter, st);
+            if (rc != -1) return rc;
+        }
+        {   // large systems, compiled shapes: one fused launch, a warp per 8 loops, both products on the FP64 tensor cores
+            const int rc = closed_loop_dmma_try(set, plant, B, ctrl_idx, x0, u_past0, y_past0, u_s, y_s, w, noise_seed,
+                                                scenario_id0, noise_eps, n_steps, u_sys, y_sys, status, iters, x_final, st);
+            if (rc != -1) return rc;
+        }
+        {   // large systems: the batch as the N dimension of FP64 tensor-core GEMMs
+            const int rc = closed_loop_gemm_try(set, plant, B, ctrl_idx, x0, u_past0, y_past0, u_s, y_s, w, noise_seed,
+                                                scenario_id0, noise_eps, n_steps, u_sys, y_sys, status, iters, x_final, st);
+            if (rc != -1) return rc;
+        }
     }
     // plant matrices -> device (small; one staging buffer)
     const size_t nA = (size_t)nxp * nxp, nB = (size_t)nxp * d.m, nC = (size_t)d.p * nxp, nD = (size_t)d.p * d.m;

@@ -211,6 +211,36 @@ int ddmpc_generate_example_data(const ddmpc_plant *plant, const double *pinv_Ot,
 int ddmpc_pcg64_uniform(uint64_t *rng_state, int S, int count, double lo, double hi, double scale, double *out,
                         void *stream);
 
+/* Kernel selection of ddmpc_closed_loop_batch.  DDMPC_PATH_AUTO (the default) picks by controller structure, shape and
+ * batch size; the others force one implementation where it applies (else the generic kernel runs) -
+ * the parity tests use this to compare every kernel with every other on the same inputs. */
+enum {
+    DDMPC_PATH_AUTO = 0,
+    DDMPC_PATH_GENERIC = 1,   /* k_closed_loop: thread per loop, any sizes / controller kinds                    */
+    DDMPC_PATH_FAST = 2,      /* k_closed_loop_fast: register-resident hybrid DFMA + DMMA, shared controller      */
+    DDMPC_PATH_WS = 3,        /* k_closed_loop_ws: warp-specialised all-tensor-core, four-tank n-step shape       */
+    DDMPC_PATH_PERLOOP = 4,   /* k_closed_loop_perloop: 8 lanes per loop, per-loop controllers / small batches    */
+    DDMPC_PATH_DMMA = 5,      /* k_closed_loop_dmma: config-4 shapes, warp per 8 loops on the FP64 tensor cores   */
+    DDMPC_PATH_GEMM = 6       /* closed_loop_gemm: batch as the N dimension of FP64 tensor-core GEMMs             */
+};
+/* Per-set options: "closed_loop_path" (DDMPC_PATH_*), "dmma_warps" (1, 2 or 4: CTA size of the config-4 kernel),
+ * "loops_per_thread" (0 = automatic, 1, 2: hybrid kernel).  Not thread-safe against running calls on the same set. */
+int ddmpc_set_option(ddmpc_set *set, const char *name, int value);
+
+/* Number of controllers of the set whose setup failed (not persistently exciting / factorisation); their indices
+ * are reported by ddmpc_set_info.  Solves and closed loops that use such a controller return status
+ * DDMPC_SOLVE_NONFINITE and NaN outputs. */
+int ddmpc_set_failed_count(const ddmpc_set *set);
+
+/* ---- Roofline denominators, measured on the current device (csrc/probes.cu; bench.py calls them in the run whose
+ * fractions it reports).  Both synchronise.
+ *   ddmpc_probe_fp64_tflops: sustained FP64 TFLOP/s of the chip issued as DFMA (use_dmma = 0) or as DMMA m8n8k4.
+ *   ddmpc_probe_store_ms:    best-of-5 time to write u (B, n_steps, 2) and y (B, n_steps, 2) (device buffers, 32-byte
+ *                            aligned) with no compute, in the closed-loop kernels' own pattern (coalesced = 0: a thread
+ *                            owns a loop and writes one 32-byte sector at a time) or fully coalesced (= 1). */
+int ddmpc_probe_fp64_tflops(int use_dmma, double *tflops, void *stream);
+int ddmpc_probe_store_ms(int B, int n_steps, int coalesced, double *u, double *y, double *ms, void *stream);
+
 /* Number of kernels this library has launched since load (bench bookkeeping). */
 uint64_t ddmpc_kernel_launches(void);
 

@@ -2,35 +2,57 @@
 
     python scripts/time_variants.py [--loops 65536] [--reps 30]
 
-Each variant is selected with the environment switches DESIGN.md section 6a lists; the library reads them at every call.
-Prints the median launch time (CUDA events around 10 graph replays, output buffers larger than L2) and, for the
-variants that support it, the time without the trajectory stores (DDMPC_DEBUG_NOSTORE=1: compute only).
+The product kernels are selected with ControllerSet.set_option("closed_loop_path", ...); the measured-and-dropped
+designs live in experiments/closed_loop_variants.cu, which this script builds into experiments/libddmpc_experiments.so
+(nvcc, sm_100a) and calls through ddmpc_exp_closed_loop().  Prints the median launch time (CUDA events around 10 graph
+replays, output buffers larger than L2) and, where supported, the time without the trajectory stores (compute only).
 """
 from __future__ import annotations
 
 import argparse
+import ctypes as C
 import os
+import subprocess
 import sys
 
 import numpy as np
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
 
+# (name, product path or None, experiment variant or None, nostore)
 VARIANTS = [
-    ("ws (default)", {}),
-    ("ws, no stores", {"DDMPC_DEBUG_NOSTORE": "1"}),
-    ("ws, 4 math warps", {"DDMPC_WS_MATH_WARPS": "4"}),
-    ("ws, 4 math warps, no stores", {"DDMPC_WS_MATH_WARPS": "4", "DDMPC_DEBUG_NOSTORE": "1"}),
-    ("ws, math warps draw", {"DDMPC_WS_MATH_DRAWS": "1"}),
-    ("ws, math warps draw, no stores", {"DDMPC_WS_MATH_DRAWS": "1", "DDMPC_DEBUG_NOSTORE": "1"}),
-    ("rws (DDMPC_REG=2)", {"DDMPC_REG": "2"}),
-    ("rws, no stores", {"DDMPC_REG": "2", "DDMPC_DEBUG_NOSTORE": "1"}),
-    ("regx (DDMPC_REG=3)", {"DDMPC_REG": "3"}),
-    ("regx, no stores", {"DDMPC_REG": "3", "DDMPC_DEBUG_NOSTORE": "1"}),
-    ("reg NT=4 (DDMPC_REG=1)", {"DDMPC_REG": "1"}),
-    ("hybrid (DDMPC_WS=0)", {"DDMPC_WS": "0"}),
+    ("ws (default)", "ws", None, 0),
+    ("ws, no stores", None, "ws2", 1),
+    ("ws, 4 math warps", None, "ws4", 0),
+    ("ws, 1 math warp", None, "ws1", 0),
+    ("ws, math warps draw", None, "ws2md", 0),
+    ("rws", None, "rws", 0),
+    ("rws, no stores", None, "rws", 1),
+    ("regx", None, "regx", 0),
+    ("reg NT=4", None, "reg", 0),
+    ("reg NT=4, no stores", None, "reg", 1),
+    ("single-warp mma", None, "mma", 0),
+    ("hybrid", "fast", None, 0),
+    ("8 lanes per loop", "perloop", None, 0),
 ]
-SWITCHES = ("DDMPC_WS", "DDMPC_WS_MATH_WARPS", "DDMPC_WS_MATH_DRAWS", "DDMPC_REG", "DDMPC_REG_NT", "DDMPC_DEBUG_NOSTORE", "DDMPC_PLANT_MMA")
+
+
+def build_experiments() -> C.CDLL:
+    from direct_data_driven_mpc_b200 import _lib
+    src = os.path.join(ROOT, "experiments", "closed_loop_variants.cu")
+    out = os.path.join(ROOT, "experiments", "libddmpc_experiments.so")
+    csrc = os.path.dirname(_lib.LIB_PATH)
+    if not os.path.exists(out) or os.path.getmtime(out) < os.path.getmtime(src):
+        subprocess.run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler",
+                        "-fPIC", "-shared", "-o", out, src, "-L" + csrc, "-lddmpc"], check=True)
+    C.CDLL(_lib.LIB_PATH, mode=C.RTLD_GLOBAL)
+    lib = C.CDLL(out)
+    vp, i32, f64, u64 = C.c_void_p, C.c_int, C.c_double, C.c_uint64
+    lib.ddmpc_exp_closed_loop.restype = i32
+    lib.ddmpc_exp_closed_loop.argtypes = [vp, C.POINTER(_lib.Plant), C.c_char_p, i32, i32, vp, vp, vp, vp, vp, vp, u64, u64,
+                                          f64, i32, vp, vp, vp, vp, vp, vp]
+    return lib
 
 
 def main() -> None:
@@ -55,17 +77,28 @@ def main() -> None:
     u_sys = torch.empty(B, n_steps, 2, dtype=torch.float64, device=dev)
     y_sys = torch.empty(B, n_steps, 2, dtype=torch.float64, device=dev)
 
-    def step():
-        return cs.closed_loop(plant, x0, up0, yp0, us, ys, n_steps, w=None, noise_seed=0, scenario_id0=0,
-                              noise_eps=0.002, out=(u_sys, y_sys))
+    exp = build_experiments()
+    from direct_data_driven_mpc_b200 import _lib
+    ps = plant.c_struct()
+    status = torch.empty(B, dtype=torch.int32, device=dev)
+    iters = torch.empty(B, dtype=torch.int32, device=dev)
 
     ref = None
-    for name, env in VARIANTS:
+    for name, path, variant, nostore in VARIANTS:
         if args.only and args.only not in name:
             continue
-        for k in SWITCHES:
-            os.environ.pop(k, None)
-        os.environ.update(env)
+        if path is not None:
+            cs.set_option("closed_loop_path", path)
+
+            def step():
+                return cs.closed_loop(plant, x0, up0, yp0, us, ys, n_steps, w=None, noise_seed=0, scenario_id0=0,
+                                      noise_eps=0.002, out=(u_sys, y_sys))
+        else:
+            def step(variant=variant, nostore=nostore):
+                _lib.check(exp.ddmpc_exp_closed_loop(cs._h, C.byref(ps), variant.encode(), nostore, B, x0.data_ptr(),
+                                                     up0.data_ptr(), yp0.data_ptr(), us.data_ptr(), ys.data_ptr(), None, 0, 0,
+                                                     0.002, n_steps, u_sys.data_ptr(), y_sys.data_ptr(), status.data_ptr(),
+                                                     iters.data_ptr(), None, torch.cuda.current_stream().cuda_stream))
         for _ in range(3):
             step()
         torch.cuda.synchronize()
@@ -91,7 +124,7 @@ def main() -> None:
             e1.synchronize()
             ts.append(e0.elapsed_time(e1) / 10)
         line = f"{name:28s} median {np.median(ts):.4f} ms  min {np.min(ts):.4f} ms"
-        if "DDMPC_DEBUG_NOSTORE" not in env:
+        if not nostore:
             cur = (u_sys.clone(), y_sys.clone())
             if ref is None:
                 ref = cur
@@ -100,8 +133,6 @@ def main() -> None:
                 dy = float((cur[1] - ref[1]).abs().max() / ref[1].abs().max())
                 line += f"  max rel diff vs first variant: u {du:.2e} y {dy:.2e}"
         print(line, flush=True)
-    for k in SWITCHES:
-        os.environ.pop(k, None)
 
 
 if __name__ == "__main__":

@@ -266,10 +266,10 @@ def fixture_errors():
 def fixture_config4(n_steps=3):
     """BASELINE config 4 (synthetic n = 20, m = p = 4, N = 2000, L = 40): the reference class on the large problem
     (2661 variables, 800 equalities), three closed-loop steps of the 1-step scheme and one 20-step block."""
-    from direct_data_driven_mpc_b200 import scenarios as S
+    from oracle import workloads as W     # NumPy recipe of the config-4 data (the product package is not imported here)
     out = {}
     for nmpc, steps in ((1, n_steps), (20, 20)):
-        sc = S.config4_batch(1, n_mpc_step=nmpc)
+        sc = W.config4(n_mpc_step=nmpc)
         prm, pl = sc["params"], sc["plant"]
         ctrl = DirectDataDrivenMPCController(
             n=20, m=4, p=4, u_d=sc["u_d"], y_d=sc["y_d"], L=40, Q=prm["Q"], R=prm["R"], u_s=prm["u_s"], y_s=prm["y_s"],
@@ -277,7 +277,7 @@ def fixture_config4(n_steps=3):
             slack_var_constraint_type=SlackVarConstraintTypes.NONE, controller_type=DataDrivenMPCType.ROBUST,
             n_mpc_step=nmpc, use_terminal_constraint=True)
         r = np.random.default_rng(3)
-        x0 = sc["x0"][0] + 0.1 * r.normal(size=20)
+        x0 = sc["x_end"] + 0.1 * r.normal(size=20)
         w = pl.eps_max * r.uniform(-1, 1, (steps, 4))
         plant = O.Plant(pl.A, pl.B, pl.C, pl.D, pl.eps_max); plant.x = x0.copy()
         rec = Recorder(ctrl)

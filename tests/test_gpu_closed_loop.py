@@ -247,7 +247,7 @@ def test_config3_full_size_properties():
 
 
 @pytest.mark.parametrize("n_mpc,n_steps", [(20, 47), (8, 20), (10, 10)])
-def test_config4_gemm_path_vs_generic_and_oracle(n_mpc, n_steps, monkeypatch):
+def test_config4_gemm_path_vs_generic_and_oracle(n_mpc, n_steps):
     """Large-system path (batch as the N dimension of DMMA GEMMs, block-stepped plant) vs the generic
     thread-per-loop kernel on 512 loops, and vs the oracle on a sample; Philox and uploaded noise."""
     from direct_data_driven_mpc_b200 import ControllerSet, scenarios as S
@@ -263,13 +263,15 @@ def test_config4_gemm_path_vs_generic_and_oracle(n_mpc, n_steps, monkeypatch):
     w = pl.eps_max * r.uniform(-1, 1, (B, n_steps, 4))
     for noise in ("philox", "uploaded"):
         kw = dict(w=w) if noise == "uploaded" else dict(noise_seed=5, scenario_id0=1000, noise_eps=0.002)
-        monkeypatch.delenv("DDMPC_FORCE_GENERIC", raising=False)
+        cs.set_option("closed_loop_path", "gemm")
+        launches0 = _launches()
         u1, y1, s1, i1, xf1 = cs.closed_loop(pl, x0, sc["u_past0"], sc["y_past0"], u_s, y_s, n_steps,
                                              want_x_final=True, **kw)
-        monkeypatch.setenv("DDMPC_FORCE_GENERIC", "1")
+        assert _launches() - launches0 > 3                         # the per-iteration GEMMs, not a fused kernel
+        cs.set_option("closed_loop_path", "generic")
         u2, y2, s2, i2, xf2 = cs.closed_loop(pl, x0, sc["u_past0"], sc["y_past0"], u_s, y_s, n_steps,
                                              want_x_final=True, **kw)
-        monkeypatch.delenv("DDMPC_FORCE_GENERIC", raising=False)
+        cs.set_option("closed_loop_path", "auto")
         assert int(s1.max()) == 0 and int(s2.max()) == 0
         assert (i1 == i2).all()
         assert _rel(u1.cpu().numpy(), u2.cpu().numpy()) < 1e-9 and _rel(y1.cpu().numpy(), y2.cpu().numpy()) < 1e-9
@@ -288,7 +290,7 @@ def test_config4_gemm_path_vs_generic_and_oracle(n_mpc, n_steps, monkeypatch):
 
 
 @pytest.mark.parametrize("n_mpc,n_steps,B", [(1, 23, 515), (20, 47, 515), (20, 401, 264)])
-def test_config4_fused_dmma_kernel_vs_generic_and_oracle(n_mpc, n_steps, B, monkeypatch):
+def test_config4_fused_dmma_kernel_vs_generic_and_oracle(n_mpc, n_steps, B):
     """k_closed_loop_dmma (one launch, a warp per 8 loops, ring window in shared memory) vs the generic
     thread-per-loop kernel on a ragged batch, and vs the oracle on a sample; Philox and uploaded noise."""
     from direct_data_driven_mpc_b200 import ControllerSet, scenarios as S
@@ -307,10 +309,10 @@ def test_config4_fused_dmma_kernel_vs_generic_and_oracle(n_mpc, n_steps, B, monk
         u1, y1, s1, i1, xf1 = cs.closed_loop(pl, x0, sc["u_past0"], sc["y_past0"], u_s, y_s, n_steps,
                                              want_x_final=True, **kw)
         assert _launches() - launches0 == 1                        # the fused kernel, not the per-iteration GEMMs
-        monkeypatch.setenv("DDMPC_FORCE_GENERIC", "1")
+        cs.set_option("closed_loop_path", "generic")
         u2, y2, s2, i2, xf2 = cs.closed_loop(pl, x0, sc["u_past0"], sc["y_past0"], u_s, y_s, n_steps,
                                              want_x_final=True, **kw)
-        monkeypatch.delenv("DDMPC_FORCE_GENERIC", raising=False)
+        cs.set_option("closed_loop_path", "auto")
         assert int(s1.max()) == 0 and int(s2.max()) == 0
         assert (i1 == i2).all()
         assert _rel(u1.cpu().numpy(), u2.cpu().numpy()) < 1e-9 and _rel(y1.cpu().numpy(), y2.cpu().numpy()) < 1e-9
@@ -329,7 +331,7 @@ def test_config4_fused_dmma_kernel_vs_generic_and_oracle(n_mpc, n_steps, B, monk
 
 
 @pytest.mark.parametrize("c", [1.0, 0.3])
-def test_convex_fused_path_vs_generic_and_oracle(c, monkeypatch):
+def test_convex_fused_path_vs_generic_and_oracle(c):
     """CONVEX slack bound inside the fused kernel (slack rows on the tensor cores, warp-cooperative ADMM for
     the violating loops) vs the generic thread-per-loop kernel (70 loops: several blocks, dead lanes) and vs
     the oracle's active-set solution on a sample."""
@@ -342,11 +344,10 @@ def test_convex_fused_path_vs_generic_and_oracle(c, monkeypatch):
     ys = us @ _plant().equilibrium_gain().T
     up0, yp0 = np.tile(u_d[-4:].reshape(1, -1), (B, 1)), np.tile(y_d[-4:].reshape(1, -1), (B, 1))
     w = 0.002 * r.uniform(-1, 1, (B, n_steps, 2))
-    monkeypatch.delenv("DDMPC_FORCE_GENERIC", raising=False)
     u1, y1, s1, i1 = cs.closed_loop(_plant(), xs, up0, yp0, us, ys, n_steps, w=w)
-    monkeypatch.setenv("DDMPC_FORCE_GENERIC", "1")
+    cs.set_option("closed_loop_path", "generic")
     u2, y2, s2, i2 = cs.closed_loop(_plant(), xs, up0, yp0, us, ys, n_steps, w=w)
-    monkeypatch.delenv("DDMPC_FORCE_GENERIC", raising=False)
+    cs.set_option("closed_loop_path", "auto")
     assert int(s1.max()) == 0 and int(s2.max()) == 0
     assert int(i1.max()) > 10                                  # the box really binds somewhere
     assert (i1 == i2).all(), (i1 - i2).abs().max()
@@ -365,10 +366,10 @@ def test_convex_fused_path_vs_generic_and_oracle(c, monkeypatch):
     args = (np.tile(u_d[-4:].reshape(1, -1), (Bb, 1)), np.tile(y_d[-4:].reshape(1, -1), (Bb, 1)),
             np.tile(prm["u_s"].T, (Bb, 1)), np.tile(prm["y_s"].T, (Bb, 1)))
     u3, y3, s3, i3 = cs.closed_loop(_plant(), sc_x, *args, 21, noise_seed=9, scenario_id0=5, noise_eps=0.002)
-    monkeypatch.setenv("DDMPC_FORCE_GENERIC", "1")
+    cs.set_option("closed_loop_path", "generic")
     u4, y4, s4, i4 = cs.closed_loop(_plant(), sc_x[:64], *(a[:64] for a in args), 21, noise_seed=9, scenario_id0=5,
                                     noise_eps=0.002)
-    monkeypatch.delenv("DDMPC_FORCE_GENERIC", raising=False)
+    cs.set_option("closed_loop_path", "auto")
     assert _rel(u3[:64].cpu().numpy(), u4.cpu().numpy()) < 1e-8 and (i3[:64] == i4).all()
 
 
@@ -390,11 +391,11 @@ def test_batched_reproduction_matches_reference_semantics(golden_repro):
     assert bool(uc["diverged"][0])                               # UCON diverges by design (reproduction.py:21-28)
 
 
-def test_tensor_core_variants_match_hybrid(monkeypatch):
-    """The warp-specialised kernel (k_closed_loop_ws, the default for large batches), the opt-in register-chained kernel
-    (k_closed_loop_reg, DDMPC_REG=1) and the opt-in single-warp k_closed_loop_mma (all three: plant through the block
-    map on the FP64 MMA pipe) vs the hybrid fused kernel (DDMPC_WS=0), including a partial last block, uploaded noise
-    and a ragged batch."""
+def test_fused_four_tank_kernels_match_each_other():
+    """The warp-specialised kernel (k_closed_loop_ws, the default for large batches: plant through the block map on the
+    FP64 MMA pipe), the 8-lanes-per-loop kernel (k_closed_loop_perloop) and the generic thread-per-loop kernel vs the
+    hybrid fused kernel (k_closed_loop_fast), including a partial last block, uploaded noise and a ragged batch.
+    (The measured-and-dropped variants live in experiments/ and are compared by scripts/time_variants.py.)"""
     plant_o, prm, rng, x0, u_d, y_d = O.example_scenario(0)
     cs, _ = _set(u_d, y_d)
     B = 16384 + 70
@@ -407,28 +408,26 @@ def test_tensor_core_variants_match_hybrid(monkeypatch):
                         (401, dict(noise_seed=0, scenario_id0=0, noise_eps=0.002)),
                         (12, dict(w=0.002 * r.uniform(-1, 1, (B, 12, 2)))),
                         (3, dict(w=0.002 * r.uniform(-1, 1, (B, 3, 2))))):
-        monkeypatch.setenv("DDMPC_WS", "0")
-        monkeypatch.delenv("DDMPC_PLANT_MMA", raising=False)
+        cs.set_option("closed_loop_path", "fast")
         u1, y1, s1, i1, x1 = cs.closed_loop(_plant(), xs, up0, yp0, us, ys, n_steps, want_x_final=True, **kw)
-        for env in (dict(DDMPC_WS="1"), dict(DDMPC_WS_MATH_WARPS="4"), dict(DDMPC_WS_MATH_WARPS="1"), dict(DDMPC_WS_MATH_DRAWS="1"), dict(DDMPC_REG="2"), dict(DDMPC_REG="3"), dict(DDMPC_REG="1"), dict(DDMPC_REG="1", DDMPC_REG_NT="2"), dict(DDMPC_REG="1", DDMPC_REG_NT="8"),
-                    dict(DDMPC_WS="0", DDMPC_PLANT_MMA="1")):     # warp-specialised (default), register-chained NT = 4 / 2 / 8, single-warp MMA
-            for k, v in env.items():
-                monkeypatch.setenv(k, v)
+        for path in ("ws", "auto", "perloop", "generic"):
+            cs.set_option("closed_loop_path", path)
+            launches0 = _launches()
             u2, y2, s2, i2, x2 = cs.closed_loop(_plant(), xs, up0, yp0, us, ys, n_steps, want_x_final=True, **kw)
-            for k in ("DDMPC_PLANT_MMA", "DDMPC_WS", "DDMPC_WS_MATH_WARPS", "DDMPC_WS_MATH_DRAWS", "DDMPC_REG", "DDMPC_REG_NT"):
-                monkeypatch.delenv(k, raising=False)
-            assert int(s2.max()) == 0 and (i1 == i2).all(), env
-            assert _rel(u2.cpu().numpy(), u1.cpu().numpy()) < 1e-9 and _rel(y2.cpu().numpy(), y1.cpu().numpy()) < 1e-9, env
-            assert _rel(x2.cpu().numpy(), x1.cpu().numpy()) < 1e-9, env
+            assert _launches() - launches0 == 1, path
+            assert int(s2.max()) == 0 and (i1 == i2).all(), path
+            assert _rel(u2.cpu().numpy(), u1.cpu().numpy()) < 1e-9 and _rel(y2.cpu().numpy(), y1.cpu().numpy()) < 1e-9, path
+            assert _rel(x2.cpu().numpy(), x1.cpu().numpy()) < 1e-9, path
+        cs.set_option("closed_loop_path", "auto")
 
 
-@pytest.mark.parametrize("reg", ["0", "1", "2", "3"])
-def test_warp_specialised_kernel_vs_oracle(reg, monkeypatch):
-    """Large-batch paths (k_closed_loop_ws by default, k_closed_loop_reg with DDMPC_REG=1) against the literal-KKT
-    oracle on whole 401-step loops."""
-    monkeypatch.setenv("DDMPC_REG", reg)
+@pytest.mark.parametrize("path", ["auto", "perloop", "fast"])
+def test_warp_specialised_kernel_vs_oracle(path):
+    """Large-batch paths (k_closed_loop_ws by default; the 8-lanes-per-loop and hybrid kernels when forced) against the
+    literal-KKT oracle on whole 401-step loops."""
     plant_o, prm, rng, x0, u_d, y_d = O.example_scenario(0)
     cs, _ = _set(u_d, y_d)
+    cs.set_option("closed_loop_path", path)
     B, n_steps = 16384 + 3, 401
     r = np.random.default_rng(8)
     xs = np.tile(plant_o.x, (B, 1)) + 0.05 * r.normal(size=(B, 4))
@@ -612,16 +611,16 @@ def test_set_lifecycle_returns_device_memory():
     assert free0 - free1 < 32 * 2**20, (free0, free1)
 
 
-def test_nonfinite_inputs_flag_only_their_own_loops(monkeypatch):
+def test_nonfinite_inputs_flag_only_their_own_loops():
     """Status DDMPC_SOLVE_NONFINITE (3) for exactly the loops that were given a NaN / Inf initial state, set-point or
-    window, on every closed-loop kernel: generic, hybrid, warp-specialised and the register-chained variants (four-tank),
-    the fused FP64 tensor-core kernel and the generic one (config 4)."""
+    window, on every closed-loop kernel: generic, 8-lanes-per-loop, hybrid and warp-specialised (four-tank), the fused
+    FP64 tensor-core kernel and the generic one (config 4)."""
     from direct_data_driven_mpc_b200 import ControllerSet, scenarios as S
     plant_o, prm, rng, x0, u_d, y_d = O.example_scenario(0)
     cs, _ = _set(u_d, y_d)
     bad = {5: "x0", 77: "u_s", 4100: "y_past", 16390: "x0"}
-    for B, envs in ((300, (dict(DDMPC_FORCE_GENERIC="1"), dict())),
-                    (16384 + 9, (dict(), dict(DDMPC_WS="0"), dict(DDMPC_REG="1"), dict(DDMPC_REG="2"), dict(DDMPC_REG="3")))):
+    for B, envs in ((300, ("generic", "auto", "fast", "perloop")),
+                    (16384 + 9, ("auto", "fast", "perloop"))):
         xs = np.tile(plant_o.x, (B, 1))
         us, ys = np.tile(prm["u_s"].T, (B, 1)), np.tile(prm["y_s"].T, (B, 1))
         up0, yp0 = np.tile(u_d[-4:].reshape(1, -1), (B, 1)), np.tile(y_d[-4:].reshape(1, -1), (B, 1))
@@ -637,11 +636,9 @@ def test_nonfinite_inputs_flag_only_their_own_loops(monkeypatch):
             else:
                 yp0[b, 3] = np.nan
         for env in envs:
-            for k, v in env.items():
-                monkeypatch.setenv(k, v)
+            cs.set_option("closed_loop_path", env)
             u, y, st, it = cs.closed_loop(_plant(), xs, up0, yp0, us, ys, 41, noise_seed=2, noise_eps=0.002)
-            for k in env:
-                monkeypatch.delenv(k, raising=False)
+            cs.set_option("closed_loop_path", "auto")
             assert np.array_equal(st.cpu().numpy(), expect), (B, env, np.nonzero(st.cpu().numpy() != expect)[0][:8])
             good = expect == 0
             assert np.isfinite(u.cpu().numpy()[good]).all() and np.isfinite(y.cpu().numpy()[good]).all()
@@ -657,18 +654,15 @@ def test_nonfinite_inputs_flag_only_their_own_loops(monkeypatch):
         us[258, 1] = -np.inf
         up0[519, 11] = np.nan
         expect[[3, 258, 519]] = 3
-        for env in (dict(), dict(DDMPC_FORCE_GENERIC="1")):
-            for k, v in env.items():
-                monkeypatch.setenv(k, v)
+        for env in ("auto", "generic"):
+            c4.set_option("closed_loop_path", env)
             u, y, st, it = c4.closed_loop(pl, xs, up0, sc["y_past0"], us, sc["y_s"], 45, noise_seed=2, noise_eps=0.002)
-            for k in env:
-                monkeypatch.delenv(k, raising=False)
             assert np.array_equal(st.cpu().numpy(), expect), (n_mpc, env, np.nonzero(st.cpu().numpy() != expect)[0][:8])
 
 
 @pytest.mark.parametrize("n_mpc", [1, 20])
-def test_dmma_kernel_cta_sizes_agree_bitwise(n_mpc, monkeypatch):
-    """k_closed_loop_dmma with CTAs of 1 (default), 2 and 4 warps (DDMPC_DMMA_WARPS): the warps are independent, so the
+def test_dmma_kernel_cta_sizes_agree_bitwise(n_mpc):
+    """k_closed_loop_dmma with CTAs of 1 (default), 2 and 4 warps (set option "dmma_warps"): the warps are independent, so the
     results must be identical bit for bit, ragged batch included."""
     from direct_data_driven_mpc_b200 import ControllerSet, scenarios as S
     B, n_steps = 8 * 67 + 3, 45
@@ -677,12 +671,11 @@ def test_dmma_kernel_cta_sizes_agree_bitwise(n_mpc, monkeypatch):
     cs = ControllerSet(prm["n"], 4, 4, sc["u_d"], sc["y_d"], prm["L"], prm["Q"], prm["R"], prm["eps_max"],
                        prm["lamb_alpha"], prm["lamb_sigma"], prm["c"], 0, 1, n_mpc, True)
     outs = []
-    for w in ("1", "2", "4"):
-        monkeypatch.setenv("DDMPC_DMMA_WARPS", w)
+    for w in (1, 2, 4):
+        cs.set_option("dmma_warps", w)
         u, y, st, it, xf = cs.closed_loop(pl, sc["x0"], sc["u_past0"], sc["y_past0"], sc["u_s"], sc["y_s"], n_steps,
                                           want_x_final=True, noise_seed=9, scenario_id0=77, noise_eps=0.002)
         assert int(st.max()) == 0
         outs.append((u.cpu().numpy(), y.cpu().numpy(), xf.cpu().numpy()))
-    monkeypatch.delenv("DDMPC_DMMA_WARPS", raising=False)
     for o in outs[1:]:
         assert all(np.array_equal(a, b) for a, b in zip(o, outs[0]))

@@ -60,3 +60,24 @@ def test_hankel_window_error_is_raised_on_host():
     from direct_data_driven_mpc_b200 import hankel_matrix
     with pytest.raises(ValueError, match="N must be greater than or equal to L"):
         hankel_matrix(np.zeros((3, 2)), 4)
+
+
+def test_workload_recipes_agree():
+    """oracle/workloads.py (lib-free NumPy recipes used by bench.py's CPU arm and the fixture generators) and the
+    product-side direct_data_driven_mpc_b200/scenarios.py produce identical arrays for configs 3 and 4."""
+    import numpy as np
+    from oracle import workloads as W
+    from direct_data_driven_mpc_b200 import scenarios as S
+    w3, s3 = W.config3(0), S.config3_batch(512, seed=0)
+    assert np.array_equal(w3["u_d"], s3["u_d"]) and np.array_equal(w3["y_d"], s3["y_d"])
+    assert np.array_equal(w3["x_start"], s3["x0"][0])
+    assert np.array_equal(w3["u_s"], s3["u_s"][:256]) and np.array_equal(w3["y_s"], s3["y_s"][:256])
+    assert np.array_equal(s3["u_s"][256:512], s3["u_s"][:256])
+    for nmpc in (1, 20):
+        w4, s4 = W.config4(n_mpc_step=nmpc), S.config4_batch(2, n_mpc_step=nmpc)
+        for k in ("u_d", "y_d"):
+            assert np.array_equal(w4[k], s4[k])
+        assert np.array_equal(w4["x_end"], s4["x0"][0]) and np.array_equal(w4["y_s"], s4["y_s"][0])
+        for k in "ABCD":
+            assert np.array_equal(getattr(w4["plant"], k), getattr(s4["plant"], k))
+        assert w4["params"]["n_mpc_step"] == nmpc and np.array_equal(w4["params"]["Q"], s4["params"]["Q"])
