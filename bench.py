@@ -3,12 +3,15 @@
 
 Workload (BASELINE config 3): four-tank robust n-step DD-MPC
 (n_mpc_step = 4, terminal constraint on, slack NONE), shared data (seed 0),
-65,536 closed loops per GPU (256 set-points x 256 noise realisations),
-n_steps = 401 -> 101 QP solves per loop, 6.62 M solves per step per GPU.
-One "step" = one fused closed-loop pass over the whole batch.
+closed loops = 256 set-points x noise realisations, n_steps = 401 -> 101 QP
+solves per loop.  One "step" = one fused closed-loop pass over the whole batch.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-  torchrun ... bench.py --gpus N ...      (one rank per GPU, weak scaling)
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--scaling weak|strong]
+  torchrun ... bench.py --gpus N ...      (one rank per GPU)
+
+--scaling weak  (default): 65,536 loops PER GPU (6.62 M solves per step per GPU).
+--scaling strong: BASELINE config 3 as written, 65,536 loops IN TOTAL, cut into N contiguous shards.
+A weak-scaling run on N > 1 GPUs also measures the strong-scaling configuration and reports it under "strong".
 
 Prints ONE JSON line on rank 0 (see the task contract for the keys).
 """
@@ -17,7 +20,6 @@ from __future__ import annotations
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -32,6 +34,7 @@ METRIC = "batched DD-MPC QP solves/sec"
 UNIT = "solves/s"
 N_STEPS = 401
 SOLVES_PER_LOOP = 101          # ceil(401 / 4)
+CONFIG3_LOOPS = 65536
 
 
 def parse_args():
@@ -40,16 +43,24 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--loops", type=int, default=65536, help="closed loops per GPU")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--loops", type=int, default=CONFIG3_LOOPS,
+                    help="closed loops per GPU (weak scaling) or in total (strong scaling)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the config 2 / 4 / 5 / CONVEX measurements")
     ap.add_argument("--no-graph", action="store_true", help="time direct launches instead of CUDA-graph replays")
     ap.add_argument("--e2e-steps", type=int, default=10)
     return ap.parse_args()
 
 
+WORKLOAD_TEXT = ("config 3: four-tank robust n-step DD-MPC (n_mpc_step=4, terminal on, slack NONE), shared data seed 0, "
+                 "256 set-points x noise realisations, n_steps=401 (101 QP solves per loop)")
+
+
 # --------------------------------------------------------------------------
-# CPU baseline (oracle port; the only place outside tests that runs oracle/)
+# CPU arm (oracle port; the only place outside tests that runs oracle/).  It imports NOTHING from the product package:
+# no libddmpc.so is mapped into these processes.
 # --------------------------------------------------------------------------
 def _cpu_worker(args):
     """One process = one host core: closed loops of the bench workload with the oracle."""
@@ -60,10 +71,9 @@ def _cpu_worker(args):
     except Exception:
         pass
     from oracle import ddmpc_oracle as O
-    from direct_data_driven_mpc_b200 import scenarios as S
-    prm = S.four_tank_controller_params()
-    rng, x0, u_d, y_d, x_end = S.example_data(0)
-    us_g, ys_g = S.setpoint_grid(S.four_tank_plant(), 16, first=(prm["u_s"], prm["y_s"]))
+    from oracle import workloads as W
+    sc = W.config3(0)
+    prm, u_d, y_d = sc["params"], sc["u_d"], sc["y_d"]
     cache = flavour == "cached_factor"
     ctrl = O.OracleController(4, 2, 2, u_d, y_d, 30, prm["Q"], prm["R"], prm["u_s"], prm["y_s"], prm["eps_max"],
                               prm["lamb_alpha"], prm["lamb_sigma"], prm["c"], O.SLACK_NONE, O.ROBUST, 4, True,
@@ -74,8 +84,8 @@ def _cpu_worker(args):
     b = wid
     n_steps = N_STEPS if cache else 21
     while time.perf_counter() - t0 < budget_s:
-        plant.x = x_end.copy()
-        ctrl.u_s, ctrl.y_s = us_g[b % 256].reshape(-1, 1), ys_g[b % 256].reshape(-1, 1)
+        plant.x = sc["x_start"].copy()
+        ctrl.u_s, ctrl.y_s = sc["u_s"][b % 256].reshape(-1, 1), sc["y_s"][b % 256].reshape(-1, 1)
         ctrl.set_past_input_output_data(u_d[-4:].reshape(-1, 1), y_d[-4:].reshape(-1, 1))
         w = O.philox_noise(0, np.array([b]), n_steps, 2, 0.002)[0]
         O.closed_loop(plant, ctrl, n_steps, w)
@@ -159,9 +169,13 @@ def run_reference(args, rank, world):
     cb["sample"] += f"; {n_eff} such samples executed for --steps {args.steps}"
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args.loops, world),
+        "config": {"workload": WORKLOAD_TEXT, "n_steps": N_STEPS,
+                   "noise": "Philox4x32-10, seed 0, stream = scenario id (oracle/ddmpc_oracle.py philox_noise)",
+                   "execution": f"oracle port on {cb['cores']} host cores, one process per core (rank 0 only; no GPU work): "
+                                "every process runs whole closed loops of the workload back to back for the sample time",
+                   "step": f"one step = a {per_step:.0f} s time sample"},
         "cpu_baseline": cb,
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -171,15 +185,21 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(loops, world):
-    return {"workload": "config 3: four-tank robust n-step DD-MPC (n_mpc_step=4, terminal on, slack NONE), shared "
-                        "data seed 0, 256 set-points x noise realisations, n_steps=401 (101 QP solves per loop)",
+def workload_config(loops, world, scaling, kernel):
+    return {"workload": WORKLOAD_TEXT,
             "loops_per_gpu": loops, "global_loops": loops * world, "n_steps": N_STEPS,
             "noise": "device Philox4x32-10, seed 0, stream = global scenario id",
-            "l2": "each step writes 841 MB of trajectories per GPU (> 126 MB L2); no flush needed",
-            "parallelism": f"scenario-sharded x{world}, no data-path collective; one NCCL all_gather of per-loop "
-                           "metrics after the timed steps",
-            "launch": "each step is one k_closed_loop_ws launch (warp-specialised all-tensor-core kernel) replayed from a CUDA graph"}
+            "l2": f"each step writes {loops * N_STEPS * 32 / 1e6:.0f} MB of trajectories per GPU"
+                  + (" (> 126 MB L2); no flush needed" if loops * N_STEPS * 32 > 126e6 else
+                     " (< 126 MB L2: the outputs of consecutive steps overwrite each other in L2)"),
+            "parallelism": f"scenario-sharded x{world} ({scaling} scaling), no data-path collective; one NCCL all_gather of "
+                           "per-loop metrics inside the timed region, the full-trajectory gather timed separately (gather)",
+            "launch": f"each step is one {kernel} launch replayed from a CUDA graph"}
+
+
+def kernel_for(loops: int) -> str:
+    """Name of the kernel ddmpc_closed_loop_batch selects for this batch of the bench workload."""
+    return "k_closed_loop_ws" if loops >= 16384 else "k_closed_loop_perloop"
 
 
 # --------------------------------------------------------------------------
@@ -262,7 +282,43 @@ def bind_to_gpu_numa_node(dev_index: int):
         return f"not bound ({type(exc).__name__})"
 
 
-def measure_e2e(args, cs, sc, plant, id0, solves_per_step, world, barrier, dev, u_sys):
+def graph_of(step, enable=True):
+    """Capture `step` (warmed on a side stream first) in a CUDA graph; returns (callable, launches per step, graph)."""
+    import torch
+    from direct_data_driven_mpc_b200 import _lib
+    if not enable:
+        return step, None, None
+    try:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            step()
+        torch.cuda.current_stream().wait_stream(side)
+        l0 = _lib.kernel_launches()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            step()
+        return graph.replay, _lib.kernel_launches() - l0, graph
+    except Exception as exc:  # pragma: no cover
+        print(f"CUDA graph capture failed ({exc}); timing direct launches", file=sys.stderr)
+        return step, None, None
+
+
+def median_ms(run, reps=30, warm=3):
+    """Median device time of one call of `run` (CUDA events around each call, on the current stream)."""
+    import torch
+    for _ in range(warm):
+        run()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    for a, b in ev:
+        a.record()
+        run()
+        b.record()
+    torch.cuda.synchronize()
+    return float(np.median([a.elapsed_time(b) for a, b in ev]))
+
+
+def measure_e2e(args, cs, sc, plant, id0, solves_per_step, world, barrier, dev, u_sys, y_sys):
     """`e2e`: the same metric through the host-buffer API (ControllerSet.closed_loop_host): every step copies its
     inputs from pinned host memory and brings the full trajectories back to pinned host memory."""
     import torch
@@ -295,17 +351,67 @@ def measure_e2e(args, cs, sc, plant, id0, solves_per_step, world, barrier, dev, 
     assert int(hst.max()) == 0
     # (chunks of the host path may take a different kernel specialisation: same maths, different FP64 summation order)
     assert torch.allclose(hu[:64], u_sys[:64].cpu(), rtol=1e-9, atol=1e-9), "host-API result differs from the device-resident run"
+    # the floor of this number: the raw device->host copy of the trajectories alone (every rank at the same time)
+    barrier()
+    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    hu.copy_(u_sys, non_blocking=True)
+    torch.cuda.synchronize()
+    barrier()
+    r0.record()
+    for _ in range(3):
+        hu.copy_(u_sys, non_blocking=True)
+        hy.copy_(y_sys, non_blocking=True)
+    r1.record()
+    barrier()
+    rms = torch.tensor([r0.elapsed_time(r1) / 3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(rms, op=dist.ReduceOp.MAX)
     h2d = sum(t.numel() * t.element_size() for t in (hx0, hup, hyp, hus, hys))
     d2h = hu.numel() * 8 + hy.numel() * 8 + B * 4
     os.sched_setaffinity(0, old_affinity)      # the CPU baseline must see every core again
     return {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-           "ms_per_step": float(ems.item()) / args.e2e_steps,
-           "api": "ControllerSet.closed_loop_host (pinned host in, full trajectories out, 4 chunks on 2 persistent streams)",
-           "numa": numa}
+            "ms_per_step": float(ems.item()) / args.e2e_steps,
+            "raw_d2h_ms": float(rms.item()),
+            "raw_d2h_note": "cudaMemcpyAsync of the same trajectory bytes into the same pinned buffers, nothing else, all "
+                            "ranks concurrently, max over ranks: the floor of ms_per_step on this box",
+            "api": "ControllerSet.closed_loop_host (pinned host in, full trajectories out, 4 chunks on 2 persistent streams)",
+            "numa": numa}
 
 
+def measure_gather(u_sys, y_sys, world, dev, barrier, reps=3):
+    """K6: the one collective of a job - all ranks receive the full trajectories (NCCL all_gather over NVLink)."""
+    import torch
+    import torch.distributed as dist
+    from direct_data_driven_mpc_b200.sharding import gather_shards
+    nbytes = (u_sys.numel() + y_sys.numel()) * 8
+    if world == 1:
+        return {"gather_ms": 0.0, "bytes_received_per_rank": 0, "note": "single GPU: nothing to gather"}
+    total = u_sys.shape[0] * world
+    gu = gather_shards(u_sys, total)           # warm-up: communicator buffers, allocator
+    gy = gather_shards(y_sys, total)
+    ok = bool(torch.equal(gu[dist.get_rank() * u_sys.shape[0]:(dist.get_rank() + 1) * u_sys.shape[0]], u_sys))
+    del gu, gy
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        gu = gather_shards(u_sys, total)
+        gy = gather_shards(y_sys, total)
+        del gu, gy
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device=dev)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    g_ms = float(ms.item())
+    recv = nbytes * (world - 1)
+    return {"gather_ms": g_ms, "bytes_received_per_rank": recv, "bytes_per_rank_shard": nbytes,
+            "achieved_gbs_per_gpu": recv / (g_ms * 1e-3) / 1e9, "nvlink5_peak_gbs_per_direction": 900.0,
+            "frac_of_nvlink": recv / (g_ms * 1e-3) / 1e9 / 900.0, "own_shard_round_trips": ok,
+            "collective": "torch.distributed all_gather_into_tensor (NCCL) of u_sys and y_sys, every rank receives every shard; "
+                          "device time, max over ranks, mean of 3"}
 
-def secondary_config4(dev, B=16384):
+
+def secondary_config4(dev, B=16384, fp64_peak=None, dmma_warps=None):
     """BASELINE config 4 (synthetic n = 20, m = p = 4, N = 2000, L = 40; 16384 closed loops of 401 steps) through the
     fused FP64 tensor-core kernel (dmma_loop.cu), device-resident inputs, CUDA events.  Not the headline: reported next
     to it so the tensor-core-bound configuration has a measured number in the same run."""
@@ -313,7 +419,7 @@ def secondary_config4(dev, B=16384):
     from direct_data_driven_mpc_b200 import ControllerSet
     from direct_data_driven_mpc_b200 import scenarios as S
     out = {"workload": f"config 4: synthetic stable LTI n=20 m=p=4 N=2000 L=40 robust, {B} loops x 401 steps",
-           "fp64_peak_tflops": 37.2, "fp64_peak_source": "scripts/probes/fp64_pipes.cu: 64 FMA/clk/SM x 148 SMs x 1965 MHz"}
+           "fp64_peak_tflops": fp64_peak, "fp64_peak_source": "ddmpc_probe_fp64_tflops (DMMA m8n8k4), measured in this run"}
     for nmpc in (1, 20):
         sc = S.config4_batch(B, n_mpc_step=nmpc)
         prm, pl = sc["params"], sc["plant"]
@@ -323,6 +429,8 @@ def secondary_config4(dev, B=16384):
                            prm["lamb_alpha"], prm["lamb_sigma"], prm["c"], 0, 1, nmpc, True, device=dev)
         torch.cuda.synchronize()
         setup_ms = (time.perf_counter() - t) * 1e3
+        if dmma_warps:
+            cs.set_option("dmma_warps", dmma_warps)
         td = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
         args = (pl, td(sc["x0"]), td(sc["u_past0"]), td(sc["y_past0"]), td(sc["u_s"]), td(sc["y_s"]), N_STEPS)
         bufs = (torch.empty(B, N_STEPS, 4, dtype=torch.float64, device=dev),
@@ -343,10 +451,125 @@ def secondary_config4(dev, B=16384):
         dmma = -(-nmpc * 4 // 8) * (168 // 4) + -(-(nmpc * 4 + 20) // 8) * ((20 + nmpc * 4) // 4)
         flops = 2.0 * 256 * dmma * (B / 8) * (solves / B)
         err = float((bufs[1][:, -1] - args[5]).abs().max())
+        tf = flops / (ms * 1e-3) / 1e12
         out[f"n_mpc_{nmpc}"] = {"loop_ms": ms, "solves_per_s": solves / (ms * 1e-3), "setup_ms": setup_ms,
                                 "status_max": int(st.max().item()), "final_tracking_error_max": err,
-                                "executed_tflops": flops / (ms * 1e-3) / 1e12,
-                                "frac_of_fp64_peak": flops / (ms * 1e-3) / 1e12 / 37.2}
+                                "executed_tflops": tf, "frac_of_fp64_peak": tf / fp64_peak if fp64_peak else None}
+        del cs
+    return out
+
+
+def secondary_config2(dev, B=4096):
+    """BASELINE config 2: 4096 closed loops over seeds, loop b = the example script with --seed b (its own data, hence its
+    own controller), five controller variants; data generated on the device with the reference's NumPy streams.
+    Kernel: k_closed_loop_perloop (equality-only variants) / generic k_closed_loop (CONVEX)."""
+    import torch
+    from direct_data_driven_mpc_b200 import ControllerSet
+    from direct_data_driven_mpc_b200 import scenarios as S
+    pl, prm = S.four_tank_plant(), S.four_tank_controller_params()
+    torch.cuda.synchronize()
+    t = time.perf_counter()
+    ds = S.DeviceScenarios(seeds=range(B), device=dev)
+    w_dev = ds.uniform(N_STEPS * 2, -1.0, 1.0, 0.002).reshape(B, N_STEPS, 2)       # controller_operation.py:263
+    torch.cuda.synchronize()
+    out = {"workload": f"config 2: {B} closed loops over seeds, per-seed data and controllers, 401 steps, parity-mode noise "
+                       "(the seed's own generator)", "data_gen_ms": (time.perf_counter() - t) * 1e3, "variants": {}}
+    ud, yd, x0 = ds.u_d, ds.y_d, ds.x_end
+    td = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    idx = torch.arange(B, device=dev, dtype=torch.int32)
+    for name, slack, term, nmpc, ctype in [("ROBUST TEC n-step", 0, True, 4, 1), ("ROBUST TEC 1-step", 0, True, 1, 1),
+                                           ("ROBUST UCON 1-step", 0, False, 1, 1), ("ROBUST CONVEX n-step", 1, True, 4, 1),
+                                           ("NOMINAL 1-step", 0, True, 1, 0)]:
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        cs = ControllerSet(4, 2, 2, ud, yd, 30, prm["Q"], prm["R"], prm["eps_max"], prm["lamb_alpha"], prm["lamb_sigma"],
+                           1.0, slack, ctype, nmpc, term, device=dev)
+        torch.cuda.synchronize()
+        setup_ms = (time.perf_counter() - t) * 1e3
+        a = (pl, x0, ud[:, -4:].reshape(B, -1).contiguous(), yd[:, -4:].reshape(B, -1).contiguous(),
+             td(np.tile(prm["u_s"].T, (B, 1))), td(np.tile(prm["y_s"].T, (B, 1))), N_STEPS)
+        bufs = (torch.empty(B, N_STEPS, 2, dtype=torch.float64, device=dev), torch.empty(B, N_STEPS, 2, dtype=torch.float64, device=dev))
+        run = lambda: cs.closed_loop(*a, w=w_dev, ctrl_idx=idx, out=bufs, check_idx=False)
+        _, _, st, it = run()
+        ms = median_ms(run, reps=10, warm=2)
+        solves = B * (-(-N_STEPS // nmpc))
+        out["variants"][name] = {"setup_ms": setup_ms, "controllers_per_s": B / (setup_ms * 1e-3), "controllers_failed": cs.n_failed,
+                                 "loop_ms": ms, "qp_solves": solves, "solves_per_s": solves / (ms * 1e-3),
+                                 "admm_iterations_mean": float(it.sum().item()) / solves, "status_max": int(st.max().item())}
+        del cs
+    return out
+
+
+def secondary_config5(dev):
+    """BASELINE config 5: lambda_alpha*eps x lambda_sigma x L sweep on four-tank (16 x 16 weights x 14 horizons = 3584
+    controllers on shared data, 64 closed loops each): controllers set up per second and closed-loop throughput."""
+    import torch
+    from direct_data_driven_mpc_b200 import ControllerSet
+    from direct_data_driven_mpc_b200 import scenarios as S
+    pl, prm = S.four_tank_plant(), S.four_tank_controller_params()
+    rng, x0, u_d, y_d, x_end = S.example_data(0)
+    la = np.logspace(-3, 1, 16) / prm["eps_max"]
+    ls = np.logspace(1, 5, 16)
+    LA, LS = [g.reshape(-1) for g in np.meshgrid(la, ls, indexing="ij")]
+    nl = 64
+    B = LA.size * nl
+    idx = torch.from_numpy(np.repeat(np.arange(LA.size), nl)).to(dev, dtype=torch.int32)
+    td = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    a_common = (td(np.tile(x_end, (B, 1))), td(np.tile(u_d[-4:].reshape(1, -1), (B, 1))), td(np.tile(y_d[-4:].reshape(1, -1), (B, 1))),
+                td(np.tile(prm["u_s"].T, (B, 1))), td(np.tile(prm["y_s"].T, (B, 1))))
+    tot_ctrl, tot_t, tot_solves, tot_loop_ms, failed = 0, 0.0, 0, 0.0, 0
+    for L in range(8, 61, 4):
+        Q, R = 3.0 * np.eye(2 * L), 1e-4 * np.eye(2 * L)
+        mk = lambda: ControllerSet(4, 2, 2, u_d, y_d, L, Q, R, prm["eps_max"], LA, LS, 1.0, 0, 1, 4, True, count=LA.size, device=dev)
+        cs = mk()
+        del cs                                 # warm the stream-ordered memory pool for this size
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        cs = mk()
+        torch.cuda.synchronize()
+        tot_t += time.perf_counter() - t
+        failed += cs.n_failed
+        run = lambda: cs.closed_loop(pl, *a_common, N_STEPS, noise_seed=0, noise_eps=0.002, ctrl_idx=idx, check_idx=False)
+        _, _, st, it = run()
+        tot_loop_ms += median_ms(run, reps=5, warm=1)
+        tot_ctrl += LA.size
+        tot_solves += int(it.sum().item())
+        del cs
+    return {"workload": "config 5: 16 x 16 (lambda_alpha*eps, lambda_sigma) x 14 horizons L = 8..60 on shared four-tank data, "
+                        "64 closed loops x 401 steps per controller",
+            "controllers": tot_ctrl, "controllers_failed": failed, "setup_s": tot_t, "controllers_per_s": tot_ctrl / tot_t,
+            "qp_solves": tot_solves, "loops_ms_total": tot_loop_ms, "solves_per_s": tot_solves / (tot_loop_ms * 1e-3)}
+
+
+def secondary_convex(dev, sc, fp64_peak, B=CONFIG3_LOOPS):
+    """Config 3 with the CONVEX slack bound ||sigma_pred||_inf <= c eps_max (controller.py:659-675), c = 1 and c = 0.3:
+    the iterative part of the solver (box-row ADMM) inside the fused closed loop."""
+    import torch
+    from direct_data_driven_mpc_b200 import ControllerSet
+    prm, plant = sc["params"], sc["plant"]
+    d = lambda a: torch.from_numpy(np.ascontiguousarray(a[:B])).to(dev)
+    args = (plant, d(sc["x0"]), d(sc["u_past0"]), d(sc["y_past0"]), d(sc["u_s"]), d(sc["y_s"]), N_STEPS)
+    bufs = (torch.empty(B, N_STEPS, 2, dtype=torch.float64, device=dev), torch.empty(B, N_STEPS, 2, dtype=torch.float64, device=dev))
+    out = {"workload": f"config 3 with slack CONVEX, {B} loops x 401 steps, tol 1e-8", "fp64_peak_tflops": fp64_peak}
+    nb, nth = 60, 20
+    for c in (1.0, 0.3):
+        cs = ControllerSet(prm["n"], 2, 2, sc["u_d"], sc["y_d"], prm["L"], prm["Q"], prm["R"], prm["eps_max"],
+                           prm["lamb_alpha"], prm["lamb_sigma"], c, 1, 1, 4, True, device=dev)
+        run = lambda: cs.closed_loop(*args, noise_seed=0, noise_eps=0.002, out=bufs)
+        _, _, st, it = run()
+        ms = median_ms(run, reps=5, warm=1)
+        solves = B * SOLVES_PER_LOOP
+        iters = float(it.sum().item())
+        active_loops = int((it > SOLVES_PER_LOOP).sum().item())
+        # executed work: every solve pays the gain product + plant block (640 flop) and the slack check Ks theta
+        # (2 nb n_theta); every ADMM iteration beyond the check one Phi d product (2 nb^2).  The final t = Phi d and the
+        # Psi correction of the active solves are not counted (their number is not reported by the kernel).
+        flops = solves * (640 + 2 * nb * nth) + (iters - solves) * 2 * nb * nb
+        tf = flops / (ms * 1e-3) / 1e12
+        out[f"c_{c}"] = {"loop_ms": ms, "solves_per_s": solves / (ms * 1e-3), "status_max": int(st.max().item()),
+                         "iterations_mean_per_solve": iters / solves, "admm_iterations_total": iters - solves,
+                         "loops_with_an_active_bound": active_loops, "executed_tflops": tf,
+                         "frac_of_fp64_peak": tf / fp64_peak if fp64_peak else None}
         del cs
     return out
 
@@ -374,8 +597,15 @@ def main():
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep NCCL's banner off stdout (one JSON line only)
         dist.init_process_group("nccl", device_id=dev)
 
-    B = args.loops
-    sc = S.config3_batch(B, seed=0)
+    strong = args.scaling == "strong"
+    if strong and args.loops % world:
+        raise SystemExit("--scaling strong needs --loops divisible by the number of GPUs")
+    B = args.loops // world if strong else args.loops            # loops on this GPU
+    total = B * world
+    sc = S.config3_batch(total if strong else B, seed=0)
+    if strong:                                       # this rank's contiguous shard of the 65,536 scenarios
+        for k in ("x0", "u_past0", "y_past0", "u_s", "y_s"):
+            sc[k] = sc[k][rank * B:(rank + 1) * B]
     prm, plant = sc["params"], sc["plant"]
     t_setup0 = time.perf_counter()
     cs = ControllerSet(prm["n"], 2, 2, sc["u_d"], sc["y_d"], prm["L"], prm["Q"], prm["R"], prm["eps_max"],
@@ -409,23 +639,9 @@ def main():
     assert solves_per_step == B * SOLVES_PER_LOOP
     # One step = one kernel launch; the Python call around it costs 0.1-0.4 ms on a busy host, more than the
     # kernel.  Capture the step once in a CUDA graph and replay it (launch-bound inner loop -> graph).
-    graph, launches_per_step = None, 1
-    if not args.no_graph:
-        try:
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                step()
-            torch.cuda.current_stream().wait_stream(side)
-            l0 = _lib.kernel_launches()
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                _, _, status, iters = step()
-            launches_per_step = _lib.kernel_launches() - l0
-        except Exception as exc:  # pragma: no cover
-            print(f"CUDA graph capture failed ({exc}); timing direct launches", file=sys.stderr)
-            graph = None
-    run_step = graph.replay if graph is not None else step
+    run_step, launches_per_step, graph = graph_of(step, not args.no_graph)
+    if launches_per_step is None:
+        launches_per_step = 1
     for _ in range(max(args.warmup, 3)):       # W untimed warm-up steps, no idle gap before the timed region
         run_step()
     # warm the per-loop metric kernels (first use loads their CUDA modules) and the collective
@@ -438,15 +654,9 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     ev0.record()
-    dbg = os.environ.get("BENCH_DEBUG_EVENTS") == "1"
-    dbg_ev = []
     for _ in range(args.steps):
         run_step()
-        if dbg:
-            e = torch.cuda.Event(enable_timing=True)
-            e.record()
-            dbg_ev.append(e)
-    # the only collective of the job: per-loop metrics (final tracking error + status) to every rank
+    # per-loop metrics (final tracking error) to every rank: the collective a Monte-Carlo job needs every pass
     track = (y_sys[:, -1, :] - ys).abs().amax(dim=1)
     if world > 1:
         gathered = [torch.empty_like(track) for _ in range(world)]
@@ -455,10 +665,6 @@ def main():
     barrier()
     t1 = time.perf_counter()
     launches = (_lib.kernel_launches() - launches0) if graph is None else launches_per_step * args.steps
-    if dbg and rank == 0:
-        ts = np.array([dbg_ev[i].elapsed_time(dbg_ev[i + 1]) for i in range(len(dbg_ev) - 1)])
-        print("per-step ms: first", np.round(ts[:8], 3), "median", np.median(ts), "p90", np.percentile(ts, 90), "max",
-              ts.max(), "host loop s", t1 - t0, file=sys.stderr)
     ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -467,49 +673,132 @@ def main():
     value = world * solves_per_step * args.steps / (total_ms * 1e-3)
     clk = clocks.stop(t0, t1) if rank == 0 else None
 
-    # ---- dominant kernel alone (k_closed_loop), CUDA events on its stream, for the roofline
-    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-           for _ in range(min(args.steps, 50))]
-    for a, b_ in kev:
-        a.record()
-        run_step()
-        b_.record()
-    torch.cuda.synchronize()
+    # ---- dominant kernel alone, CUDA events on its stream, for the roofline
     # median, not mean: a host hiccup between two replays (busy multi-rank boxes) must not count as kernel time
-    k_ms = float(np.median([a.elapsed_time(b_) for a, b_ in kev]))
+    k_ms = median_ms(run_step, reps=min(max(args.steps, 10), 50), warm=0)
     alg_bytes = B * N_STEPS * (2 + 2) * 8          # u_sys + y_sys written once (Philox noise: nothing read)
     peak, peak_src = measured_peaks()
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
-    traffic = None
+    kernel = kernel_for(B)
+    # roofline denominators measured in this run, on this device (csrc/probes.cu)
+    fp64_dmma = fp64_dfma = floor_owner = floor_coal = None
+    try:
+        stream = torch.cuda.current_stream().cuda_stream
+        fp64_dmma = _lib.probe_fp64_tflops(True, stream)
+        fp64_dfma = _lib.probe_fp64_tflops(False, stream)
+        floor_owner = _lib.probe_store_ms(B, N_STEPS, False, u_sys.data_ptr(), y_sys.data_ptr(), stream)
+        floor_coal = _lib.probe_store_ms(B, N_STEPS, True, u_sys.data_ptr(), y_sys.data_ptr(), stream)
+        run_step()                                 # the probes overwrote the trajectories
+        torch.cuda.synchronize()
+    except Exception as exc:  # pragma: no cover
+        print(f"probes failed: {exc!r}", file=sys.stderr)
+    traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get("k_closed_loop_ws_dram_bytes_per_launch")
+            tj = json.load(open(tpath))
+            ent = tj.get(kernel)
+            if ent and ent.get("loops") == B:
+                traffic, traffic_src = ent["dram_bytes_per_launch"], ent["source"]
         except Exception:
             traffic = None
-    # the default kernel for this batch size is the warp-specialised all-tensor-core one (fast_loop.cu): per n-step
-    # block and 64 loops 32 + 48 DMMA m8n8k4 (256 FMA each, zero padding of the 12-row plant block map included)
-    roofline = {"bound": "hbm", "kernel": "k_closed_loop_ws", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+    # executed flops per solve: ws kernel = 32 + 48 DMMA m8n8k4 (256 FMA each, zero padding of the 12-row plant block
+    # map included) per 64 loops and n-step block; per-loop kernel = (8 x 16 gain + 8 x 4 set-point fold once) + 12 x 12 map
+    flops_per_solve = 2 * 80 * 256 // 64 if kernel == "k_closed_loop_ws" else 2 * (8 * 16 + 12 * 12)
+    roofline = {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": k_ms,
-                "flops_per_solve_executed": 2 * 80 * 256 // 64,
-                "store_pattern_floor_ms": 0.204,
-                "store_pattern_note": "841 MB written as 32-byte sectors 6416 B apart (reference layout (B, n_steps, m)) take "
-                                      "0.204 ms on a B200 with no compute at all (scripts/probes/store_pattern.cu, "
-                                      "profiles/r1_probes.txt); a fully coalesced write of the same bytes takes 0.138 ms"}
+                "flops_per_solve_executed": flops_per_solve,
+                "fp64": {"executed_tflops": flops_per_solve * solves_per_step / (k_ms * 1e-3) / 1e12,
+                         "peak_tflops_dmma": fp64_dmma, "peak_tflops_dfma": fp64_dfma,
+                         "frac": (flops_per_solve * solves_per_step / (k_ms * 1e-3) / 1e12 / fp64_dmma) if fp64_dmma else None,
+                         "peak_source": "ddmpc_probe_fp64_tflops, this run, this device"},
+                "store_pattern_floor_ms": floor_owner, "coalesced_store_floor_ms": floor_coal,
+                "frac_of_store_pattern_floor": (floor_owner / k_ms) if floor_owner else None,
+                "store_pattern_note": "time to write the same trajectory bytes with NO compute, measured in this run "
+                                      "(ddmpc_probe_store_ms): in the reference layout (B, n_steps, m) a loop owns a contiguous "
+                                      "run and produces 32 bytes of it per step pair, so a warp store touches 32 sectors "
+                                      "16*n_steps bytes apart (store_pattern_floor_ms); fully coalesced stores of the same "
+                                      "bytes (coalesced_store_floor_ms) are the HBM write peak"}
+
+    # ---- K6: gather of the full trajectories (the only data-path collective of a job), timed on NCCL
+    gather = None
+    try:
+        gather = measure_gather(u_sys, y_sys, world, dev, barrier)
+        gather["value_incl_gather"] = world * solves_per_step / ((ms_per_step + gather["gather_ms"]) * 1e-3)
+        gather["value_incl_gather_note"] = "one job = one closed-loop pass + the gather of its trajectories"
+    except Exception as exc:  # pragma: no cover
+        gather = {"error": repr(exc)}
+
+    # ---- strong scaling: BASELINE config 3 as written (65,536 loops in total, sharded), measured in the same run
+    strong_res = None
+    if not strong and world > 1 and CONFIG3_LOOPS % world == 0:
+        try:
+            Bs = CONFIG3_LOOPS // world
+            sl = slice(rank * Bs, (rank + 1) * Bs)
+            sc3 = S.config3_batch(CONFIG3_LOOPS, seed=0)
+            sx0, sup, syp, sus, sys_ = (d(sc3[k][sl]) for k in ("x0", "u_past0", "y_past0", "u_s", "y_s"))
+            su, sy = u_sys[:Bs], y_sys[:Bs]
+            sstep = lambda: cs.closed_loop(plant, sx0, sup, syp, sus, sys_, N_STEPS, w=None, noise_seed=0,
+                                           scenario_id0=rank * Bs, noise_eps=0.002, out=(su, sy))
+            _, _, sst, sit = sstep()
+            srun, _, sgraph = graph_of(sstep, not args.no_graph)
+            for _ in range(5):
+                srun()
+            barrier()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            for _ in range(args.steps):
+                srun()
+            s1.record()
+            barrier()
+            sms = torch.tensor([s0.elapsed_time(s1) / args.steps], dtype=torch.float64, device=dev)
+            dist.all_reduce(sms, op=dist.ReduceOp.MAX)
+            sg = measure_gather(su.contiguous(), sy.contiguous(), world, dev, barrier)
+            s_ms = float(sms.item())
+            strong_res = {"loops_total": CONFIG3_LOOPS, "loops_per_gpu": Bs, "kernel": kernel_for(Bs), "ms_per_step": s_ms,
+                          "value": CONFIG3_LOOPS * SOLVES_PER_LOOP / (s_ms * 1e-3), "unit": UNIT, "status_max": int(sst.max().item()),
+                          "gather_ms": sg["gather_ms"],
+                          "value_incl_gather": CONFIG3_LOOPS * SOLVES_PER_LOOP / ((s_ms + sg["gather_ms"]) * 1e-3),
+                          "note": "BASELINE config 3 as written: 65,536 closed loops in total, contiguous shards, device time, "
+                                  "max over ranks"}
+            step()                                 # restore the weak-scaling outputs for the checks below
+            torch.cuda.synchronize()
+        except Exception as exc:  # pragma: no cover
+            strong_res = {"error": repr(exc)}
 
     # ---- end to end through the host-buffer API: pinned inputs H2D, trajectories D2H, every step
     e2e = None
     try:
-        e2e = measure_e2e(args, cs, sc, plant, id0, solves_per_step, world, barrier, dev, u_sys)
+        e2e = measure_e2e(args, cs, sc, plant, id0, solves_per_step, world, barrier, dev, u_sys, y_sys)
     except Exception as exc:  # pragma: no cover - never lose the main line over an auxiliary measurement
         e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": None, "d2h_bytes_per_step": None, "error": repr(exc)}
-    cb, latency, secondary = None, None, None
+    cb, latency, secondary, shard_times = None, None, None, None
     if rank == 0 and world == 1:
+        # what one GPU of a strong-scaled job runs: the shard sizes of 65,536 loops over 2 / 4 / 8 GPUs
         try:
-            secondary = secondary_config4(dev)
+            shard_times = {}
+            for Bs in (32768, 16384, 8192):
+                if Bs >= B:
+                    continue
+                sstep = lambda: cs.closed_loop(plant, x0[:Bs], up0[:Bs], yp0[:Bs], us[:Bs], ys[:Bs], N_STEPS, w=None, noise_seed=0,
+                                               scenario_id0=0, noise_eps=0.002, out=(u_sys[:Bs], y_sys[:Bs]))
+                srun, _, sgraph = graph_of(sstep, not args.no_graph)
+                shard_times[str(Bs)] = {"ms": median_ms(srun, reps=20), "kernel": kernel_for(Bs)}
+            step()
+            torch.cuda.synchronize()
         except Exception as exc:  # pragma: no cover
-            secondary = {"error": repr(exc)}
+            shard_times = {"error": repr(exc)}
+    if rank == 0 and world == 1 and not args.no_secondary:
+        secondary = {}
+        for name, fn in (("config4", lambda: secondary_config4(dev, fp64_peak=fp64_dmma)),
+                         ("config2", lambda: secondary_config2(dev)),
+                         ("config5", lambda: secondary_config5(dev)),
+                         ("convex", lambda: secondary_convex(dev, sc, fp64_dmma, min(B, CONFIG3_LOOPS)))):
+            try:
+                secondary[name] = fn()
+            except Exception as exc:  # pragma: no cover
+                secondary[name] = {"error": repr(exc)}
     if rank == 0:
         from direct_data_driven_mpc_b200 import (DataDrivenMPCType, DirectDataDrivenMPCController,
                                                  SlackVarConstraintTypes)
@@ -540,9 +829,10 @@ def main():
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(B, world),
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling,
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(B, world, args.scaling, kernel),
             "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cb,
+            "gather": gather, "strong": strong_res, "single_gpu_shard_times": shard_times,
             "single_loop_latency": latency, "secondary": secondary,
             "setup_ms": setup_ms, "solves_per_step_per_gpu": solves_per_step,
             "final_tracking_error_max": float(track.max().item()),

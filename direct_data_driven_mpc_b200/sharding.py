@@ -41,6 +41,12 @@ def gather_shards(local: torch.Tensor, total: int, group=None, dst: Optional[int
     if local.shape[0] != sizes[rank]:
         raise ValueError(f"rank {rank} holds {local.shape[0]} rows, expected {sizes[rank]}")
     mx = max(sizes)
+    if dst is None and min(sizes) == mx and local.is_cuda and dist.get_backend(group) == "nccl":
+        # equal shards on NCCL: gather straight into the concatenated result (no list of parts, no second copy)
+        local = local.contiguous()
+        out = torch.empty((total,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(out, local, group=group)
+        return out
     if local.shape[0] < mx:
         pad = torch.zeros((mx - local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
         local = torch.cat([local, pad], dim=0)
