@@ -199,7 +199,7 @@ def workload_config(loops, world, scaling, kernel):
 
 def kernel_for(loops: int) -> str:
     """Name of the kernel ddmpc_closed_loop_batch selects for this batch of the bench workload."""
-    return "k_closed_loop_ws" if loops >= 16384 else "k_closed_loop_perloop"
+    return "k_closed_loop_ws" if loops >= 6144 else "k_closed_loop_perloop"
 
 
 # --------------------------------------------------------------------------

@@ -255,7 +255,7 @@ class ControllerSet:
     def closed_loop(self, plant: LTIPlant, x0, u_past0, y_past0, u_s, y_s, n_steps: int, w=None,
                     noise_seed: int = 0, scenario_id0: int = 0, noise_eps: Optional[float] = None, ctrl_idx=None,
                     tol: float = 1e-8, max_iter: int = 2000, out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
-                    want_x_final: bool = False):
+                    want_x_final: bool = False, check_idx: bool = True):
         """B closed loops of ``n_steps`` steps, in lockstep on the device.
 
         w: (B, n_steps, p) pre-scaled noise (parity mode) or None for device Philox noise

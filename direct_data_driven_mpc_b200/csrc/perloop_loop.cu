@@ -132,32 +132,46 @@ k_closed_loop_perloop(const __grid_constant__ PlMaps<NMPC * P + NX, NX + NMPC * 
 
     int status = DDMPC_SOLVE_OPTIMAL;
     const int nblk = (a.n_steps + NMPC - 1) / NMPC;
+    // uploaded noise (parity mode) of output row k + G i of the block starting at step t0
+    auto fetch_row = [&](int t0, int i) -> double {
+        const int r = k + G * i;
+        return (G * i < RY && r < RY && t0 + r / P < a.n_steps) ? __ldg(a.w + (f0 + t0) * P + r) : 0.0;
+    };
+    // noise of that row: the prefetched value, or word (q & 3) of Philox call (q >> 2) for noise word q = step * P + output
+    auto noise_row = [&](int t0, int i, double fetched) -> double {
+        if constexpr (PHILOX) {
+            const int r = k + G * i;
+            if (G * i >= RY) return 0.0;
+            const unsigned q = (unsigned)t0 * (unsigned)P + (unsigned)(r < RY ? r : 0);
+            uint32_t c0 = q >> 2, c1 = 0u, c2 = sid_lo, c3 = sid_hi;
+#pragma unroll
+            for (int rr = 0; rr < 10; ++rr) pl_philox_round(c0, c1, c2, c3, a.rk[2 * rr], a.rk[2 * rr + 1]);
+            const unsigned w4 = q & 3u;
+            const uint32_t word = w4 == 0 ? c0 : (w4 == 1 ? c1 : (w4 == 2 ? c2 : c3));
+            const double v = a.eps * (2.0 * __hiloint2double((int)(0x3FF00000u | (word >> 12)), (int)(word << 20)) - 3.0);
+            return r < RY ? v : 0.0;
+        } else {
+            return fetched;
+        }
+    };
+    double nz_next[RP];
+#pragma unroll
+    for (int i = 0; i < RP; ++i) nz_next[i] = PHILOX ? 0.0 : fetch_row(0, i);
     double Y[RY];
 #pragma unroll
     for (int j = 0; j < RY; ++j) Y[j] = 0.0;
     for (int blk = 0, t0 = 0; blk < nblk; ++blk, t0 += NMPC) {
         const int steps = min(NMPC, a.n_steps - t0);
         if (steps < NMPC) load_map(maps.Mt);
-        // ---- measurement noise of this lane's output rows (independent of the solve: issued first)
+        // ---- measurement noise of this lane's output rows: Philox words are computed here (independent of the solve chain);
+        //      uploaded noise was fetched one block ahead, so its global-memory latency is off the critical path
         double nz[RP];
 #pragma unroll
-        for (int i = 0; i < RP; ++i) {
-            const int r = k + G * i;
-            nz[i] = 0.0;
-            if (G * i < RY) {
-                if constexpr (PHILOX) {
-                    // noise word q = step * P + output is word (q & 3) of Philox call (q >> 2)  (solve.cu)
-                    const unsigned q = (unsigned)t0 * (unsigned)P + (unsigned)(r < RY ? r : 0);
-                    uint32_t c0 = q >> 2, c1 = 0u, c2 = sid_lo, c3 = sid_hi;
+        for (int i = 0; i < RP; ++i) nz[i] = noise_row(t0, i, nz_next[i]);
+        if constexpr (!PHILOX) {
+            if (blk + 1 < nblk) {
 #pragma unroll
-                    for (int rr = 0; rr < 10; ++rr) pl_philox_round(c0, c1, c2, c3, a.rk[2 * rr], a.rk[2 * rr + 1]);
-                    const unsigned w4 = q & 3u;
-                    const uint32_t word = w4 == 0 ? c0 : (w4 == 1 ? c1 : (w4 == 2 ? c2 : c3));
-                    const double v = a.eps * (2.0 * __hiloint2double((int)(0x3FF00000u | (word >> 12)), (int)(word << 20)) - 3.0);
-                    nz[i] = r < RY ? v : 0.0;
-                } else {
-                    if (r < RY && t0 + r / P < a.n_steps) nz[i] = __ldg(a.w + (f0 + t0) * P + r);
-                }
+                for (int i = 0; i < RP; ++i) nz_next[i] = fetch_row(t0 + NMPC, i);
             }
         }
         // ---- NOMINAL with rank-deficient data: consistency of the window with range(H) (solve.cu, k_closed_loop)
@@ -318,10 +332,14 @@ static int launch_perloop(const ddmpc_plant *plant, PerLoopArgs a, uint64_t seed
     return DDMPC_OK;
 }
 
-// Largest batch of a SHARED equality-only controller that still takes this kernel: below it the thread-per-loop
-// kernels (fast_loop.cu) leave most of the machine idle and are bound by their serial chain (0.25 ms for ANY batch up
-// to 65,536 four-tank loops); from 16,384 loops on the warp-specialised tensor-core kernel takes over.
-static constexpr int kPerLoopSharedMaxB = 16383;
+// Largest batch of a SHARED equality-only controller that still takes this kernel.  Measured on B200 (config 3, ms per
+// 401-step pass; scripts/time_paths.py, profiles/r2_closed_loop_paths.txt):
+//      loops     1024     4096     8192    16384    65536
+//      perloop  0.045    0.053    0.102    0.194    0.665       8 lanes per loop: shortest chain, 8x the instructions
+//      ws       0.071    0.071    0.073    0.096    0.243       warp-specialised tensor-core kernel (n-step shape)
+//      hybrid   0.141    0.143    0.145    0.151    0.249       thread per loop
+// (n_mpc_step = 1: perloop 0.126 / 0.157 / - / 0.487 / 1.76, hybrid 0.174 / 0.174 / - / 0.227 / 0.355.)
+static constexpr int kPerLoopSharedMaxB = 6143;
 
 // Returns DDMPC_OK when handled, -1 when this path does not apply.
 int closed_loop_perloop_try(const ddmpc_set *set, const ddmpc_plant *plant, int B, const int *ctrl_idx, const double *x0,

@@ -978,7 +978,7 @@ int ddmpc_set_option(ddmpc_set *set, const char *name, int value) {
     if (!set || !name) return fail(DDMPC_ERR_INVALID_ARG, "set_option: null argument");
     const std::string nm(name);
     if (nm == "closed_loop_path") {
-        if (value < DDMPC_PATH_AUTO || value > DDMPC_PATH_GEMM) return fail(DDMPC_ERR_INVALID_ARG, "set_option: unknown path %d", value);
+        if (value < DDMPC_PATH_AUTO || value > DDMPC_PATH_CVX) return fail(DDMPC_ERR_INVALID_ARG, "set_option: unknown path %d", value);
         set->opt_path = value;
     } else if (nm == "dmma_warps") {
         if (value != 1 && value != 2 && value != 4) return fail(DDMPC_ERR_INVALID_ARG, "set_option: dmma_warps must be 1, 2 or 4");
@@ -986,6 +986,9 @@ int ddmpc_set_option(ddmpc_set *set, const char *name, int value) {
     } else if (nm == "loops_per_thread") {
         if (value < 0 || value > 2) return fail(DDMPC_ERR_INVALID_ARG, "set_option: loops_per_thread must be 0, 1 or 2");
         set->opt_lpt = value;
+    } else if (nm == "solve_path") {
+        if (value < 0 || value > 2) return fail(DDMPC_ERR_INVALID_ARG, "set_option: solve_path must be 0, 1 or 2");
+        set->opt_solve = value;
     } else {
         return fail(DDMPC_ERR_INVALID_ARG, "set_option: unknown option '%s'", name);
     }

@@ -592,6 +592,16 @@ int closed_loop_fast_try(const ddmpc_set *set, const ddmpc_plant *plant, int B, 
                          double *y_sys, int *status, int *iters, double *x_final, double tol, int max_iter,
                          cudaStream_t st);
 
+int closed_loop_cvx_try(const ddmpc_set *set, const ddmpc_plant *plant, int B, const int *ctrl_idx, const double *x0,
+                        const double *u_past0, const double *y_past0, const double *u_s, const double *y_s,
+                        const double *w, uint64_t seed, uint64_t id0, double eps, int n_steps, double *u_sys,
+                        double *y_sys, int *status, int *iters, double *x_final, double tol, int max_iter,
+                        cudaStream_t st);
+
+int solve_batch_cvx_dmma(const ddmpc_set *set, int B, const int *ctrl_idx, const double *u_past, const double *y_past,
+                         const double *u_s, const double *y_s, double tol, int max_iter, double *optimal_u, double *cost,
+                         int *status, int *iters, double *t_out, cudaStream_t st);
+
 int closed_loop_perloop_try(const ddmpc_set *set, const ddmpc_plant *plant, int B, const int *ctrl_idx, const double *x0,
                             const double *u_past0, const double *y_past0, const double *u_s, const double *y_s,
                             const double *w, uint64_t seed, uint64_t id0, double eps, int n_steps, double *u_sys,
@@ -644,6 +654,11 @@ int solve_batch_device(const ddmpc_set *set, int B, const int *ctrl_idx, const d
     if (B == 0) return DDMPC_OK;
     if (!u_past || !y_past || !u_s || !y_s || !optimal_u)
         return fail(DDMPC_ERR_INVALID_ARG, "solve_batch: null argument");
+    if (set->opt_solve != 1) {   // shared CONVEX controller, large batch: GEMMs + box-row ADMM on the tensor cores
+        const int rc = solve_batch_cvx_dmma(set, B, ctrl_idx, u_past, y_past, u_s, y_s, tol, max_iter, optimal_u, cost, status,
+                                            iters, t_out, st);
+        if (rc != -1) return rc;
+    }
     KArgs a = make_kargs(set, tol, max_iter);
     if (B <= 64) {   // latency path: one CTA per solve
         const size_t sh = sizeof(double) * ((size_t)a.nth + 4 * (size_t)a.nb + 64 + (size_t)a.Lm);
@@ -825,6 +840,12 @@ int ddmpc_closed_loop_batch(const ddmpc_set *set, const ddmpc_plant *plant, int 
         {   // 8 lanes per loop: per-loop controllers (any batch), NOMINAL, small batches of a shared controller
             const int rc = closed_loop_perloop_try(set, plant, B, ctrl_idx, x0, u_past0, y_past0, u_s, y_s, w, noise_seed,
                                                    scenario_id0, noise_eps, n_steps, u_sys, y_sys, status, iters, x_final, st);
+            if (rc != -1) return rc;
+        }
+        {   // shared CONVEX controller, four-tank n-step shape: slack check and box-row ADMM on the FP64 tensor cores
+            const int rc = closed_loop_cvx_try(set, plant, B, ctrl_idx, x0, u_past0, y_past0, u_s, y_s, w, noise_seed,
+                                               scenario_id0, noise_eps, n_steps, u_sys, y_sys, status, iters, x_final, tol,
+                                               max_iter, st);
             if (rc != -1) return rc;
         }
         {   // register-resident / warp-specialised kernels (shared ROBUST controller, four-tank-size system)

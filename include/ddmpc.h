@@ -221,10 +221,12 @@ enum {
     DDMPC_PATH_WS = 3,        /* k_closed_loop_ws: warp-specialised all-tensor-core, four-tank n-step shape       */
     DDMPC_PATH_PERLOOP = 4,   /* k_closed_loop_perloop: 8 lanes per loop, per-loop controllers / small batches    */
     DDMPC_PATH_DMMA = 5,      /* k_closed_loop_dmma: config-4 shapes, warp per 8 loops on the FP64 tensor cores   */
-    DDMPC_PATH_GEMM = 6       /* closed_loop_gemm: batch as the N dimension of FP64 tensor-core GEMMs             */
+    DDMPC_PATH_GEMM = 6,      /* closed_loop_gemm: batch as the N dimension of FP64 tensor-core GEMMs             */
+    DDMPC_PATH_CVX = 7        /* k_closed_loop_cvx: shared CONVEX controller, slack check + ADMM on the tensor cores */
 };
 /* Per-set options: "closed_loop_path" (DDMPC_PATH_*), "dmma_warps" (1, 2 or 4: CTA size of the config-4 kernel),
- * "loops_per_thread" (0 = automatic, 1, 2: hybrid kernel).  Not thread-safe against running calls on the same set. */
+ * "loops_per_thread" (0 = automatic, 1, 2: hybrid kernel), "solve_path" (0 = automatic, 1 = thread / CTA per solve kernels,
+ * 2 = tensor-core ADMM pipeline where it applies).  Not thread-safe against running calls on the same set. */
 int ddmpc_set_option(ddmpc_set *set, const char *name, int value);
 
 /* Number of controllers of the set whose setup failed (not persistently exciting / factorisation); their indices

@@ -61,8 +61,10 @@ def main() -> None:
     c = run(args.reference, "examples/robust_data_driven_mpc_reproduction.py", ["--verbose", "0"], lines)
     for i, name in ((1, "TEC"), (2, "TEC_N_STEP"), (3, "UCON")):
         n = g[f"u_{name}"].shape[0]                      # the UCON fixture holds the first 150 steps (it diverges by design)
-        eu = rel(c[f"{i}_plot_input_output_u_k"][:n], g[f"u_{name}"])
-        ey = rel(c[f"{i}_plot_input_output_y_k"][:n], g[f"y_{name}"])
+        # the script plots [U_n; u_sys]: the n = 4 warm-up steps come first (robust_data_driven_mpc_reproduction.py:294-295)
+        assert np.array_equal(c[f"{i}_plot_input_output_u_k"][:4], g["U_n"])
+        eu = rel(c[f"{i}_plot_input_output_u_k"][4:4 + n], g[f"u_{name}"])
+        ey = rel(c[f"{i}_plot_input_output_y_k"][4:4 + n], g[f"y_{name}"])
         lines.append(f"reproduction script (seed 4, t_sim 600) {name}: u rel err {eu:.2e}, y rel err {ey:.2e} over {n} steps "
                      f"(script ran {c[f'{i}_plot_input_output_u_k'].shape[0]})")
         ok &= eu <= 1e-5 and ey <= 1e-5

@@ -59,7 +59,11 @@ def install_plot_stubs(captured: list) -> None:
     for name in ("plot_input_output", "plot_input_output_animation", "save_animation", "create_input_output_figure",
                  "plot_data"):
         setattr(viz, name, recorder(name))
-    viz.__getattr__ = lambda name: recorder(name)            # any other plotting helper a script may import
+    def other(name):                                         # any other plotting helper a script may import
+        if name.startswith("__"):                            # (inspect.getmodule probes __file__ etc. of every module)
+            raise AttributeError(name)
+        return recorder(name)
+    viz.__getattr__ = other
     sys.modules["utilities.visualization.data_visualization"] = viz
 
 
@@ -81,6 +85,7 @@ def main() -> None:
         sys.modules["cvxpy"] = mini_cvxpy
         sys.path.insert(0, ref)
     else:
+        import torch  # noqa: F401  (before the matplotlib stand-ins exist: torch inspects sys.modules while it loads)
         sys.path.insert(0, ref)
         sys.path.insert(0, ROOT)                             # shadow package wins over the reference's own package
     install_plot_stubs(captured)

@@ -344,14 +344,23 @@ def test_convex_fused_path_vs_generic_and_oracle(c):
     ys = us @ _plant().equilibrium_gain().T
     up0, yp0 = np.tile(u_d[-4:].reshape(1, -1), (B, 1)), np.tile(y_d[-4:].reshape(1, -1), (B, 1))
     w = 0.002 * r.uniform(-1, 1, (B, n_steps, 2))
-    u1, y1, s1, i1 = cs.closed_loop(_plant(), xs, up0, yp0, us, ys, n_steps, w=w)
+    l0 = _launches()
+    u1, y1, s1, i1 = cs.closed_loop(_plant(), xs, up0, yp0, us, ys, n_steps, w=w)        # auto = k_closed_loop_cvx
+    assert _launches() - l0 == 1
     cs.set_option("closed_loop_path", "generic")
     u2, y2, s2, i2 = cs.closed_loop(_plant(), xs, up0, yp0, us, ys, n_steps, w=w)
+    cs.set_option("closed_loop_path", "fast")                  # hybrid kernel: slack rows on DMMA, one-loop-at-a-time warp ADMM
+    u5, y5, s5, i5 = cs.closed_loop(_plant(), xs, up0, yp0, us, ys, n_steps, w=w)
+    cs.set_option("closed_loop_path", "cvx")
+    u6, y6, s6, i6, x6 = cs.closed_loop(_plant(), xs, up0, yp0, us, ys, n_steps, w=w, want_x_final=True)
     cs.set_option("closed_loop_path", "auto")
-    assert int(s1.max()) == 0 and int(s2.max()) == 0
+    assert np.array_equal(u1.cpu().numpy(), u6.cpu().numpy())
+    assert int(s1.max()) == 0 and int(s2.max()) == 0 and int(s5.max()) == 0
     assert int(i1.max()) > 10                                  # the box really binds somewhere
     assert (i1 == i2).all(), (i1 - i2).abs().max()
+    assert (i5 == i2).all()
     assert _rel(u1.cpu().numpy(), u2.cpu().numpy()) < 1e-8 and _rel(y1.cpu().numpy(), y2.cpu().numpy()) < 1e-8
+    assert _rel(u5.cpu().numpy(), u2.cpu().numpy()) < 1e-8 and _rel(y5.cpu().numpy(), y2.cpu().numpy()) < 1e-8
     u1, y1 = u1.cpu().numpy(), y1.cpu().numpy()
     for b in (0, 33, 69):
         po = O.four_tank_plant()

@@ -75,10 +75,12 @@ def test_pe_rank():
     from direct_data_driven_mpc_b200 import ControllerSet
     ud = np.hstack([np.sin(0.3 * t) + np.sin(0.7 * t), np.cos(0.2 * t)])[:120] + 1e-9 * rng.normal(size=(120, 2))
     yd = rng.normal(size=(120, 2))
-    cs = ControllerSet(2, 2, 2, ud, yd, 8, np.eye(16), np.eye(16), 0.01, 1.0, 10.0, 1.0, 0, 1, 1, True)
-    rank, status = cs.info(0)                                      # order L + 2n = 12: rank 2 * 12 -> PE accepted;
-    assert rank == 24 and status != 7                              # (data this ill-conditioned may still fail the
-                                                                   # Gram factorisation: status 10, not "not PE")
+    try:                                                           # order L + 2n = 12: rank 2 * 12 -> PE accepted;
+        cs = ControllerSet(2, 2, 2, ud, yd, 8, np.eye(16), np.eye(16), 0.01, 1.0, 10.0, 1.0, 0, 1, 1, True)
+        assert cs.info(0) == (24, 0)
+    except ValueError as exc:                                      # data this ill-conditioned may still fail the Gram
+        assert "positive definite" in str(exc)                     # factorisation of the robust setup - but not the PE test
+        assert "persistently exciting" not in str(exc)
 
 
 def _four_tank_set(slack, term, c=1.0, n_mpc=4, seed=0, ctrl=1):

@@ -156,6 +156,47 @@ def test_solve_batch_large_batch_kernel_matches_small_batch_kernel(slack, c):
         assert np.abs(u_big[b].cpu().numpy() - so.optimal_u).max() < 1e-5 * max(1.0, np.abs(so.optimal_u).max())
 
 
+@pytest.mark.parametrize("c,B", [(1.0, 1024), (0.3, 1500), (0.2, 2077)])
+def test_tensor_core_admm_pipeline_matches_scalar_kernels_and_oracle(c, B):
+    """Shared CONVEX controller, B >= 1024: the solve runs as k_gemm products around k_admm_dmma (box-row ADMM with
+    Phi d on the FP64 tensor cores, csrc/cvx_loop.cu).  Same iterates as the thread-per-solve kernel (option
+    "solve_path" = 1) up to FP64 summation order: equal iteration counts, u and cost to 1e-9; oracle on a sample;
+    ragged batch (B not a multiple of the 32 problems of a CTA); a non-finite problem stays confined to itself."""
+    cs, qp, prm, u_d, y_d = _set(1, True, c, n_mpc=4)
+    up, yp, us, ys = _thetas(u_d, y_d, prm, B, seed=5)
+    us[7, 0] = np.nan                                              # one poisoned problem
+    l0 = _launches()
+    u1, c1, s1, i1 = cs.solve_batch(up, yp, us, ys, tol=1e-8)
+    assert _launches() - l0 == 8                                   # pack, 2 GEMM, ADMM, GEMM, 2 GEMM + cost rows
+    cs.set_option("solve_path", 1)
+    u2, c2, s2, i2 = cs.solve_batch(up, yp, us, ys, tol=1e-8)
+    cs.set_option("solve_path", 0)
+    s1n, s2n = s1.cpu().numpy(), s2.cpu().numpy()
+    assert s1n[7] == 3 and s2n[7] == 3 and (np.delete(s1n, 7) == 0).all() and (np.delete(s2n, 7) == 0).all()
+    good = np.ones(B, dtype=bool); good[7] = False
+    i1n, i2n = i1.cpu().numpy()[good], i2.cpu().numpy()[good]
+    assert (i1n > 1).sum() > B // 20                               # the box binds in a good share of the problems
+    assert np.abs(i1n - i2n).max() <= 1 and (i1n != i2n).mean() < 0.01   # (a residual may cross the threshold one iteration apart)
+    u1n, u2n = u1.cpu().numpy()[good], u2.cpu().numpy()[good]
+    assert np.abs(u1n - u2n).max() <= 1e-8 * max(1.0, np.abs(u2n).max())
+    c1n, c2n = c1.cpu().numpy()[good], c2.cpu().numpy()[good]
+    assert np.abs(c1n - c2n).max() <= 1e-8 * max(1.0, np.abs(c2n).max())
+    for b in (0, 1, 31, 32, B // 2, B - 1):
+        so = qp.solve(up[b], yp[b], us[b], ys[b])
+        assert np.abs(u1[b].cpu().numpy() - so.optimal_u).max() < 1e-5 * max(1.0, np.abs(so.optimal_u).max()), b
+        assert abs(float(c1[b]) - so.cost) <= 1e-6 * max(1.0, abs(so.cost))
+    # full primal through the same pipeline (sigma within its bound, dynamics constraint holds)
+    ub, yb, sg, al = cs.solve_full_batch(up[good][:1100], yp[good][:1100], us[good][:1100], ys[good][:1100])
+    assert float(sg[:, 8:].abs().max()) <= c * 0.002 * (1 + 1e-6)
+    so = qp.solve(up[good][3], yp[good][3], us[good][3], ys[good][3])
+    assert np.abs(sg[3].cpu().numpy() - so.sigma.reshape(-1)).max() < 1e-7
+
+
+def _launches():
+    from direct_data_driven_mpc_b200 import _lib
+    return _lib.kernel_launches()
+
+
 @pytest.mark.parametrize("L", [8, 20, 60])
 def test_config5_lambda_horizon_grid_vs_oracle(L):
     """BASELINE config 5 parity sample: corners of the lambda_alpha*eps x lambda_sigma grid at three horizons, one
