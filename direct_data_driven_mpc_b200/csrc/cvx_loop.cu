@@ -145,9 +145,9 @@ __device__ __forceinline__ void admm_cta(const double (&aPhi)[2][CV_KS], const d
         for (int nt = 0; nt < CV_NT; ++nt)
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-                if ((frozen >> (2 * nt + h)) & 1u) continue;         // (uniform over the 8 lanes of the column)
-                const double r = colmax8(res[nt][h]);
-                if (g == 0) atomicMax(&sm.red[slot][8 * nt + 2 * q + h], (unsigned long long)__double_as_longlong(r));
+                const double r = colmax8(res[nt][h]);                // (every lane takes part in the shuffles: columns differ in q)
+                if (g == 0 && !((frozen >> (2 * nt + h)) & 1u))
+                    atomicMax(&sm.red[slot][8 * nt + 2 * q + h], (unsigned long long)__double_as_longlong(r));
             }
         __syncthreads();
 #pragma unroll
