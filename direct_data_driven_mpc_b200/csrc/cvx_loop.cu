@@ -23,6 +23,7 @@
 //                        row split, 40 DMMA per warp), the gain product, the ADMM when any of the CTA's 32 loops violates
 //                        the bound, the plant block map, noise and recording - one launch for the whole run.
 // Replaces the thread-per-problem ADMM of solve.cu / the one-loop-at-a-time warp ADMM of fast_loop.cu for these shapes.
+#include <type_traits>
 #include <vector>
 
 #include "linalg.cuh"
@@ -413,8 +414,10 @@ __device__ __forceinline__ double cv_unit32(uint32_t x) {
     return __hiloint2double((int)(0x3FF00000u | (x >> 12)), (int)(x << 20));
 }
 
-template <bool PHILOX>
-__global__ void __launch_bounds__(128, 2)
+// MINB = CTAs per SM the register allocation is held to (2: no spills; 3, 4: the ADMM section spills, the per-block path
+// does not - more resident warps for the latency-bound steady state).
+template <bool PHILOX, int MINB>
+__global__ void __launch_bounds__(128, MINB)
 k_closed_loop_cvx(const __grid_constant__ CvxMaps maps, const CvxArgs a) {
     constexpr int NW = 16, NSPK = 5;                                 // window rows; k-steps of the 20 theta entries
     extern __shared__ __align__(16) unsigned char cv_raw[];
@@ -458,8 +461,11 @@ k_closed_loop_cvx(const __grid_constant__ CvxMaps maps, const CvxArgs a) {
     };
     load_map(maps.Mb);
     const int nblk = (a.n_steps + 3) / 4;
-    for (int t = 0; t < nblk; ++t) {
-        const int cur = t & 1, nxt = cur ^ 1;
+    const double bound = a.bhi[0];                                   // pure CONVEX: every box row is [-c eps_max, c eps_max]
+    // One MPC iteration.  The window buffers alternate with the block parity, which is a compile-time constant here (the
+    // loop below is unrolled by two) so that every shared-memory address is a fixed offset.
+    auto block = [&](auto parity, const int t) {
+        constexpr int cur = decltype(parity)::value, nxt = cur ^ 1;
         if (t == nblk - 1 && a.n_tail != 0) load_map(maps.Mt);       // last, partial block (controller_operation.py:278)
         __syncthreads();                                             // window / state / set-points of all 32 loops are in place
         // ---- measurement noise of (loop, step q): parked in the output rows of the next window, where the plant
@@ -499,13 +505,30 @@ k_closed_loop_cvx(const __grid_constant__ CvxMaps maps, const CvxArgs a) {
                 for (int nt = 0; nt < CV_NT; ++nt) dmma884(su[mt][nt], aKs[mt][ks], bv[nt]);
             dmma884(cu, aKu[ks], row[8 * warp + g]);
         }
-        unsigned viol, bad;
-        box_flags(su, lo, hi, q, viol, bad);
-        if (lane == 0) { sm.admm.vmask[cur][warp] = viol; sm.admm.bmask[cur][warp] = bad; }
+        // ---- screening: does any slack row of any loop leave the box?  (max over this lane's two rows, one compare and
+        //      one vote per fragment column; fmax drops NaN, and a loop whose state is non-finite must not iterate anyway)
+        unsigned susp = 0u;
+#pragma unroll
+        for (int nt = 0; nt < CV_NT; ++nt)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const double m = h ? fmax(fabs(su[0][nt].y), fabs(su[1][nt].y)) : fmax(fabs(su[0][nt].x), fabs(su[1][nt].x));
+                const unsigned bv = __ballot_sync(0xffffffffu, m > bound);
+                susp |= bv;                                          // (which column does not matter yet)
+            }
+        if (lane == 0) sm.admm.vmask[cur][warp] = susp;
         __syncthreads();
-        const unsigned vall = sm.admm.vmask[cur][0] | sm.admm.vmask[cur][1] | sm.admm.vmask[cur][2] | sm.admm.vmask[cur][3];
-        const unsigned ball = sm.admm.bmask[cur][0] | sm.admm.bmask[cur][1] | sm.admm.bmask[cur][2] | sm.admm.bmask[cur][3];
-        const unsigned act32 = vall & ~ball;
+        unsigned act32 = 0u;
+        if ((sm.admm.vmask[cur][0] | sm.admm.vmask[cur][1] | sm.admm.vmask[cur][2] | sm.admm.vmask[cur][3]) != 0u) {
+            // rare (first blocks after a set-point change): which loops violate, which hold non-finite numbers
+            unsigned viol, bad;
+            box_flags(su, lo, hi, q, viol, bad);
+            if (lane == 0) { sm.admm.vmask[nxt][warp] = viol; sm.admm.bmask[cur][warp] = bad; }
+            __syncthreads();
+            const unsigned vall = sm.admm.vmask[nxt][0] | sm.admm.vmask[nxt][1] | sm.admm.vmask[nxt][2] | sm.admm.vmask[nxt][3];
+            const unsigned ball = sm.admm.bmask[cur][0] | sm.admm.bmask[cur][1] | sm.admm.bmask[cur][2] | sm.admm.bmask[cur][3];
+            act32 = vall & ~ball;
+        }
         if (act32 != 0u) {                                           // CTA-uniform: some loop violates its slack bound
             // ---- box-row ADMM on the tensor cores, then the correction of the planned inputs  U -= Psi[0:8, :] t
 #pragma unroll
@@ -574,6 +597,14 @@ k_closed_loop_cvx(const __grid_constant__ CvxMaps maps, const CvxArgs a) {
             *reinterpret_cast<double2 *>(a.u_sys + (f0 + k) * 2) = make_double2(sm.th[nxt][2 * q][lcol], sm.th[nxt][2 * q + 1][lcol]);
             *reinterpret_cast<double2 *>(a.y_sys + (f0 + k) * 2) = make_double2(sm.th[nxt][8 + 2 * q][lcol], sm.th[nxt][8 + 2 * q + 1][lcol]);
         }
+    };
+    {
+        int t = 0;
+        for (; t + 1 < nblk; t += 2) {
+            block(std::integral_constant<int, 0>{}, t);
+            block(std::integral_constant<int, 1>{}, t + 1);
+        }
+        if (t < nblk) block(std::integral_constant<int, 0>{}, t);
     }
     __syncthreads();
     // ---- verdict of loop 8 warp + g (lanes q = 0..3 hold one state entry and one step of the last block each)
@@ -635,12 +666,19 @@ int closed_loop_cvx_try(const ddmpc_set *set, const ddmpc_plant *plant, int B, c
     }
     static std::atomic<unsigned long long> attr_done{0};
     if (first_time_on_device(attr_done)) {
-        DDMPC_TRY(admm_smem_attr((const void *)k_closed_loop_cvx<true>, sizeof(CvxSmem)));
-        DDMPC_TRY(admm_smem_attr((const void *)k_closed_loop_cvx<false>, sizeof(CvxSmem)));
+        DDMPC_TRY(admm_smem_attr((const void *)k_closed_loop_cvx<true, 2>, sizeof(CvxSmem)));
+        DDMPC_TRY(admm_smem_attr((const void *)k_closed_loop_cvx<false, 2>, sizeof(CvxSmem)));
+        DDMPC_TRY(admm_smem_attr((const void *)k_closed_loop_cvx<true, 3>, sizeof(CvxSmem)));
+        DDMPC_TRY(admm_smem_attr((const void *)k_closed_loop_cvx<false, 3>, sizeof(CvxSmem)));
     }
     const int grid = ceil_div(B, CV_NL);
-    if (w) k_closed_loop_cvx<false><<<grid, 128, sizeof(CvxSmem), st>>>(maps, a);
-    else k_closed_loop_cvx<true><<<grid, 128, sizeof(CvxSmem), st>>>(maps, a);
+    if (set->opt_cvx_ctas == 2) {
+        if (w) k_closed_loop_cvx<false, 2><<<grid, 128, sizeof(CvxSmem), st>>>(maps, a);
+        else k_closed_loop_cvx<true, 2><<<grid, 128, sizeof(CvxSmem), st>>>(maps, a);
+    } else {
+        if (w) k_closed_loop_cvx<false, 3><<<grid, 128, sizeof(CvxSmem), st>>>(maps, a);
+        else k_closed_loop_cvx<true, 3><<<grid, 128, sizeof(CvxSmem), st>>>(maps, a);
+    }
     DDMPC_LAUNCH_CHECK();
     return DDMPC_OK;
 }

@@ -986,6 +986,9 @@ int ddmpc_set_option(ddmpc_set *set, const char *name, int value) {
     } else if (nm == "loops_per_thread") {
         if (value < 0 || value > 2) return fail(DDMPC_ERR_INVALID_ARG, "set_option: loops_per_thread must be 0, 1 or 2");
         set->opt_lpt = value;
+    } else if (nm == "cvx_ctas_per_sm") {
+        if (value != 2 && value != 3) return fail(DDMPC_ERR_INVALID_ARG, "set_option: cvx_ctas_per_sm must be 2 or 3");
+        set->opt_cvx_ctas = value;
     } else if (nm == "solve_path") {
         if (value < 0 || value > 2) return fail(DDMPC_ERR_INVALID_ARG, "set_option: solve_path must be 0, 1 or 2");
         set->opt_solve = value;
