@@ -49,6 +49,10 @@ struct PerLoopArgs {
     double *u_sys, *y_sys, *x_final;
     int *status, *iters;
     uint32_t rk[20];                   // Philox round keys (key + r * Weyl), filled on the host
+    // box rows (CONVEX slack bound), per controller: Ks (nb, nth), Phi (nb, nb), Psi (Lm, nb), scaled bounds, tolerance scale
+    int nb, max_iter;
+    double tol;
+    const double *Ks, *Phi, *Psi, *blo, *bhi, *bmax;
 };
 
 __device__ __forceinline__ void pl_philox_round(uint32_t &c0, uint32_t &c1, uint32_t &c2, uint32_t &c3, uint32_t k0,
@@ -61,7 +65,10 @@ __device__ __forceinline__ void pl_philox_round(uint32_t &c0, uint32_t &c1, uint
     c2 = n2;
 }
 
-template <int N, int M, int P, int NX, int NMPC, bool PHILOX>
+// BOX: the controllers carry box rows (CONVEX slack bound): after the gain product the 8 lanes of a loop compute its
+// slack rows Ks theta (rows k, k + 8, ..) and, if one leaves the box, run the box-row ADMM of DESIGN.md 1.1 cooperatively:
+// every operator is PRIVATE to the loop (no shared matrix, no GEMM), streamed from L2 with 16-byte loads.
+template <int N, int M, int P, int NX, int NMPC, bool PHILOX, bool BOX = false>
 __global__ void __launch_bounds__(128)
 k_closed_loop_perloop(const __grid_constant__ PlMaps<NMPC * P + NX, NX + NMPC * M> maps, const PerLoopArgs a) {
     constexpr int G = 8;                                   // lanes per loop
@@ -72,6 +79,7 @@ k_closed_loop_perloop(const __grid_constant__ PlMaps<NMPC * P + NX, NX + NMPC * 
     constexpr int S = ((EX + 11) / 16) * 16 + 4;           // stride = 4 (mod 16) doubles: the 4 loops of a warp read
                                                            // their (broadcast) 16-byte pieces from disjoint banks
     __shared__ __align__(16) double ex_s[16][S];
+    __shared__ __align__(16) double box_s[BOX ? 16 : 1][BOX ? 3 : 1][BOX ? 64 : 2];   // per loop: ADMM iterate d (then t), z, w
     const int lane = threadIdx.x & 31, k = lane & (G - 1);
     const int slot = threadIdx.x >> 3;                     // loop slot in the CTA
     double *ex = ex_s[slot];
@@ -130,7 +138,7 @@ k_closed_loop_perloop(const __grid_constant__ PlMaps<NMPC * P + NX, NX + NMPC * 
     }
     const bool any_f = a.F && __any_sync(0xffffffffu, fnz != 0);
 
-    int status = DDMPC_SOLVE_OPTIMAL;
+    int status = DDMPC_SOLVE_OPTIMAL, extra = 0;
     const int nblk = (a.n_steps + NMPC - 1) / NMPC;
     // uploaded noise (parity mode) of output row k + G i of the block starting at step t0
     auto fetch_row = [&](int t0, int i) -> double {
@@ -204,6 +212,156 @@ k_closed_loop_perloop(const __grid_constant__ PlMaps<NMPC * P + NX, NX + NMPC * 
 #pragma unroll
             for (int j = 0; j < NW; ++j) acc[j & 3] = fma(Kw[i][j], win[j], acc[j & 3]);
             u_own[i] = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + csp[i];
+        }
+        if constexpr (BOX) {
+            // ---- slack rows of this loop, rows k + 8 i: s_unc = Ks theta
+            const int nb = a.nb;
+            const double *Ksc = a.Ks + (size_t)c * nb * a.nth, *loc = a.blo + (size_t)c * nb, *hic = a.bhi + (size_t)c * nb;
+            double su[8];
+            bool viol = false, bad = false;
+            double smax = 0.0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int r = k + G * i;
+                su[i] = 0.0;
+                if (r < nb) {
+                    const double2 *row = reinterpret_cast<const double2 *>(Ksc + (size_t)r * a.nth);
+                    double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+                    for (int j = 0; j < NW / 2; ++j) {
+                        const double2 kv = __ldg(row + j);
+                        a0 = fma(kv.x, win[2 * j], a0);
+                        a1 = fma(kv.y, win[2 * j + 1], a1);
+                    }
+#pragma unroll
+                    for (int j = 0; j < NSP / 2; ++j) {
+                        const double2 kv = __ldg(row + NW / 2 + j);
+                        a0 = fma(kv.x, sp[2 * j], a0);
+                        a1 = fma(kv.y, sp[2 * j + 1], a1);
+                    }
+                    const double sv = a0 + a1;
+                    su[i] = sv;
+                    viol = viol || sv < __ldg(loc + r) || sv > __ldg(hic + r);
+                    bad = bad || !isfinite(sv);
+                    smax = fmax(smax, fabs(sv));
+                }
+            }
+            const unsigned gmask = 0xffu << (lane & 24);             // the 8 lanes of this loop
+            const unsigned vm = __ballot_sync(0xffffffffu, viol), bm = __ballot_sync(0xffffffffu, bad);
+            const bool act = (vm & gmask) != 0u && (bm & gmask) == 0u;
+            if (__any_sync(0xffffffffu, act)) {                      // warp-uniform: some loop of the warp violates its box
+                const double *Phic = a.Phi + (size_t)c * nb * nb;
+                double *bd = box_s[slot][0], *bz = box_s[slot][1], *bw = box_s[slot][2];
+#pragma unroll
+                for (int o = 1; o < G; o <<= 1) smax = fmax(smax, __shfl_xor_sync(0xffffffffu, smax, o));
+                const double thr = a.tol * fmax(__ldg(a.bmax + c), smax);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int r = k + G * i;
+                    if (r < nb) {
+                        const double zz = fmin(fmax(su[i], __ldg(loc + r)), __ldg(hic + r));
+                        bz[r] = zz;
+                        bw[r] = 0.0;
+                        bd[r] = su[i] - zz;
+                    }
+                }
+                // row r of Phi times the iterate in bd
+                auto phi_row = [&](int r) -> double {
+                    const double2 *row = reinterpret_cast<const double2 *>(Phic + (size_t)r * nb);
+                    const double2 *dv = reinterpret_cast<const double2 *>(bd);
+                    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+                    int j = 0;
+                    for (; j + 1 < nb / 2; j += 2) {
+                        const double2 p0 = __ldg(row + j), p1 = __ldg(row + j + 1), d0 = dv[j], d1 = dv[j + 1];
+                        a0 = fma(p0.x, d0.x, a0); a1 = fma(p0.y, d0.y, a1);
+                        a2 = fma(p1.x, d1.x, a2); a3 = fma(p1.y, d1.y, a3);
+                    }
+                    if (j < nb / 2) {
+                        const double2 p0 = __ldg(row + j), d0 = dv[j];
+                        a0 = fma(p0.x, d0.x, a0); a1 = fma(p0.y, d0.y, a1);
+                    }
+                    return (a0 + a1) + (a2 + a3);
+                };
+                bool conv = !act;
+                int it = 0, it_conv = 1;
+                while (true) {
+                    __syncwarp();                                    // the iterate of every loop is complete
+                    if (!__any_sync(0xffffffffu, !conv) || it >= a.max_iter) break;
+                    ++it;
+                    double dn[8], res = 0.0;
+                    if (!conv) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int r = k + G * i;
+                            dn[i] = 0.0;
+                            if (r < nb) {
+                                const double zi = bz[r], wi = bw[r];
+                                const double si = (zi - wi) + phi_row(r);
+                                const double sr = DDMPC_ADMM_RELAX * si + (1.0 - DDMPC_ADMM_RELAX) * zi;   // over-relaxation (solve.cu)
+                                const double zn = fmin(fmax(sr + wi, __ldg(loc + r)), __ldg(hic + r));
+                                res = fmax(res, fmax(fabs(si - zn), fabs(zn - zi)));
+                                const double wn = wi + sr - zn;
+                                bz[r] = zn;
+                                bw[r] = wn;
+                                dn[i] = su[i] - zn + wn;
+                            }
+                        }
+                    }
+                    __syncwarp();                                    // every lane has read the old iterate
+                    if (!conv) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int r = k + G * i;
+                            if (r < nb) bd[r] = dn[i];
+                        }
+                    }
+#pragma unroll
+                    for (int o = 1; o < G; o <<= 1) res = fmax(res, __shfl_xor_sync(0xffffffffu, res, o));
+                    if (!conv) {
+                        it_conv = it;
+                        conv = res <= thr;
+                    }
+                }
+                if (act) {
+                    if (!conv) status = max(status, (int)DDMPC_SOLVE_OPTIMAL_INACCURATE);
+                    extra += it_conv - 1;
+                }
+                // t = Phi d at the fixed point, then the correction of the planned inputs u -= Psi t
+                double tv[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int r = k + G * i;
+                    tv[i] = (act && r < nb) ? phi_row(r) : 0.0;
+                }
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int r = k + G * i;
+                    if (r < nb) bd[r] = tv[i];
+                }
+                __syncwarp();
+                if (act) {
+                    const double *Psic = a.Psi + (size_t)c * a.Lm * nb;
+#pragma unroll
+                    for (int i = 0; i < RU; ++i) {
+                        const int r = k + G * i;
+                        if (r < R) {
+                            const double2 *row = reinterpret_cast<const double2 *>(Psic + (size_t)r * nb);
+                            const double2 *dv = reinterpret_cast<const double2 *>(bd);
+                            double a0 = 0.0, a1 = 0.0;
+                            for (int j = 0; j < nb / 2; ++j) {
+                                const double2 pv = __ldg(row + j), d0 = dv[j];
+                                a0 = fma(pv.x, d0.x, a0);
+                                a1 = fma(pv.y, d0.y, a1);
+                            }
+                            u_own[i] -= a0 + a1;
+                        }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < RU; ++i) {
             const int r = k + G * i;
             if (r < R) ex[r] = u_own[i];
         }
@@ -289,7 +447,7 @@ k_closed_loop_perloop(const __grid_constant__ PlMaps<NMPC * P + NX, NX + NMPC * 
     if (live) {
         if (k == 0) {
             if (a.status) a.status[b] = status;
-            if (a.iters) a.iters[b] = nblk;
+            if (a.iters) a.iters[b] = nblk + extra;
         }
         if (a.x_final) {
 #pragma unroll
@@ -326,7 +484,14 @@ static int launch_perloop(const ddmpc_plant *plant, PerLoopArgs a, uint64_t seed
     // one-warp CTAs deal a small batch to the SMs at the finest grain; larger CTAs once the batch fills the machine
     const int wpc = a.B > 65536 ? 4 : (a.B > 16384 ? 2 : 1);
     const int grid = ceil_div(a.B, 4 * wpc);
-    if (a.w) k_closed_loop_perloop<N, M, P, NX, NMPC, false><<<grid, 32 * wpc, 0, st>>>(maps, a);
+    if (a.nb > 0) {
+        if constexpr ((N * (M + P)) % 2 == 0 && (M + P) % 2 == 0) {
+            if (a.w) k_closed_loop_perloop<N, M, P, NX, NMPC, false, true><<<grid, 32 * wpc, 0, st>>>(maps, a);
+            else k_closed_loop_perloop<N, M, P, NX, NMPC, true, true><<<grid, 32 * wpc, 0, st>>>(maps, a);
+        } else {
+            return -1;
+        }
+    } else if (a.w) k_closed_loop_perloop<N, M, P, NX, NMPC, false><<<grid, 32 * wpc, 0, st>>>(maps, a);
     else k_closed_loop_perloop<N, M, P, NX, NMPC, true><<<grid, 32 * wpc, 0, st>>>(maps, a);
     DDMPC_LAUNCH_CHECK();
     return DDMPC_OK;
@@ -345,14 +510,19 @@ static constexpr int kPerLoopSharedMaxB = 6143;
 int closed_loop_perloop_try(const ddmpc_set *set, const ddmpc_plant *plant, int B, const int *ctrl_idx, const double *x0,
                             const double *u_past0, const double *y_past0, const double *u_s, const double *y_s,
                             const double *w, uint64_t seed, uint64_t id0, double eps, int n_steps, double *u_sys,
-                            double *y_sys, int *status, int *iters, double *x_final, cudaStream_t st) {
+                            double *y_sys, int *status, int *iters, double *x_final, double tol, int max_iter,
+                            cudaStream_t st) {
     const Plan &pl = set->plan;
     const Dims &d = pl.d;
-    if (d.nb > 0) return -1;                               // box rows: other kernels
+    // box rows: the CONVEX slack bound only (input / output boxes add an infeasibility check: generic kernel); 16-byte
+    // loads of the per-loop operators need even row lengths
+    if (d.nb > 0 && (d.nbu > 0 || d.nby > 0 || d.nb > 64 || (d.nb & 1) || (d.nth & 1))) return -1;
     const int path = set->opt_path;
     if (path != DDMPC_PATH_AUTO && path != DDMPC_PATH_PERLOOP) return -1;
     const bool per_loop = ctrl_idx != nullptr || pl.count != 1 || !d.robust;
-    if (path == DDMPC_PATH_AUTO && !per_loop && B > kPerLoopSharedMaxB) return -1;
+    // shared equality-only controller: large batches belong to the thread-per-loop / tensor-core kernels; a shared
+    // CONVEX controller of a shape k_closed_loop_cvx does not cover stays here whatever the batch
+    if (path == DDMPC_PATH_AUTO && !per_loop && d.nb == 0 && B > kPerLoopSharedMaxB) return -1;
     PerLoopArgs a{};
     a.B = B; a.n_steps = n_steps; a.nth = d.nth; a.Lm = d.Lm; a.nfix = d.nfix;
     a.ctrl_idx = ctrl_idx;
@@ -362,6 +532,8 @@ int closed_loop_perloop_try(const ddmpc_set *set, const ddmpc_plant *plant, int 
     a.x0 = x0; a.u_past0 = u_past0; a.y_past0 = y_past0; a.u_s = u_s; a.y_s = y_s; a.w = w;
     a.id0 = id0; a.eps = eps;
     a.u_sys = u_sys; a.y_sys = y_sys; a.x_final = x_final; a.status = status; a.iters = iters;
+    a.nb = d.nb; a.max_iter = max_iter > 0 ? max_iter : 1000; a.tol = tol > 0.0 ? tol : 1e-8;
+    a.Ks = pl.Ks.d(); a.Phi = pl.Phi.d(); a.Psi = pl.Psi.d(); a.blo = pl.lo.d(); a.bhi = pl.hi.d(); a.bmax = pl.bmax.d();
     const int nmpc = set->prm.n_mpc_step;
 #define DDMPC_PERLOOP_CASE(N_, M_, P_, NX_, NMPC_)                                                   \
     if (d.n == N_ && d.m == M_ && d.p == P_ && plant->n_x == NX_ && nmpc == NMPC_)                   \

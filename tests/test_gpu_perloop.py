@@ -64,6 +64,42 @@ def test_per_seed_controllers_vs_generic_kernel(ctype, term, n_mpc, n_steps):
         assert _rel(x1.cpu().numpy(), x2.cpu().numpy()) < 1e-9
 
 
+@pytest.mark.parametrize("n_mpc,c", [(4, 0.3), (1, 0.25), (4, 1.0)])
+def test_per_seed_convex_controllers_vs_generic_kernel_and_oracle(n_mpc, c):
+    """Per-loop CONVEX controllers (config 2, slack bound ||sigma_pred||_inf <= c eps_max): the 8 lanes of a loop run its
+    box-row ADMM cooperatively with the loop's private Ks / Phi / Psi.  Same iterates as the generic kernel (equal
+    iteration counts, 1e-8 on the trajectories); oracle active-set solution on a sample."""
+    from direct_data_driven_mpc_b200 import ControllerSet
+    B, n_steps = 21, 26
+    prm = O.four_tank_params()
+    ud, yd, xs, data = _per_seed(B)
+    cs = ControllerSet(4, 2, 2, ud, yd, 30, prm["Q"], prm["R"], prm["eps_max"], prm["lamb_alpha"], prm["lamb_sigma"], c, 1, 1,
+                       n_mpc, True)
+    r = np.random.default_rng(4)
+    us = np.tile(prm["u_s"].T, (B, 1)) * r.uniform(0.8, 1.2, (B, 1))
+    ys = us @ _plant().equilibrium_gain().T
+    w = 0.002 * r.uniform(-1, 1, (B, n_steps, 2))
+    args = (_plant(), xs, ud[:, -4:].reshape(B, -1), yd[:, -4:].reshape(B, -1), us, ys, n_steps)
+    l0 = _launches()
+    u1, y1, s1, i1 = cs.closed_loop(*args, w=w, ctrl_idx=np.arange(B))
+    assert _launches() - l0 == 1
+    cs.set_option("closed_loop_path", "generic")
+    u2, y2, s2, i2 = cs.closed_loop(*args, w=w, ctrl_idx=np.arange(B))
+    cs.set_option("closed_loop_path", "auto")
+    assert int(s1.max()) == 0 and int(s2.max()) == 0
+    if c < 1.0:
+        assert int(i1.max()) > -(-n_steps // n_mpc) + 5          # the box really binds somewhere
+    assert (i1 == i2).all(), (i1 - i2).abs().max()
+    assert _rel(u1.cpu().numpy(), u2.cpu().numpy()) < 1e-8 and _rel(y1.cpu().numpy(), y2.cpu().numpy()) < 1e-8
+    for b in (0, 7, B - 1):
+        po = O.four_tank_plant()
+        po.x = xs[b].copy()
+        ctrl = O.make_controller(prm, ud[b], yd[b], n_mpc_step=n_mpc, slack_type=O.SLACK_CONVEX, c=c)
+        ctrl.u_s, ctrl.y_s = us[b].reshape(-1, 1), ys[b].reshape(-1, 1)
+        u_ref, y_ref = O.closed_loop(po, ctrl, n_steps, w[b])
+        assert _rel(u1[b].cpu().numpy(), u_ref) < 1e-5 and _rel(y1[b].cpu().numpy(), y_ref) < 1e-5, b
+
+
 def test_nominal_noise_free_data_feasibility_check():
     """NOMINAL controller built from noise-free data (rank-deficient Hankel matrix: the feasibility map F is not zero):
     a consistent window is "optimal", an inconsistent one "infeasible" (status 2), as the generic kernel reports."""
