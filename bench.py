@@ -571,6 +571,39 @@ def secondary_convex(dev, sc, fp64_peak, B=CONFIG3_LOOPS):
                          "loops_with_an_active_bound": active_loops, "executed_tflops": tf,
                          "frac_of_fp64_peak": tf / fp64_peak if fp64_peak else None}
         del cs
+    # ---- the batched solve itself (ddmpc_solve_batch, no plant): B QPs of one shared CONVEX controller through the
+    #      tensor-core pipeline (k_gemm products around k_admm_dmma, csrc/cvx_loop.cu), every problem with a binding box
+    try:
+        c = 0.3
+        cs = ControllerSet(prm["n"], 2, 2, sc["u_d"], sc["y_d"], prm["L"], prm["Q"], prm["R"], prm["eps_max"],
+                           prm["lamb_alpha"], prm["lamb_sigma"], c, 1, 1, 4, True, device=dev)
+        r = np.random.default_rng(0)
+        ks = r.integers(0, sc["u_d"].shape[0] - 4, B)
+        up = torch.from_numpy(np.stack([sc["u_d"][k:k + 4].reshape(-1) for k in ks])).to(dev)
+        yp = torch.from_numpy(np.stack([sc["y_d"][k:k + 4].reshape(-1) for k in ks])).to(dev)
+        us, ys = d(sc["u_s"]), d(sc["y_s"])
+        run = lambda: cs.solve_batch(up, yp, us, ys, tol=1e-8, want_cost=False)
+        _, _, st, it = run()
+        ms = median_ms(run, reps=5, warm=1)
+        cs.set_option("solve_path", 1)
+        run1 = lambda: cs.solve_batch(up, yp, us, ys, tol=1e-8, want_cost=False)
+        ms_scalar = median_ms(run1, reps=3, warm=1)
+        iters = float(it.sum().item())
+        active = int((it > 1).sum().item())
+        # executed: u0 = Ku theta (2 Lm n_theta), s = Ks theta (2 nb n_theta), u -= Psi t (2 Lm nb) per problem as GEMMs;
+        # per ADMM iteration of an ACTIVE problem one Phi d (2 nb^2); the lock-step iterations a CTA spends on problems
+        # that have already converged are executed too but are not counted here
+        flops = B * (2 * 60 * nth + 2 * nb * nth + 2 * 60 * nb) + (iters - (B - active)) * 2 * nb * nb
+        tf = flops / (ms * 1e-3) / 1e12
+        out["solve_batch"] = {"problems": B, "c": c, "pipeline_ms": ms, "solves_per_s": B / (ms * 1e-3),
+                              "thread_per_solve_kernel_ms": ms_scalar, "speedup_vs_thread_per_solve": ms_scalar / ms,
+                              "problems_with_an_active_bound": active, "iterations_mean_per_active_problem":
+                              (iters - (B - active)) / max(active, 1), "status_max": int(st.max().item()),
+                              "executed_tflops_useful": tf, "frac_of_fp64_peak": tf / fp64_peak if fp64_peak else None,
+                              "kernels": "k_pack_theta, k_gemm x2, k_admm_dmma, k_gemm"}
+        del cs
+    except Exception as exc:  # pragma: no cover
+        out["solve_batch"] = {"error": repr(exc)}
     return out
 
 

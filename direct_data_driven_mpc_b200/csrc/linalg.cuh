@@ -2,6 +2,8 @@
 // strided GEMM (optional diagonal scaling), Cholesky, triangular solves and a
 // parallel-ordered cyclic Jacobi eigensolver.  One batch entry per controller.
 #pragma once
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace ddmpc {
@@ -177,8 +179,9 @@ k_potrf(int n, double *__restrict__ A, long ld, long bs, int *__restrict__ info)
 // Same factorisation with the lower triangle held in shared memory (packed, row-major: (i, j) at i(i+1)/2 + j) for
 // matrices that fit (n <= 208): the unblocked right-looking update moves n^3/6 elements, which is L2 traffic in
 // k_potrf and shared-memory traffic here.  One CTA of 256 threads per matrix; a warp per row of the trailing update.
+// off > 0: the matrix is a diagonal block (first row `off`) of a blocked factorisation: info keeps the first failure.
 static __global__ void __launch_bounds__(256)
-k_potrf_smem(int n, double *__restrict__ A, long ld, long bs, int *__restrict__ info) {
+k_potrf_smem(int n, double *__restrict__ A, long ld, long bs, int *__restrict__ info, int off = 0) {
     extern __shared__ double sh[];          // Lp[n(n+1)/2], col[n], dg[n]
     A += (long)blockIdx.x * bs;
     const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, NW = T >> 5;
@@ -220,7 +223,35 @@ k_potrf_smem(int n, double *__restrict__ A, long ld, long bs, int *__restrict__ 
         for (int j = lane; j < i; j += 32) row[j] = src[j];
         if (lane == 0) row[i] = dg[i];
     }
-    if (tid == 0 && info) info[blockIdx.x] = bad;
+    if (tid == 0 && info) {
+        if (off == 0) info[blockIdx.x] = bad;
+        else if (bad && !info[blockIdx.x]) info[blockIdx.x] = bad + off;
+    }
+}
+
+// Row-wise triangular solve of a panel: each row a of A21 (m x jb, ld) <- a L11^-T, i.e. x L11^T = a (forward
+// substitution along the row).  One thread per row; L11 (jb x jb, ld) is read by every thread at the same address.
+static __global__ void __launch_bounds__(64)
+k_trsm_rows(int m, int jb, const double *__restrict__ L11, double *__restrict__ A21, long ld, long bs) {
+    extern __shared__ double xs[];          // [jb][blockDim]: the row being solved stays on chip (a thread re-reads every
+                                            // entry it has produced: through global memory that was an L2 round trip each)
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, T = blockDim.x, tid = threadIdx.x;
+    if (i >= m) return;
+    L11 += (long)blockIdx.y * bs;
+    double *row = A21 + (long)blockIdx.y * bs + (long)i * ld;
+    for (int k = 0; k < jb; ++k) xs[k * T + tid] = row[k];
+    for (int k = 0; k < jb; ++k) {
+        const double *Lk = L11 + (long)k * ld;
+        double a0 = xs[k * T + tid], a1 = 0.0;
+        int l = 0;
+        for (; l + 1 < k; l += 2) {
+            a0 = fma(-__ldg(Lk + l), xs[l * T + tid], a0);
+            a1 = fma(-__ldg(Lk + l + 1), xs[(l + 1) * T + tid], a1);
+        }
+        if (l < k) a0 = fma(-__ldg(Lk + l), xs[l * T + tid], a0);
+        xs[k * T + tid] = (a0 + a1) / __ldg(Lk + k);
+    }
+    for (int k = 0; k < jb; ++k) row[k] = xs[k * T + tid];
 }
 
 inline int potrf(cudaStream_t st, int batch, int n, double *A, long ld, long bs, int *info) {
@@ -230,13 +261,29 @@ inline int potrf(cudaStream_t st, int batch, int n, double *A, long ld, long bs,
         static std::atomic<unsigned long long> attr_done{0};
         if (first_time_on_device(attr_done))
             DDMPC_CUDA(cudaFuncSetAttribute(k_potrf_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        k_potrf_smem<<<batch, 256, sh, st>>>(n, A, ld, bs, info);
+        k_potrf_smem<<<batch, 256, sh, st>>>(n, A, ld, bs, info, 0);
         DDMPC_LAUNCH_CHECK();
         return DDMPC_OK;
     }
-    int threads = n >= 256 ? 1024 : (n >= 96 ? 512 : 256);
-    k_potrf<<<batch, threads, 0, st>>>(n, A, ld, bs, info);
-    DDMPC_LAUNCH_CHECK();
+    // Larger matrices (config 4: r = 480, n_f = 560): blocked right-looking factorisation.  The diagonal block is
+    // factorised in shared memory, the panel below it solved one row per thread, and the trailing update
+    // A22 -= L21 L21^T - where the flops are - runs on the FP64 tensor cores (k_gemm).  The unblocked one-CTA kernel
+    // took 14.9 ms for n = 480; this takes well under a millisecond.
+    constexpr int NBK = 64;
+    const size_t shb = sizeof(double) * ((size_t)NBK * (NBK + 1) / 2 + 2 * (size_t)NBK);
+    for (int j0 = 0; j0 < n; j0 += NBK) {
+        const int jb = std::min(NBK, n - j0), m2 = n - j0 - jb;
+        double *A11 = A + (long)j0 * ld + j0;
+        k_potrf_smem<<<batch, 256, shb, st>>>(jb, A11, ld, bs, info, j0);
+        DDMPC_LAUNCH_CHECK();
+        if (m2 <= 0) break;
+        double *A21 = A + (long)(j0 + jb) * ld + j0, *A22 = A + (long)(j0 + jb) * ld + (j0 + jb);
+        dim3 gr(ceil_div(m2, 64), batch);
+        k_trsm_rows<<<gr, 64, sizeof(double) * jb * 64, st>>>(m2, jb, A11, A21, ld, bs);
+        DDMPC_LAUNCH_CHECK();
+        const Mat P21 = mat(A21, ld, 1, bs);
+        DDMPC_TRY(gemm(st, batch, m2, m2, jb, -1.0, P21, tr(P21), 1.0, A22, ld, 1, bs));
+    }
     return DDMPC_OK;
 }
 
@@ -282,11 +329,77 @@ k_trsm(int n, int nrhs, int trans, const double *__restrict__ Lm, long ldl, long
     }
 }
 
+// Same solves for a small diagonal block (n <= 64) with the right-hand side held in shared memory [n][blockDim].
+static __global__ void __launch_bounds__(64)
+k_trsm_blk(int n, int nrhs, int trans, const double *__restrict__ Lm, long ldl, long bsl,
+           double *__restrict__ Bm, long ldb, long bsb) {
+    extern __shared__ double xs[];
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, T = blockDim.x, tid = threadIdx.x;
+    if (j >= nrhs) return;
+    Lm += (long)blockIdx.y * bsl;
+    Bm += (long)blockIdx.y * bsb;
+    for (int i = 0; i < n; ++i) xs[i * T + tid] = Bm[(long)i * ldb + j];
+    if (!trans) {
+        for (int i = 0; i < n; ++i) {
+            const double *Li = Lm + (long)i * ldl;
+            double a0 = xs[i * T + tid], a1 = 0.0;
+            int k = 0;
+            for (; k + 1 < i; k += 2) {
+                a0 = fma(-__ldg(Li + k), xs[k * T + tid], a0);
+                a1 = fma(-__ldg(Li + k + 1), xs[(k + 1) * T + tid], a1);
+            }
+            if (k < i) a0 = fma(-__ldg(Li + k), xs[k * T + tid], a0);
+            xs[i * T + tid] = (a0 + a1) / __ldg(Li + i);
+        }
+    } else {
+        for (int i = n - 1; i >= 0; --i) {
+            double a0 = xs[i * T + tid], a1 = 0.0;
+            int k = i + 1;
+            for (; k + 1 < n; k += 2) {
+                a0 = fma(-__ldg(Lm + (long)k * ldl + i), xs[k * T + tid], a0);
+                a1 = fma(-__ldg(Lm + (long)(k + 1) * ldl + i), xs[(k + 1) * T + tid], a1);
+            }
+            if (k < n) a0 = fma(-__ldg(Lm + (long)k * ldl + i), xs[k * T + tid], a0);
+            xs[i * T + tid] = (a0 + a1) / __ldg(Lm + (long)i * ldl + i);
+        }
+    }
+    for (int i = 0; i < n; ++i) Bm[(long)i * ldb + j] = xs[i * T + tid];
+}
+
 // X = (L L^T)^-1 B in place
 inline int potrs(cudaStream_t st, int batch, int n, int nrhs, const double *L, long ldl, long bsl,
                  double *B, long ldb, long bsb) {
     if (n <= 0 || nrhs <= 0 || batch <= 0) return DDMPC_OK;
     const int threads = nrhs >= 128 ? 128 : (nrhs >= 64 ? 64 : 32);
+    if (n >= 96 && (long)batch * nrhs < 8192) {
+        // Few right-hand sides in total (a single controller, or a small set): one thread per right-hand side leaves
+        // the GPU to a handful of threads walking n^2 / 2 dependent steps each (0.6-1.1 ms for n = 136, 12 ms for
+        // n = 480).  Blocked substitution: the diagonal block is solved per thread as before (NB steps), the rest of
+        // the right-hand side is updated with one tensor-core GEMM per block.
+        const int NB = n >= 256 ? 64 : 32;
+        const Mat Lall = mat(L, ldl, 1, bsl);
+        for (int j0 = 0; j0 < n; j0 += NB) {                       // L X = B, top to bottom
+            const int jb = std::min(NB, n - j0), m2 = n - j0 - jb;
+            dim3 grid(ceil_div(nrhs, 64), batch);
+            k_trsm_blk<<<grid, 64, sizeof(double) * jb * 64, st>>>(jb, nrhs, 0, L + (long)j0 * ldl + j0, ldl, bsl, B + (long)j0 * ldb, ldb, bsb);
+            DDMPC_LAUNCH_CHECK();
+            if (m2 > 0)
+                DDMPC_TRY(gemm(st, batch, m2, nrhs, jb, -1.0, mat(L + (long)(j0 + jb) * ldl + j0, ldl, 1, bsl),
+                               mat(B + (long)j0 * ldb, ldb, 1, bsb), 1.0, B + (long)(j0 + jb) * ldb, ldb, 1, bsb));
+        }
+        const int last = ((n - 1) / NB) * NB;
+        for (int j0 = last; j0 >= 0; j0 -= NB) {                    // L^T X = B, bottom to top
+            const int jb = std::min(NB, n - j0);
+            dim3 grid(ceil_div(nrhs, 64), batch);
+            k_trsm_blk<<<grid, 64, sizeof(double) * jb * 64, st>>>(jb, nrhs, 1, L + (long)j0 * ldl + j0, ldl, bsl, B + (long)j0 * ldb, ldb, bsb);
+            DDMPC_LAUNCH_CHECK();
+            if (j0 > 0)     // B[0:j0, :] -= L[j0:j0+jb, 0:j0]^T X[j0:j0+jb, :]
+                DDMPC_TRY(gemm(st, batch, j0, nrhs, jb, -1.0, tr(mat(L + (long)j0 * ldl, ldl, 1, bsl)),
+                               mat(B + (long)j0 * ldb, ldb, 1, bsb), 1.0, B, ldb, 1, bsb));
+        }
+        (void)Lall;
+        return DDMPC_OK;
+    }
     dim3 grid(ceil_div(nrhs, threads), batch);
     k_trsm<<<grid, threads, 0, st>>>(n, nrhs, 0, L, ldl, bsl, B, ldb, bsb);
     DDMPC_LAUNCH_CHECK();
@@ -310,6 +423,7 @@ k_pivot_rank(int n, double *__restrict__ A, long ld, long bs, double rel, int *_
     int *redi = reinterpret_cast<int *>(red + 32);
     __shared__ double s_piv, s_first;
     __shared__ int s_idx, s_stop;
+    if (rank[blockIdx.x] == n) return;      // already certified full rank by the shifted Cholesky (pe_rank_device stage 0)
     for (int i = tid; i < n; i += T) alive[i] = 1.0;
     if (tid == 0) { s_stop = 0; s_first = 0.0; }
     __syncthreads();
@@ -365,6 +479,29 @@ inline int pivot_rank(cudaStream_t st, int batch, int n, double *A, long ld, lon
     k_pivot_rank<<<batch, threads, sh, st>>>(n, A, ld, bs, rel, rank);
     DDMPC_LAUNCH_CHECK();
     return DDMPC_OK;
+}
+
+// Stage 0 of the rank test: A <- A - tau I with tau = rel * max diag(A) (one CTA per batch entry).  If the Cholesky
+// factorisation of the shifted matrix succeeds, lambda_min(A) > tau (inertia), i.e. A is full rank with a wide margin.
+static __global__ void __launch_bounds__(256)
+k_shift_diag(int n, double *__restrict__ A, long ld, long bs, double rel) {
+    A += (long)blockIdx.x * bs;
+    __shared__ double red[256];
+    double m = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) m = fmax(m, A[(long)i * ld + i]);
+    red[threadIdx.x] = m;
+    __syncthreads();
+    for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o) red[threadIdx.x] = fmax(red[threadIdx.x], red[threadIdx.x + o]);
+        __syncthreads();
+    }
+    const double tau = rel * red[0];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) A[(long)i * ld + i] -= tau;
+}
+// rank[b] = n when the factorisation of entry b succeeded (info[b] == 0), else -1 (undecided)
+static __global__ void k_rank_from_info(int batch, int n, const int *__restrict__ info, int *__restrict__ rank) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < batch) rank[b] = info[b] == 0 ? n : -1;
 }
 
 // ---------------------------------------------------------------------------
