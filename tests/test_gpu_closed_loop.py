@@ -479,6 +479,31 @@ def test_closed_loop_host_matches_device_api(chunks):
             assert _rel(hu.numpy(), u1.cpu().numpy()) < 1e-9 and _rel(hy.numpy(), y1.cpu().numpy()) < 1e-9
 
 
+def test_closed_loop_host_chunks_on_the_gemm_path():
+    """The chunked host API alternates its chunks between two streams.  On the GEMM path (large system, n_mpc_step = 8:
+    not a compiled shape of the fused DMMA kernel) the per-call loop state used to live in a workspace cached in the
+    set, which two concurrent chunks would have shared; it is now allocated per call in stream order."""
+    import torch
+    from direct_data_driven_mpc_b200 import ControllerSet, scenarios as S
+    B, n_steps, n_mpc = 1600, 20, 8
+    sc = S.config4_batch(B, n_mpc_step=n_mpc)
+    prm, pl = sc["params"], sc["plant"]
+    cs = ControllerSet(prm["n"], 4, 4, sc["u_d"], sc["y_d"], prm["L"], prm["Q"], prm["R"], prm["eps_max"],
+                       prm["lamb_alpha"], prm["lamb_sigma"], prm["c"], 0, 1, n_mpc, True)
+    r = np.random.default_rng(2)
+    x0 = sc["x0"] + 0.1 * r.normal(size=sc["x0"].shape)
+    u_s = sc["u_s"] * r.uniform(0.8, 1.2, (B, 1))
+    y_s = u_s @ pl.equilibrium_gain().T
+    kw = dict(noise_seed=3, scenario_id0=50, noise_eps=0.002)
+    l0 = _launches()
+    u1, y1, s1, _ = cs.closed_loop(pl, x0, sc["u_past0"], sc["y_past0"], u_s, y_s, n_steps, **kw)
+    assert _launches() - l0 > 3                                    # the per-iteration GEMMs, not a fused kernel
+    for rep in range(3):
+        hu, hy, hs = cs.closed_loop_host(pl, x0, sc["u_past0"], sc["y_past0"], u_s, y_s, n_steps, chunks=3, **kw)
+        assert int(hs.max()) == 0
+        assert _rel(hu.numpy(), u1.cpu().numpy()) < 1e-12 and _rel(hy.numpy(), y1.cpu().numpy()) < 1e-12, rep
+
+
 def test_fused_kernels_are_run_to_run_deterministic():
     """Every fused kernel, run three times on the same inputs, must return bit-identical trajectories: the warp-
     specialised kernel rotates shared-memory buffers between warps and the config-4 kernel rotates a ring in place, so
