@@ -13,7 +13,7 @@
 #include <algorithm>
 #include <vector>
 
-#include "common.cuh"
+#include "linalg.cuh"
 #include "plan.cuh"
 
 namespace ddmpc {
@@ -414,6 +414,14 @@ __global__ void k_full_alpha(KArgs a, int B, const int *__restrict__ ctrl_idx, i
     for (int k = 0; k < a.r; ++k) acc = fma(Hc[(size_t)k * a.cols + col], g[(size_t)b * a.r + k], acc);
     alpha[e] = acc;
 }
+// t = T x = [ubar; ybar + sigma]   (B x r), the right-hand side of alpha = H^T W^-1 t
+__global__ void k_full_t(KArgs a, int B, const double *__restrict__ x, double *__restrict__ t) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (size_t)B * a.r) return;
+    const int b = (int)(e / a.r), k = (int)(e % a.r);
+    const double *xb = x + (size_t)b * a.nx;
+    t[e] = k >= a.nu ? xb[k] + xb[k + a.ny] : xb[k];
+}
 __global__ void k_split_x(KArgs a, int B, const double *__restrict__ x, double *__restrict__ ubar,
                           double *__restrict__ ybar, double *__restrict__ sigma) {
     const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -811,6 +819,18 @@ int ddmpc_solve_full_batch(const ddmpc_set *set, int B, const int32_t *ctrl_idx,
     if (alpha) {
         DDMPC_CUDA(gb.alloc(sizeof(double) * (size_t)B * d.r));
         const int shared_data = pl.data_count == 1 ? 1 : 0;
+        if (shared_data && B >= 64) {
+            // One data set for the whole batch: alpha = (T x) W^-1 H is the shared-Hankel x batch-of-iterates product
+            // of the north star, two FP64 tensor-core GEMMs (k_gemm, linalg.cuh) over the batch:
+            //   G (B x r) = T (B x r) Om       (Om = W^-1 symmetric),      alpha (B x cols) = G H
+            DevBuf tv;
+            DDMPC_CUDA(tv.alloc(sizeof(double) * (size_t)B * d.r));
+            k_full_t<<<ceil_div((long)B * d.r, T), T, 0, st>>>(a, B, xb.d(), tv.d());
+            DDMPC_LAUNCH_CHECK();
+            DDMPC_TRY(gemm(st, 1, B, d.r, d.r, 1.0, mat(tv.d(), d.r, 1, 0), mat(pl.Om.d(), d.r, 1, 0), 0.0, gb.d(), d.r, 1, 0));
+            DDMPC_TRY(gemm(st, 1, B, d.cols, d.r, 1.0, mat(gb.d(), d.r, 1, 0), mat(pl.H.d(), d.cols, 1, 0), 0.0, alpha, d.cols, 1, 0));
+            return DDMPC_OK;
+        }
         k_full_g<<<ceil_div((long)B * d.r, T), T, 0, st>>>(a, B, ctrl_idx, shared_data, pl.Om.d(), xb.d(), gb.d());
         DDMPC_LAUNCH_CHECK();
         k_full_alpha<<<ceil_div((long)B * d.cols, T), T, 0, st>>>(a, B, ctrl_idx, shared_data, pl.H.d(), gb.d(), alpha);

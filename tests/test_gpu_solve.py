@@ -65,6 +65,21 @@ def test_solve_full_primal_vs_oracle():
         assert np.abs(sg[b].cpu().numpy() - so.sigma).max() < 1e-7
         assert np.abs(al[b].cpu().numpy() - so.alpha).max() < 1e-6 * max(1, np.abs(so.alpha).max())
         assert np.abs(sg[b].cpu().numpy()[8:]).max() <= 0.3 * 0.002 * (1 + 1e-6)
+    # a larger batch takes the GEMM route for alpha = (T x) W^-1 H (shared Hankel matrix x batch of iterates on the FP64
+    # tensor cores): same numbers as the thread-per-element kernels of the small batch
+    B = 100
+    up, yp, us, ys = _thetas(u_d, y_d, prm, B, seed=4)
+    ub, yb, sg, al = cs.solve_full_batch(up, yp, us, ys)
+    ub2, yb2, sg2, al2 = cs.solve_full_batch(up[:40], yp[:40], us[:40], ys[:40])
+    assert float((al[:40] - al2).abs().max()) <= 1e-10 * max(1.0, float(al2.abs().max()))
+    H = np.vstack([cs.get("HLn_ud").reshape(68, -1), cs.get("HLn_yd").reshape(68, -1)])
+    t = torch_cat(ub, yb + sg)
+    assert np.abs(al.cpu().numpy() @ H.T - t).max() < 1e-7        # dynamics constraint [ubar; ybar + sigma] = H alpha
+
+
+def torch_cat(a, b):
+    import torch
+    return torch.cat([a, b], dim=1).cpu().numpy()
 
 
 def test_solve_batch_per_scenario_controller_index():
