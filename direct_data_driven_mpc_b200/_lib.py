@@ -19,7 +19,7 @@ NOMINAL, ROBUST = 0, 1
 SLACK_NONE, SLACK_CONVEX, SLACK_NON_CONVEX = 0, 1, 2
 SOLVE_OPTIMAL, SOLVE_OPTIMAL_INACCURATE, SOLVE_INFEASIBLE, SOLVE_NONFINITE = range(4)
 # kernel selection of ddmpc_closed_loop_batch (ddmpc_set_option "closed_loop_path")
-PATHS = {"auto": 0, "generic": 1, "fast": 2, "ws": 3, "perloop": 4, "dmma": 5, "gemm": 6, "cvx": 7}
+PATHS = {"auto": 0, "generic": 1, "fast": 2, "ws": 3, "perloop": 4, "dmma": 5, "gemm": 6, "cvx": 7, "tc": 8}
 STATUS_STRINGS = {SOLVE_OPTIMAL: "optimal", SOLVE_OPTIMAL_INACCURATE: "optimal_inaccurate",
                   SOLVE_INFEASIBLE: "infeasible", SOLVE_NONFINITE: "solver_error"}
 

@@ -12,7 +12,7 @@ import sys
 from concurrent.futures import ThreadPoolExecutor
 
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
-SOURCES = ["setup.cu", "solve.cu", "fast_loop.cu", "perloop_loop.cu", "cvx_loop.cu", "gemm_loop.cu", "dmma_loop.cu",
+SOURCES = ["setup.cu", "solve.cu", "fast_loop.cu", "perloop_loop.cu", "cvx_loop.cu", "tc_loop.cu", "gemm_loop.cu", "dmma_loop.cu",
            "scenario_gen.cu", "probes.cu"]
 HEADERS = ["common.cuh", "linalg.cuh", "plan.cuh", "fast_common.cuh", "ws_kernel.cuh",
            os.path.join("..", "..", "include", "ddmpc.h")]

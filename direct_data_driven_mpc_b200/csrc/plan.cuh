@@ -82,6 +82,9 @@ struct ddmpc_set {
     // stream-ordered: two streams may run closed loops of one set at the same time)
     mutable ddmpc::DevBuf gemm_ws;
     mutable std::vector<double> gemm_host;
+    // tc_loop.cu: TF32 hi / lo images of the gain block and the plant block map (+ the plant in FP64) and their host key
+    mutable ddmpc::DevBuf tc_ws;
+    mutable std::vector<double> tc_key;
     // dmma_loop.cu: packed A fragments (gain rows + block maps of the plant) and their host key
     mutable ddmpc::DevBuf dmma_ws;
     mutable std::vector<double> dmma_key;
@@ -91,7 +94,7 @@ struct ddmpc_set {
     mutable cudaStream_t stage_stream = nullptr;
     void detach_streams() {
         plan.detach_streams();
-        for (ddmpc::DevBuf *b : {&ctrl_status, &plant_dev, &fast_ksp, &gemm_ws, &dmma_ws, &stage_dev}) b->detach_stream();
+        for (ddmpc::DevBuf *b : {&ctrl_status, &plant_dev, &fast_ksp, &gemm_ws, &dmma_ws, &tc_ws, &stage_dev}) b->detach_stream();
     }
     ~ddmpc_set() {
         if (stage_host) cudaFreeHost(stage_host);

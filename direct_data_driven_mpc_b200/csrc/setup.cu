@@ -994,7 +994,7 @@ int ddmpc_set_option(ddmpc_set *set, const char *name, int value) {
     if (!set || !name) return fail(DDMPC_ERR_INVALID_ARG, "set_option: null argument");
     const std::string nm(name);
     if (nm == "closed_loop_path") {
-        if (value < DDMPC_PATH_AUTO || value > DDMPC_PATH_CVX) return fail(DDMPC_ERR_INVALID_ARG, "set_option: unknown path %d", value);
+        if (value < DDMPC_PATH_AUTO || value > DDMPC_PATH_TC) return fail(DDMPC_ERR_INVALID_ARG, "set_option: unknown path %d", value);
         set->opt_path = value;
     } else if (nm == "dmma_warps") {
         if (value != 1 && value != 2 && value != 4) return fail(DDMPC_ERR_INVALID_ARG, "set_option: dmma_warps must be 1, 2 or 4");

@@ -606,6 +606,11 @@ int closed_loop_cvx_try(const ddmpc_set *set, const ddmpc_plant *plant, int B, c
                         double *y_sys, int *status, int *iters, double *x_final, double tol, int max_iter,
                         cudaStream_t st);
 
+int closed_loop_tc_try(const ddmpc_set *set, const ddmpc_plant *plant, int B, const int *ctrl_idx, const double *x0,
+                       const double *u_past0, const double *y_past0, const double *u_s, const double *y_s,
+                       const double *w, uint64_t seed, uint64_t id0, double eps, int n_steps, double *u_sys,
+                       double *y_sys, int *status, int *iters, double *x_final, cudaStream_t st);
+
 int solve_batch_cvx_dmma(const ddmpc_set *set, int B, const int *ctrl_idx, const double *u_past, const double *y_past,
                          const double *u_s, const double *y_s, double tol, int max_iter, double *optimal_u, double *cost,
                          int *status, int *iters, double *t_out, cudaStream_t st);
@@ -858,6 +863,11 @@ int ddmpc_closed_loop_batch(const ddmpc_set *set, const ddmpc_plant *plant, int 
     const int nxp = plant->n_x;
     const int path = set->opt_path;
     if (path != DDMPC_PATH_GENERIC) {
+        if (path == DDMPC_PATH_TC) {   // opt-in: config-4 shape on tcgen05 / TMEM with TF32x3 arithmetic
+            const int rc = closed_loop_tc_try(set, plant, B, ctrl_idx, x0, u_past0, y_past0, u_s, y_s, w, noise_seed,
+                                              scenario_id0, noise_eps, n_steps, u_sys, y_sys, status, iters, x_final, st);
+            if (rc != -1) return rc;
+        }
         {   // shared CONVEX controller, four-tank n-step shape: slack check and box-row ADMM on the FP64 tensor cores
             const int rc = closed_loop_cvx_try(set, plant, B, ctrl_idx, x0, u_past0, y_past0, u_s, y_s, w, noise_seed,
                                                scenario_id0, noise_eps, n_steps, u_sys, y_sys, status, iters, x_final, tol,

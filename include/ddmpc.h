@@ -222,7 +222,9 @@ enum {
     DDMPC_PATH_PERLOOP = 4,   /* k_closed_loop_perloop: 8 lanes per loop, per-loop controllers / small batches    */
     DDMPC_PATH_DMMA = 5,      /* k_closed_loop_dmma: config-4 shapes, warp per 8 loops on the FP64 tensor cores   */
     DDMPC_PATH_GEMM = 6,      /* closed_loop_gemm: batch as the N dimension of FP64 tensor-core GEMMs             */
-    DDMPC_PATH_CVX = 7        /* k_closed_loop_cvx: shared CONVEX controller, slack check + ADMM on the tensor cores */
+    DDMPC_PATH_CVX = 7,       /* k_closed_loop_cvx: shared CONVEX controller, slack check + ADMM on the tensor cores */
+    DDMPC_PATH_TC = 8         /* k_closed_loop_tc: config-4 shape on tcgen05 / TMEM, TF32x3 arithmetic (u within ~5e-7 of
+                                 the FP64 kernels: inside the 1e-5 tolerance, but never selected automatically)           */
 };
 /* Per-set options: "closed_loop_path" (DDMPC_PATH_*), "dmma_warps" (1, 2 or 4: CTA size of the config-4 kernel),
  * "loops_per_thread" (0 = automatic, 1, 2: hybrid kernel), "solve_path" (0 = automatic, 1 = thread / CTA per solve kernels,

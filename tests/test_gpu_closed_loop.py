@@ -330,6 +330,36 @@ def test_config4_fused_dmma_kernel_vs_generic_and_oracle(n_mpc, n_steps, B):
         assert _rel(u1[b][:60], u_ref) < 1e-5 and _rel(y1[b][:60], y_ref) < 1e-5
 
 
+@pytest.mark.parametrize("n_steps,B", [(47, 300), (401, 140), (20, 128), (7, 5)])
+def test_config4_tcgen05_path_within_tolerance_of_fp64_kernel(n_steps, B):
+    """k_closed_loop_tc (opt-in path "tc": both products of an MPC iteration on tcgen05 / TMEM in TF32x3 arithmetic) against
+    the FP64 tensor-core kernel: 1e-5 relative on u and y (north-star tolerance; scripts/tf32x3_emulation.py predicts
+    ~5e-7), equal status and iteration counts; ragged batch, partial last block, Philox and uploaded noise, x_final."""
+    from direct_data_driven_mpc_b200 import ControllerSet, scenarios as S
+    sc = S.config4_batch(B, n_mpc_step=20)
+    prm, pl = sc["params"], sc["plant"]
+    cs = ControllerSet(prm["n"], 4, 4, sc["u_d"], sc["y_d"], prm["L"], prm["Q"], prm["R"], prm["eps_max"],
+                       prm["lamb_alpha"], prm["lamb_sigma"], prm["c"], 0, 1, 20, True)
+    r = np.random.default_rng(1)
+    x0 = sc["x0"] + 0.1 * r.normal(size=sc["x0"].shape)
+    u_s = sc["u_s"] * r.uniform(0.8, 1.2, (B, 1))
+    y_s = u_s @ pl.equilibrium_gain().T
+    w = pl.eps_max * r.uniform(-1, 1, (B, n_steps, 4))
+    for kw in (dict(noise_seed=5, scenario_id0=1000, noise_eps=0.002), dict(w=w)):
+        cs.set_option("closed_loop_path", "auto")
+        u1, y1, s1, i1, xf1 = cs.closed_loop(pl, x0, sc["u_past0"], sc["y_past0"], u_s, y_s, n_steps, want_x_final=True, **kw)
+        cs.set_option("closed_loop_path", "tc")
+        l0 = _launches()
+        u2, y2, s2, i2, xf2 = cs.closed_loop(pl, x0, sc["u_past0"], sc["y_past0"], u_s, y_s, n_steps, want_x_final=True, **kw)
+        assert _launches() - l0 == 1
+        assert int(s1.max()) == 0 and int(s2.max()) == 0 and (i1 == i2).all()
+        eu, ey = _rel(u2.cpu().numpy(), u1.cpu().numpy()), _rel(y2.cpu().numpy(), y1.cpu().numpy())
+        ex = _rel(xf2.cpu().numpy(), xf1.cpu().numpy())
+        assert eu < 1e-5 and ey < 1e-5 and ex < 1e-5, (eu, ey, ex)
+        assert eu > 1e-12                                          # (it really is the reduced-precision path)
+    cs.set_option("closed_loop_path", "auto")
+
+
 @pytest.mark.parametrize("c", [1.0, 0.3])
 def test_convex_fused_path_vs_generic_and_oracle(c):
     """CONVEX slack bound inside the fused kernel (slack rows on the tensor cores, warp-cooperative ADMM for
