@@ -1005,6 +1005,9 @@ int ddmpc_set_option(ddmpc_set *set, const char *name, int value) {
     } else if (nm == "cvx_ctas_per_sm") {
         if (value != 2 && value != 3) return fail(DDMPC_ERR_INVALID_ARG, "set_option: cvx_ctas_per_sm must be 2 or 3");
         set->opt_cvx_ctas = value;
+    } else if (nm == "tc_passes") {
+        if (value < 1 || value > 3) return fail(DDMPC_ERR_INVALID_ARG, "set_option: tc_passes must be 1, 2 or 3");
+        set->opt_tc_passes = value;
     } else if (nm == "solve_path") {
         if (value < 0 || value > 2) return fail(DDMPC_ERR_INVALID_ARG, "set_option: solve_path must be 0, 1 or 2");
         set->opt_solve = value;

@@ -20,13 +20,17 @@
 //   * the B operands (the constants Ku, Mblk, hi and lo: 196 KB) are resident in shared memory for the whole run, K-major,
 //     no swizzle, packed on the host as the exact shared-memory image (16-byte chunk c of row r at c * rows * 16 + r * 16:
 //     descriptor LBO = rows * 16, SBO = 128);
-//   * one elected thread issues the 63 + 39 tcgen05.mma of an iteration and commits to an mbarrier; the 128 owner threads
-//     then read the accumulators (tcgen05.ld), finish in FP64 (noise, trajectory stores: 32-byte aligned, 640 contiguous
-//     bytes per loop, block and array), split the results and write them back as the next operands.
+//   * one elected thread issues the 63 + 39 tcgen05.mma of an iteration and commits to an mbarrier; the epilogue then reads
+//     the accumulators (tcgen05.ld), finishes in FP64 (noise, trajectory stores: 32-byte aligned, 640 contiguous bytes per
+//     loop, block and array), splits the results and writes them back as the next operands.  A warp may only touch the
+//     TMEM lanes of its quarter (warp % 4), so the CTA has 16 warps: the four warps of a lane quarter share its 32 loops
+//     and take every fourth 8-column chunk each - with one warp per quarter the kernel was bound by the latency of that
+//     single instruction stream (0.275 ms, tensor pipe 19 % active).
 // Shared memory and TMEM are both used in full, so one CTA per SM: 16,384 loops = 128 CTAs = one wave on 148 SMs.
 //
 // Replaces the same reference code as k_closed_loop_dmma (dmma_loop.cu).
 #include <cstring>
+#include <type_traits>
 #include <vector>
 
 #include "common.cuh"
@@ -38,6 +42,8 @@ std::vector<double> block_map(const ddmpc_plant *pl, int s);   // gemm_loop.cu
 
 namespace tc {
 constexpr int NL = 128;                                    // loops per CTA = TMEM lanes
+constexpr int NG = 4;                                      // warps per TMEM lane quarter (epilogue groups)
+constexpr int NT = NL * NG;                                // threads per CTA
 constexpr int N_ = 20, M_ = 4, P_ = 4, NX = 20, NMPC = 20;
 constexpr int R = NMPC * M_, RY = NMPC * P_;               // 80 planned inputs / 80 outputs per block
 constexpr int K1 = 2 * R + M_ + P_, N1 = R;                // gain product: K = 168, N = 80
@@ -50,7 +56,7 @@ static_assert(C_SP + M_ + P_ == C_LO && C_D + N2 <= 512, "TMEM column budget");
 }  // namespace tc
 
 struct TcArgs {
-    int B, n_steps, nfull, rem, nth;
+    int B, n_steps, nfull, rem, nth, passes;
     const float *ops;                  // packed B operands: Ku hi, Ku lo, Mblk hi, Mblk lo (the shared-memory image)
     const double *Ku;                  // (L m, n_theta) FP64, for the steps of a partial last block
     const double *plant;               // A (20 x 20), B (20 x 4), C (4 x 20), D (4 x 4) FP64
@@ -81,12 +87,17 @@ __device__ __forceinline__ void tc_st8(uint32_t addr, const uint32_t (&v)[8]) {
                  "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
                  : "memory");
 }
-__device__ __forceinline__ void tc_ld8(uint32_t addr, uint32_t (&v)[8]) {
+// (asynchronous: tc_ld_wait() before the registers are used, so several loads can be in flight)
+__device__ __forceinline__ void tc_ld8_nowait(uint32_t addr, uint32_t (&v)[8]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                  : "r"(addr)
                  : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_ld8(uint32_t addr, uint32_t (&v)[8]) {
+    tc_ld8_nowait(addr, v);
+    tc_ld_wait();
 }
 // K-major, no swizzle: canonical layout ((8, n), 2) : ((1, SBO), LBO) in 16-byte units (cute/atom/mma_traits_sm100.hpp)
 __device__ __forceinline__ uint64_t tc_desc(uint32_t saddr, int rows) {
@@ -119,14 +130,15 @@ __device__ __forceinline__ double tc_unit32(uint32_t x) {
 }
 
 template <bool PHILOX>
-__global__ void __launch_bounds__(128, 1)
+__global__ void __launch_bounds__(tc::NT, 1)
 k_closed_loop_tc(const TcArgs a) {
     using namespace tc;
     extern __shared__ __align__(128) unsigned char tc_ops[];       // B operands: Ku hi | Ku lo | Mblk hi | Mblk lo
     __shared__ uint32_t tmem_base_s;
     __shared__ __align__(8) uint64_t mbar;
     const int tid = threadIdx.x, warp = tid >> 5;
-    int b = blockIdx.x * NL + tid;
+    const int lq = warp & 3, grp = warp >> 2;                      // TMEM lane quarter of this warp; its epilogue group
+    int b = blockIdx.x * NL + lq * 32 + (tid & 31);
     const bool live = b < a.B;
     if (!live) b = a.B - 1;                                        // dead lanes replay the last loop and never store
     const size_t f0 = (size_t)b * a.n_steps;
@@ -136,7 +148,7 @@ k_closed_loop_tc(const TcArgs a) {
     {   // constants -> shared memory (the packed buffer IS the shared-memory image)
         const uint4 *src = reinterpret_cast<const uint4 *>(a.ops);
         uint4 *dst = reinterpret_cast<uint4 *>(tc_ops);
-        for (int e = tid; e < OPS_BYTES / 16; e += NL) dst[e] = __ldg(src + e);
+        for (int e = tid; e < OPS_BYTES / 16; e += NT) dst[e] = __ldg(src + e);
     }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem(&tmem_base_s)), "r"(512));
@@ -149,7 +161,7 @@ k_closed_loop_tc(const TcArgs a) {
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;");
-    const uint32_t tb = tmem_base_s, tl = tb + ((uint32_t)(warp * 32) << 16);   // this thread's lane, column 0
+    const uint32_t tb = tmem_base_s, tl = tb + ((uint32_t)(lq * 32) << 16);   // this thread's lane, column 0
 
     // ---- initial state of the loop -> TMEM (hi and lo)
     auto put64 = [&](int col, const double *src, int n_valid) {    // 8 columns from FP64 values (zero beyond n_valid)
@@ -162,10 +174,10 @@ k_closed_loop_tc(const TcArgs a) {
         tc_st8(tl + col, h);
         tc_st8(tl + C_LO + col, l);
     };
-    for (int c = 0; c < XP / 8; ++c) put64(C_X + 8 * c, a.x0 + (size_t)b * NX + 8 * c, min(8, NX - 8 * c));
-    for (int c = 0; c < R / 8; ++c) put64(C_U + 8 * c, a.u_past0 + (size_t)b * R + 8 * c, 8);
-    for (int c = 0; c < RY / 8; ++c) put64(C_Y + 8 * c, a.y_past0 + (size_t)b * RY + 8 * c, 8);
-    {
+    for (int c = grp; c < XP / 8; c += NG) put64(C_X + 8 * c, a.x0 + (size_t)b * NX + 8 * c, min(8, NX - 8 * c));
+    for (int c = grp; c < R / 8; c += NG) put64(C_U + 8 * c, a.u_past0 + (size_t)b * R + 8 * c, 8);
+    for (int c = grp; c < RY / 8; c += NG) put64(C_Y + 8 * c, a.y_past0 + (size_t)b * RY + 8 * c, 8);
+    if (grp == NG - 1) {
         double sp[8];
 #pragma unroll
         for (int j = 0; j < M_; ++j) sp[j] = a.u_s[(size_t)b * M_ + j];
@@ -183,174 +195,246 @@ k_closed_loop_tc(const TcArgs a) {
     const uint32_t idesc1 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N1 >> 3) << 17) | (8u << 24);
     const uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N2 >> 3) << 17) | (8u << 24);
     const uint32_t sB1h = tc_smem(tc_ops), sB1l = sB1h + B1_BYTES, sB2h = sB1l + B1_BYTES, sB2l = sB2h + B2_BYTES;
-    // D += A_hi B_hi + A_hi B_lo + A_lo B_hi over `ks_n` k-steps of 8, then commit (elected thread only)
-    auto product = [&](int a_col, uint32_t sBh, uint32_t sBl, int rows, int ks_n, uint32_t idesc) {
-        uint32_t acc = 0u;
-#pragma unroll 1
-        for (int pass = 0; pass < 3; ++pass) {
-            const uint32_t acol = tb + (pass == 2 ? C_LO : 0) + a_col;
-            const uint32_t sB = pass == 1 ? sBl : sBh;
-#pragma unroll 1
-            for (int ks = 0; ks < ks_n; ++ks) {
-                tc_mma(tb + C_D, acol + 8 * ks, tc_desc(sB + ks * 2 * rows * 16, rows), idesc, acc);
-                acc = 1u;
+    // D += A_hi B_hi + A_hi B_lo + A_lo B_hi over KS k-steps of 8, then commit.  Called by the whole of warp 0 (a
+    // warp-uniform branch) with one lane elected inside: issued from a divergent `if (tid == 0)` the compiler wrapped
+    // every tcgen05.mma in an elect / branch loop and recomputed the descriptor with a multiply - ~12 dependent uniform-
+    // datapath instructions per MMA, which made the ISSUE of the 102 small MMAs of an iteration the critical path.  Here
+    // the k-step loop is unrolled and the descriptor of k-step ks is the base descriptor plus ks * 2 * rows in its
+    // 14-bit address field (16-byte units; shared-memory addresses stay below 2^18, so the field never carries).
+    const uint64_t dB1h = tc_desc(sB1h, N1), dB1l = tc_desc(sB1l, N1), dB2h = tc_desc(sB2h, N2), dB2l = tc_desc(sB2l, N2);
+    auto product = [&](auto ks_c, auto rows_c, int a_col, uint64_t dBh, uint64_t dBl, uint32_t idesc) {
+        constexpr int KS = decltype(ks_c)::value, ROWS = decltype(rows_c)::value;
+        uint32_t elected;
+        asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(elected));
+        if (elected) {
+#pragma unroll
+            for (int pass = 0; pass < 3; ++pass) {
+                if (pass < a.passes) {
+                    const uint32_t acol = tb + (pass == 2 ? C_LO : 0) + a_col;
+                    const uint64_t dB = pass == 1 ? dBl : dBh;
+#pragma unroll
+                    for (int ks = 0; ks < KS; ++ks)
+                        tc_mma(tb + C_D, acol + 8 * ks, dB + (uint64_t)(ks * 2 * ROWS), idesc, (pass | ks) ? 1u : 0u);
+                }
             }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tc_smem(&mbar)) : "memory");
         }
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tc_smem(&mbar)) : "memory");
+        __syncwarp();
     };
+    using KS1 = std::integral_constant<int, K1 / 8>;
+    using KS2 = std::integral_constant<int, K2 / 8>;
+    using RW1 = std::integral_constant<int, N1>;
+    using RW2 = std::integral_constant<int, N2>;
     uint32_t phase = 0u;
     double ylast[P_] = {0.0, 0.0, 0.0, 0.0};
+    constexpr int CPT = 3;                                         // 8-column chunks per thread and product (10 chunks / 4 groups)
+    // noise of step k (its 4 outputs are the 4 words of Philox call k: p = 4) or the caller's array
+    auto noise4 = [&](int k, double (&n4)[4]) {
+        if constexpr (PHILOX) {
+            uint32_t c0 = (uint32_t)k, c1 = 0u, c2 = sid_lo, c3 = sid_hi;
+#pragma unroll
+            for (int r = 0; r < 10; ++r) tc_philox_round(c0, c1, c2, c3, a.rk[2 * r], a.rk[2 * r + 1]);
+            n4[0] = a.eps * (2.0 * tc_unit32(c0) - 3.0); n4[1] = a.eps * (2.0 * tc_unit32(c1) - 3.0);
+            n4[2] = a.eps * (2.0 * tc_unit32(c2) - 3.0); n4[3] = a.eps * (2.0 * tc_unit32(c3) - 3.0);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) n4[i] = k < a.n_steps ? __ldg(a.w + (f0 + k) * P_ + i) : 0.0;
+        }
+    };
+    // The MMAs run asynchronously, so everything that is not on the chain accumulators -> next operands is done while
+    // the NEXT product is in flight: the trajectory stores and the Philox noise.  Per block:
+    //   wait(gain)  -> U operands -> barrier -> issue plant -> store u, draw the block's noise
+    //   wait(plant) -> Y, x operands -> barrier -> issue gain of the next block -> store y
+    if (warp == 0 && a.nfull > 0) product(KS1{}, RW1{}, C_U, dB1h, dB1l, idesc1);
     for (int blk = 0; blk < a.nfull; ++blk) {
         const int t0 = blk * NMPC;
-        // ---- the QP solve: U = Ku theta
-        if (tid == 0) product(C_U, sB1h, sB1l, N1, K1 / 8, idesc1);
+        // ---- the QP solve has finished: U = Ku theta
         tc_wait(&mbar, phase);
         phase ^= 1u;
         asm volatile("tcgen05.fence::after_thread_sync;");
-#pragma unroll 1
-        for (int c = 0; c < R / 8; ++c) {                          // 8 planned inputs = 2 steps at a time
-            uint32_t v[8], h[8], l[8];
-            tc_ld8(tl + C_D + 8 * c, v);
+        uint32_t vu[CPT][8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) tc_split(__uint_as_float(v[j]), h[j], l[j]);
-            tc_st8(tl + C_U + 8 * c, h);
-            tc_st8(tl + C_LO + C_U + 8 * c, l);
-            if (live) {
-                double *dst = a.u_sys + (f0 + t0) * M_ + 8 * c;    // 32-byte aligned: a step is 4 doubles
-                asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(dst), "d"((double)__uint_as_float(v[0])),
-                             "d"((double)__uint_as_float(v[1])), "d"((double)__uint_as_float(v[2])), "d"((double)__uint_as_float(v[3]))
-                             : "memory");
-                asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4), "d"((double)__uint_as_float(v[4])),
-                             "d"((double)__uint_as_float(v[5])), "d"((double)__uint_as_float(v[6])), "d"((double)__uint_as_float(v[7]))
-                             : "memory");
+        for (int i = 0; i < CPT; ++i)
+            if (grp + NG * i < R / 8) tc_ld8_nowait(tl + C_D + 8 * (grp + NG * i), vu[i]);
+        tc_ld_wait();
+#pragma unroll
+        for (int i = 0; i < CPT; ++i) {                            // 8 planned inputs = 2 steps per chunk
+            const int c = grp + NG * i;
+            if (c < R / 8) {
+                uint32_t h[8], l[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) tc_split(__uint_as_float(vu[i][j]), h[j], l[j]);
+                tc_st8(tl + C_U + 8 * c, h);
+                tc_st8(tl + C_LO + C_U + 8 * c, l);
             }
         }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;");
         __syncthreads();
         asm volatile("tcgen05.fence::after_thread_sync;");
-        // ---- 20 plant steps: [Y; x+] = Mblk [x; U]
-        if (tid == 0) product(C_X, sB2h, sB2l, N2, K2 / 8, idesc2);
-        tc_wait(&mbar, phase);
-        phase ^= 1u;
-        asm volatile("tcgen05.fence::after_thread_sync;");
-#pragma unroll 1
-        for (int c = 0; c < RY / 8; ++c) {                         // 8 outputs = 2 steps at a time
-            uint32_t v[8], h[8], l[8];
-            tc_ld8(tl + C_D + 8 * c, v);
-            double y[8];
+        // ---- 20 plant steps: [Y; x+] = Mblk [x; U]   (in flight while the inputs are recorded and the noise is drawn)
+        if (warp == 0) product(KS2{}, RW2{}, C_X, dB2h, dB2l, idesc2);
+        double yv[CPT][8];
 #pragma unroll
-            for (int s2 = 0; s2 < 2; ++s2) {
-                const int k = t0 + 2 * c + s2;                     // step: its 4 noise words are Philox call k (p = 4)
-                double n4[4];
-                if constexpr (PHILOX) {
-                    uint32_t c0 = (uint32_t)k, c1 = 0u, c2 = sid_lo, c3 = sid_hi;
-#pragma unroll
-                    for (int r = 0; r < 10; ++r) tc_philox_round(c0, c1, c2, c3, a.rk[2 * r], a.rk[2 * r + 1]);
-                    n4[0] = a.eps * (2.0 * tc_unit32(c0) - 3.0); n4[1] = a.eps * (2.0 * tc_unit32(c1) - 3.0);
-                    n4[2] = a.eps * (2.0 * tc_unit32(c2) - 3.0); n4[3] = a.eps * (2.0 * tc_unit32(c3) - 3.0);
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) n4[i] = __ldg(a.w + (f0 + k) * P_ + i);
+        for (int i = 0; i < CPT; ++i) {
+            const int c = grp + NG * i;
+            if (c < R / 8) {
+                if (live) {
+                    double *dst = a.u_sys + (f0 + t0) * M_ + 8 * c;    // 32-byte aligned: a step is 4 doubles
+                    asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(dst), "d"((double)__uint_as_float(vu[i][0])),
+                                 "d"((double)__uint_as_float(vu[i][1])), "d"((double)__uint_as_float(vu[i][2])),
+                                 "d"((double)__uint_as_float(vu[i][3]))
+                                 : "memory");
+                    asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4), "d"((double)__uint_as_float(vu[i][4])),
+                                 "d"((double)__uint_as_float(vu[i][5])), "d"((double)__uint_as_float(vu[i][6])),
+                                 "d"((double)__uint_as_float(vu[i][7]))
+                                 : "memory");
                 }
+                double n4[4];
+                noise4(t0 + 2 * c, n4);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) y[4 * s2 + i] = (double)__uint_as_float(v[4 * s2 + i]) + n4[i];
-            }
+                for (int j = 0; j < 4; ++j) yv[i][j] = n4[j];
+                noise4(t0 + 2 * c + 1, n4);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) tc_split64(y[j], h[j], l[j]);
-            tc_st8(tl + C_Y + 8 * c, h);
-            tc_st8(tl + C_LO + C_Y + 8 * c, l);
-            if (live) {
-                double *dst = a.y_sys + (f0 + t0) * P_ + 8 * c;
-                asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(dst), "d"(y[0]), "d"(y[1]), "d"(y[2]), "d"(y[3]) : "memory");
-                asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4), "d"(y[4]), "d"(y[5]), "d"(y[6]), "d"(y[7]) : "memory");
-            }
-            if (c == RY / 8 - 1) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) ylast[i] = y[4 + i];
+                for (int j = 0; j < 4; ++j) yv[i][4 + j] = n4[j];
             }
         }
-#pragma unroll 1
-        for (int c = 0; c < XP / 8; ++c) {                         // next state: rows 80..99 of the product (100..111 are padding)
-            uint32_t v[8], h[8], l[8];
-            tc_ld8(tl + C_D + RY + 8 * c, v);
+        tc_wait(&mbar, phase);
+        phase ^= 1u;
+        asm volatile("tcgen05.fence::after_thread_sync;");
+        uint32_t vy[CPT][8], vx[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                h[j] = l[j] = 0u;
-                if (8 * c + j < NX) tc_split(__uint_as_float(v[j]), h[j], l[j]);
+        for (int i = 0; i < CPT; ++i)
+            if (grp + NG * i < RY / 8) tc_ld8_nowait(tl + C_D + 8 * (grp + NG * i), vy[i]);
+        if (NG - 1 - grp < XP / 8) tc_ld8_nowait(tl + C_D + RY + 8 * (NG - 1 - grp), vx);
+        tc_ld_wait();
+#pragma unroll
+        for (int i = 0; i < CPT; ++i) {                            // 8 outputs = 2 steps per chunk: y = product + noise
+            const int c = grp + NG * i;
+            if (c < RY / 8) {
+                uint32_t h[8], l[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    yv[i][j] = (double)__uint_as_float(vy[i][j]) + yv[i][j];
+                    tc_split((float)yv[i][j], h[j], l[j]);         // (hi + lo carry 22 bits: the FP32 value is enough)
+                }
+                tc_st8(tl + C_Y + 8 * c, h);
+                tc_st8(tl + C_LO + C_Y + 8 * c, l);
             }
-            tc_st8(tl + C_X + 8 * c, h);
-            tc_st8(tl + C_LO + C_X + 8 * c, l);
+        }
+        {   // next state: rows 80..99 of the product (100..111 are padding); one chunk for each of three groups
+            const int c = NG - 1 - grp;
+            if (c < XP / 8) {
+                uint32_t h[8], l[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    h[j] = l[j] = 0u;
+                    if (8 * c + j < NX) tc_split(__uint_as_float(vx[j]), h[j], l[j]);
+                }
+                tc_st8(tl + C_X + 8 * c, h);
+                tc_st8(tl + C_LO + C_X + 8 * c, l);
+            }
         }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;");
         __syncthreads();
         asm volatile("tcgen05.fence::after_thread_sync;");
+        // ---- the solve of the next block (in flight while the outputs are recorded)
+        if (warp == 0 && blk + 1 < a.nfull) product(KS1{}, RW1{}, C_U, dB1h, dB1l, idesc1);
+        if (live) {
+#pragma unroll
+            for (int i = 0; i < CPT; ++i) {
+                const int c = grp + NG * i;
+                if (c < RY / 8) {
+                    double *dst = a.y_sys + (f0 + t0) * P_ + 8 * c;
+                    asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(dst), "d"(yv[i][0]), "d"(yv[i][1]), "d"(yv[i][2]),
+                                 "d"(yv[i][3])
+                                 : "memory");
+                    asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4), "d"(yv[i][4]), "d"(yv[i][5]),
+                                 "d"(yv[i][6]), "d"(yv[i][7])
+                                 : "memory");
+                }
+            }
+        }
     }
-    // ---- state of the loop back in FP64 (hi + lo)
+    // ---- last, partial block (controller_operation.py:278): ONE solve for its rem * m planned inputs, then rem plant steps
+    //      in FP64 on the CUDA cores (rem < 20; 401 steps leave one).  The four warps of a lane quarter split theta's 21
+    //      chunks between them (theta is read back from TMEM as hi + lo); the owner warp adds the partial sums.
+    __shared__ double part_s[NG][M_][NL];
+    const int tloop = lq * 32 + (tid & 31);
     double x[NX];
+    if (grp == 0) {
 #pragma unroll
-    for (int c = 0; c < XP / 8; ++c) {
-        uint32_t h[8], l[8];
-        tc_ld8(tl + C_X + 8 * c, h);
-        tc_ld8(tl + C_LO + C_X + 8 * c, l);
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-            if (8 * c + j < NX) x[8 * c + j] = (double)__uint_as_float(h[j]) + (double)__uint_as_float(l[j]);
-    }
-    if (a.rem > 0) {
-        // ---- last, partial block (controller_operation.py:278): one solve for its rem * m planned inputs, then rem plant
-        //      steps, in FP64 on the CUDA cores (rem < 20; 401 steps leave one)
-        double u_t[R];
-        for (int r = 0; r < a.rem * M_; ++r) u_t[r] = 0.0;
-        for (int c = 0; c < K1 / 8; ++c) {
+        for (int c = 0; c < XP / 8; ++c) {
             uint32_t h[8], l[8];
-            tc_ld8(tl + C_U + 8 * c, h);
-            tc_ld8(tl + C_LO + C_U + 8 * c, l);
+            tc_ld8_nowait(tl + C_X + 8 * c, h);
+            tc_ld8_nowait(tl + C_LO + C_X + 8 * c, l);
+            tc_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (8 * c + j < NX) x[8 * c + j] = (double)__uint_as_float(h[j]) + (double)__uint_as_float(l[j]);
+        }
+    }
+    const double *pA = a.plant, *pB = pA + NX * NX, *pC = pB + NX * M_, *pD = pC + P_ * NX;
+    for (int s = 0; s < a.rem; ++s) {
+        const int k = a.nfull * NMPC + s;
+        double acc[M_] = {0.0, 0.0, 0.0, 0.0};
+        for (int c = grp; c < K1 / 8; c += NG) {
+            uint32_t h[8], l[8];
+            tc_ld8_nowait(tl + C_U + 8 * c, h);
+            tc_ld8_nowait(tl + C_LO + C_U + 8 * c, l);
+            tc_ld_wait();
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const double th = (double)__uint_as_float(h[j]) + (double)__uint_as_float(l[j]);
-                for (int r = 0; r < a.rem * M_; ++r) u_t[r] = fma(__ldg(a.Ku + (size_t)r * a.nth + 8 * c + j), th, u_t[r]);
+#pragma unroll
+                for (int i = 0; i < M_; ++i) acc[i] = fma(__ldg(a.Ku + (size_t)(s * M_ + i) * a.nth + 8 * c + j), th, acc[i]);
             }
         }
-        const double *pA = a.plant, *pB = pA + NX * NX, *pC = pB + NX * M_, *pD = pC + P_ * NX;
-        for (int s = 0; s < a.rem; ++s) {
-            const int k = a.nfull * NMPC + s;
-            double n4[4];
-            if constexpr (PHILOX) {
-                uint32_t c0 = (uint32_t)k, c1 = 0u, c2 = sid_lo, c3 = sid_hi;
 #pragma unroll
-                for (int r = 0; r < 10; ++r) tc_philox_round(c0, c1, c2, c3, a.rk[2 * r], a.rk[2 * r + 1]);
-                n4[0] = a.eps * (2.0 * tc_unit32(c0) - 3.0); n4[1] = a.eps * (2.0 * tc_unit32(c1) - 3.0);
-                n4[2] = a.eps * (2.0 * tc_unit32(c2) - 3.0); n4[3] = a.eps * (2.0 * tc_unit32(c3) - 3.0);
-            } else {
-                for (int i = 0; i < 4; ++i) n4[i] = __ldg(a.w + (f0 + k) * P_ + i);
-            }
-            const double *us = u_t + s * M_;
+        for (int i = 0; i < M_; ++i) part_s[grp][i][tloop] = acc[i];
+        __syncthreads();
+        if (grp == 0) {
+            double n4[4], us[M_];
+            noise4(k, n4);
+#pragma unroll
+            for (int i = 0; i < M_; ++i) us[i] = (part_s[0][i][tloop] + part_s[1][i][tloop]) + (part_s[2][i][tloop] + part_s[3][i][tloop]);
             double y[P_], xn[NX];
-            for (int i = 0; i < P_; ++i) {
-                double acc = 0.0;
 #pragma unroll
-                for (int j = 0; j < NX; ++j) acc = fma(__ldg(pC + i * NX + j), x[j], acc);
-                for (int j = 0; j < M_; ++j) acc = fma(__ldg(pD + i * M_ + j), us[j], acc);
-                y[i] = acc + n4[i];
+            for (int i = 0; i < P_; ++i) {
+                double a0 = 0.0;
+#pragma unroll
+                for (int j = 0; j < NX; ++j) a0 = fma(__ldg(pC + i * NX + j), x[j], a0);
+#pragma unroll
+                for (int j = 0; j < M_; ++j) a0 = fma(__ldg(pD + i * M_ + j), us[j], a0);
+                y[i] = a0 + n4[i];
             }
 #pragma unroll
             for (int i = 0; i < NX; ++i) {
-                double acc = 0.0;
+                double a0 = 0.0;
 #pragma unroll
-                for (int j = 0; j < NX; ++j) acc = fma(__ldg(pA + i * NX + j), x[j], acc);
-                for (int j = 0; j < M_; ++j) acc = fma(__ldg(pB + i * M_ + j), us[j], acc);
-                xn[i] = acc;
+                for (int j = 0; j < NX; ++j) a0 = fma(__ldg(pA + i * NX + j), x[j], a0);
+#pragma unroll
+                for (int j = 0; j < M_; ++j) a0 = fma(__ldg(pB + i * M_ + j), us[j], a0);
+                xn[i] = a0;
             }
 #pragma unroll
             for (int i = 0; i < NX; ++i) x[i] = xn[i];
+#pragma unroll
             for (int i = 0; i < P_; ++i) ylast[i] = y[i];
             if (live) {
+#pragma unroll
                 for (int i = 0; i < M_; ++i) a.u_sys[(f0 + k) * M_ + i] = us[i];
+#pragma unroll
                 for (int i = 0; i < P_; ++i) a.y_sys[(f0 + k) * P_ + i] = y[i];
             }
         }
+        __syncthreads();                                           // part_s is reused by the next tail step
+    }
+    if (grp != 0) {                                                // the owner warp of each lane quarter reports the loop
+        asm volatile("tcgen05.fence::before_thread_sync;");
+        __syncthreads();
+        return;
     }
     bool finite = true;
 #pragma unroll
@@ -430,6 +514,7 @@ int closed_loop_tc_try(const ddmpc_set *set, const ddmpc_plant *plant, int B, co
     }
     TcArgs a{};
     a.B = B; a.n_steps = n_steps; a.nfull = n_steps / NMPC; a.rem = n_steps % NMPC; a.nth = d.nth;
+    a.passes = set->opt_tc_passes;
     a.ops = reinterpret_cast<const float *>(set->tc_ws.p);
     a.plant = reinterpret_cast<const double *>((const char *)set->tc_ws.p + OPS_BYTES);
     a.Ku = pl.Ku.d();
@@ -446,8 +531,8 @@ int closed_loop_tc_try(const ddmpc_set *set, const ddmpc_plant *plant, int B, co
         DDMPC_CUDA(cudaFuncSetAttribute(k_closed_loop_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, OPS_BYTES));
     }
     const int grid = ceil_div(B, NL);
-    if (w) k_closed_loop_tc<false><<<grid, NL, OPS_BYTES, st>>>(a);
-    else k_closed_loop_tc<true><<<grid, NL, OPS_BYTES, st>>>(a);
+    if (w) k_closed_loop_tc<false><<<grid, NT, OPS_BYTES, st>>>(a);
+    else k_closed_loop_tc<true><<<grid, NT, OPS_BYTES, st>>>(a);
     DDMPC_LAUNCH_CHECK();
     return DDMPC_OK;
 }
