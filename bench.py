@@ -454,7 +454,35 @@ def secondary_config4(dev, B=16384, fp64_peak=None, dmma_warps=None):
         tf = flops / (ms * 1e-3) / 1e12
         out[f"n_mpc_{nmpc}"] = {"loop_ms": ms, "solves_per_s": solves / (ms * 1e-3), "setup_ms": setup_ms,
                                 "status_max": int(st.max().item()), "final_tracking_error_max": err,
-                                "executed_tflops": tf, "frac_of_fp64_peak": tf / fp64_peak if fp64_peak else None}
+                                "executed_tflops": tf, "frac_of_fp64_peak": tf / fp64_peak if fp64_peak else None,
+                                "kernel": "k_closed_loop_dmma (FP64 mma.sync m8n8k4)"}
+        if nmpc == 20:
+            # the same workload on the 5th-generation tensor cores (opt-in path "tc": tcgen05 kind::tf32 with TF32x3 error
+            # compensation, loop state resident in TMEM, csrc/tc_loop.cu), and how far its trajectories are from the FP64 ones
+            try:
+                u64, y64 = bufs[0].clone(), bufs[1].clone()
+                cs.set_option("closed_loop_path", "tc")
+                for _ in range(3):
+                    _, _, st2, it2 = run()
+                e0.record()
+                for _ in range(reps):
+                    run()
+                e1.record()
+                torch.cuda.synchronize()
+                ms2 = e0.elapsed_time(e1) / reps
+                du = float((bufs[0] - u64).abs().max() / u64.abs().max())
+                dy = float((bufs[1] - y64).abs().max() / y64.abs().max())
+                # tcgen05.mma issued per 128 loops and iteration: 3 passes x (21 k-steps of 128 x 80 x 8 + 13 of 128 x 112 x 8)
+                mma_flops = 2.0 * 3 * (21 * 128 * 80 * 8 + 13 * 128 * 112 * 8) * (B / 128) * (N_STEPS // 20)
+                out["n_mpc_20_tcgen05"] = {
+                    "loop_ms": ms2, "solves_per_s": int(it2.sum().item()) / (ms2 * 1e-3), "status_max": int(st2.max().item()),
+                    "speedup_vs_fp64_kernel": ms / ms2, "max_rel_diff_u_vs_fp64_kernel": du, "max_rel_diff_y_vs_fp64_kernel": dy,
+                    "tolerance": "north star: 1e-5 relative on u", "tf32_tflops_issued": mma_flops / (ms2 * 1e-3) / 1e12,
+                    "hbm_write_gbs": B * N_STEPS * 8 * 8 / (ms2 * 1e-3) / 1e9,
+                    "kernel": "k_closed_loop_tc (tcgen05.mma kind::tf32, A operand and accumulators in TMEM)"}
+                cs.set_option("closed_loop_path", "auto")
+            except Exception as exc:  # pragma: no cover
+                out["n_mpc_20_tcgen05"] = {"error": repr(exc)}
         del cs
     return out
 

@@ -718,7 +718,7 @@ def test_nonfinite_inputs_flag_only_their_own_loops():
         us[258, 1] = -np.inf
         up0[519, 11] = np.nan
         expect[[3, 258, 519]] = 3
-        for env in ("auto", "generic"):
+        for env in ("auto", "generic") + (("tc",) if n_mpc == 20 else ()):
             c4.set_option("closed_loop_path", env)
             u, y, st, it = c4.closed_loop(pl, xs, up0, sc["y_past0"], us, sc["y_s"], 45, noise_seed=2, noise_eps=0.002)
             assert np.array_equal(st.cpu().numpy(), expect), (n_mpc, env, np.nonzero(st.cpu().numpy() != expect)[0][:8])
