@@ -62,9 +62,37 @@ __device__ __forceinline__ double colmax8(double v) {   // max over the 8 lanes 
 }
 __device__ __forceinline__ double clipd(double v, double lo, double hi) { return fmin(fmax(v, lo), hi); }
 
-// acc (rows of this warp x 32 problems) = Phi[rows, :] * D, D = sm.d[buf]
-__device__ __forceinline__ void phi_times_d(const double (&aPhi)[2][CV_KS], const double (*D)[CV_DS], int ks_n, int g, int q,
-                                            double2 (&acc)[2][CV_NT]) {
+// acc (rows of this warp x 32 problems) = Phi[rows, :] * D, D = sm.d[buf]; n-tile nt is computed when bit nt of `on` is set
+// (warp-uniform), the accumulators of the others stay zero
+// A operand of the ADMM iteration: this warp's rows of Phi, either resident in registers (64 per thread) or streamed from
+// the zero-padded 64 x 64 copy (L1-resident; the closed-loop kernel's register budget goes to its per-block path).
+struct PhiRegs {
+    double a[2][CV_KS];
+    __device__ __forceinline__ void load(const double *Phi, int nb, int warp, int g, int q) {
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+            const int r = 16 * warp + 8 * mt + g;
+#pragma unroll
+            for (int ks = 0; ks < CV_KS; ++ks) {
+                const int c = 4 * ks + q;
+                a[mt][ks] = (r < nb && c < nb) ? __ldg(Phi + (size_t)r * nb + c) : 0.0;
+            }
+        }
+    }
+    __device__ __forceinline__ double get(int mt, int ks) const { return a[mt][ks]; }
+};
+struct PhiStream {
+    const double *row[2];
+    __device__ __forceinline__ void load(const double *Phi64, int warp, int g, int q) {
+        row[0] = Phi64 + (size_t)(16 * warp + g) * CV_NR + q;
+        row[1] = row[0] + 8 * CV_NR;
+    }
+    __device__ __forceinline__ double get(int mt, int ks) const { return __ldg(row[mt] + 4 * ks); }
+};
+
+template <class PhiA>
+__device__ __forceinline__ void phi_times_d(const PhiA &aPhi, const double (*D)[CV_DS], int ks_n, int g, int q,
+                                            double2 (&acc)[2][CV_NT], unsigned on = 0xfu) {
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
@@ -72,13 +100,15 @@ __device__ __forceinline__ void phi_times_d(const double (&aPhi)[2][CV_KS], cons
 #pragma unroll
     for (int ks = 0; ks < CV_KS; ++ks) {
         if (ks < ks_n) {
-            double b[CV_NT];
 #pragma unroll
-            for (int nt = 0; nt < CV_NT; ++nt) b[nt] = D[4 * ks + q][8 * nt + g];
+            const double a0 = aPhi.get(0, ks), a1 = aPhi.get(1, ks);
 #pragma unroll
-            for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-                for (int nt = 0; nt < CV_NT; ++nt) dmma884(acc[mt][nt], aPhi[mt][ks], b[nt]);
+            for (int nt = 0; nt < CV_NT; ++nt)
+                if ((on >> nt) & 1u) {
+                    const double b = D[4 * ks + q][8 * nt + g];
+                    dmma884(acc[0][nt], a0, b);
+                    dmma884(acc[1][nt], a1, b);
+                }
         }
     }
 }
@@ -89,7 +119,8 @@ __device__ __forceinline__ void phi_times_d(const double (&aPhi)[2][CV_KS], cons
 //   sm.su  s_unc (C-fragment order), sm.thr thresholds: written by the caller, visible after the first barrier in here
 // Out: t = Phi d at the fixed point (zero for inactive problems), iterations per problem (1 when inactive), bits of the
 // problems that hit max_iter.  Ends with a barrier: sm.d may be reused by the caller.
-__device__ __forceinline__ void admm_cta(const double (&aPhi)[2][CV_KS], const double (&lo)[2], const double (&hi)[2],
+template <class PhiA>
+__device__ __forceinline__ void admm_cta(const PhiA &aPhi, const double (&lo)[2], const double (&hi)[2],
                                          unsigned act, int ks_n, int max_iter, AdmmSmem &sm, double2 (&t)[2][CV_NT],
                                          int (&iters)[CV_NT][2], unsigned &inacc) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, q = lane & 3;
@@ -108,6 +139,9 @@ __device__ __forceinline__ void admm_cta(const double (&aPhi)[2][CV_KS], const d
     for (int nt = 0; nt < CV_NT; ++nt) iters[nt][0] = iters[nt][1] = 1;
     if (tid < CV_NL) sm.red[0][tid] = sm.red[1][tid] = sm.red[2][tid] = 0ull;
     unsigned frozen = ~act & 0xffu;
+    // n-tiles whose eight problems are all frozen stop being multiplied one iteration later (by then both copies of d hold
+    // their final columns)
+    unsigned skip = 0u, full_prev = 0u;
     int cur = 0, it = 0;
     while (true) {
         const int all = __syncthreads_and(frozen == 0xffu);          // also: d[cur], su, thr, red slots are visible
@@ -115,7 +149,7 @@ __device__ __forceinline__ void admm_cta(const double (&aPhi)[2][CV_KS], const d
         ++it;
         const int slot = it % 3;
         double2 acc[2][CV_NT];
-        phi_times_d(aPhi, sm.d[cur], ks_n, g, q, acc);
+        phi_times_d(aPhi, sm.d[cur], ks_n, g, q, acc, ~skip & 0xfu);
         double res[CV_NT][2];
 #pragma unroll
         for (int nt = 0; nt < CV_NT; ++nt) res[nt][0] = res[nt][1] = 0.0;
@@ -160,6 +194,11 @@ __device__ __forceinline__ void admm_cta(const double (&aPhi)[2][CV_KS], const d
                 iters[nt][h] = it;
                 if (__longlong_as_double((long long)sm.red[slot][p]) <= sm.thr[p]) frozen |= 1u << (2 * nt + h);
             }
+        skip = full_prev;
+        full_prev = 0u;
+#pragma unroll
+        for (int nt = 0; nt < CV_NT; ++nt)
+            if (__all_sync(0xffffffffu, ((frozen >> (2 * nt)) & 3u) == 3u)) full_prev |= 1u << nt;
         // the slot of iteration it + 1 was last read in iteration it - 2: clear it (visible after the next barrier)
         if (tid < CV_NL) sm.red[(it + 1) % 3][tid] = 0ull;
         cur ^= 1;
@@ -240,18 +279,15 @@ k_admm_dmma(int B, int nb, const double *__restrict__ S, const double *__restric
     AdmmSmem &sm = *reinterpret_cast<AdmmSmem *>(cv_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, q = lane & 3;
     const int b0 = blockIdx.x * CV_NL, ks_n = (nb + 3) / 4;
-    double aPhi[2][CV_KS], lo[2], hi[2];
+    PhiRegs aPhi;
+    double lo[2], hi[2];
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt) {
         const int r = 16 * warp + 8 * mt + g;
         lo[mt] = r < nb ? blo[r] : -INFINITY;
         hi[mt] = r < nb ? bhi[r] : INFINITY;
-#pragma unroll
-        for (int ks = 0; ks < CV_KS; ++ks) {
-            const int c = 4 * ks + q;
-            aPhi[mt][ks] = (r < nb && c < nb) ? __ldg(Phi + (size_t)r * nb + c) : 0.0;
-        }
     }
+    aPhi.load(Phi, nb, warp, g, q);
     double2 su[2][CV_NT];
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt)
@@ -386,7 +422,7 @@ struct CvxMaps {
 
 struct CvxArgs {
     int B, n_steps, nb, nth, n_tail, max_iter;
-    const double *Ku, *Ks, *Phi, *Psi, *blo, *bhi, *bmax;
+    const double *Ku, *Ks, *Phi, *Phi64, *Psi, *blo, *bhi, *bmax;
     const double *x0, *u_past0, *y_past0, *u_s, *y_s, *w;
     unsigned long long id0;
     double eps, tol;
@@ -395,10 +431,12 @@ struct CvxArgs {
     uint32_t rk[20];
 };
 
+constexpr int CV_FS = 40;      // row stride of the FP32 window copy (rows q = 0..3 land on disjoint banks)
 struct CvxSmem {
     double th[2][16][CV_DS];   // measurement window [U (8 rows); Y (8 rows)] x 32 loops, by block parity
     double sp[4][CV_DS];       // set-points [u_s; y_s]
     double x[4][CV_DS];        // plant state
+    float thf[2][16][CV_FS];   // FP32 copy of the windows: B operand of the TF32 screen
     AdmmSmem admm;
 };
 
@@ -413,6 +451,21 @@ __device__ __forceinline__ void cv_philox_round(uint32_t &c0, uint32_t &c1, uint
 __device__ __forceinline__ double cv_unit32(uint32_t x) {
     return __hiloint2double((int)(0x3FF00000u | (x >> 12)), (int)(x << 20));
 }
+
+// TF32 tensor-core product of the slack-row screen (mma.sync m16n8k8; the operands' low 13 mantissa bits are ignored).
+__device__ __forceinline__ void mma_tf32(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                         uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+constexpr float kScreenRel = 1.0f / 256.0f;
+constexpr uint32_t kAbs = 0x7fffffffu;
 
 // MINB = CTAs per SM the register allocation is held to (2: no spills; 3, 4: the ADMM section spills, the per-block path
 // does not - more resident warps for the latency-bound steady state).
@@ -437,21 +490,32 @@ k_closed_loop_cvx(const __grid_constant__ CvxMaps maps, const CvxArgs a) {
         const double2 yp = *reinterpret_cast<const double2 *>(a.y_past0 + (size_t)b * 8 + 2 * q);
         sm.th[0][2 * q][lcol] = up.x; sm.th[0][2 * q + 1][lcol] = up.y;
         sm.th[0][8 + 2 * q][lcol] = yp.x; sm.th[0][8 + 2 * q + 1][lcol] = yp.y;
+        sm.thf[0][2 * q][lcol] = (float)up.x; sm.thf[0][2 * q + 1][lcol] = (float)up.y;
+        sm.thf[0][8 + 2 * q][lcol] = (float)yp.x; sm.thf[0][8 + 2 * q + 1][lcol] = (float)yp.y;
         sm.x[q][lcol] = a.x0[(size_t)b * 4 + q];
         sm.sp[q][lcol] = q < 2 ? a.u_s[(size_t)b * 2 + q] : a.y_s[(size_t)b * 2 + (q - 2)];
     }
     if (tid < CV_NL) { sm.admm.extra[tid] = 0; sm.admm.stat[tid] = DDMPC_SOLVE_OPTIMAL; }
     // ---- A fragments that stay in registers: gain rows (8 x 20), slack rows of this warp (16 x 20), plant block map
-    double aKu[NSPK], aKs[2][NSPK], aMb[2][3], lo[2], hi[2];
+    double aKu[NSPK], aMb[2][3];
+    uint32_t fKs[2][3][2], spb[CV_NT];                               // TF32 screen: slack rows, set-points
 #pragma unroll
     for (int ks = 0; ks < NSPK; ++ks) aKu[ks] = __ldg(a.Ku + (size_t)g * a.nth + 4 * ks + q);
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt) {
         const int r = 16 * warp + 8 * mt + g;
-        lo[mt] = r < nb ? a.blo[r] : -INFINITY;
-        hi[mt] = r < nb ? a.bhi[r] : INFINITY;
 #pragma unroll
-        for (int ks = 0; ks < NSPK; ++ks) aKs[mt][ks] = r < nb ? __ldg(a.Ks + (size_t)r * a.nth + 4 * ks + q) : 0.0;
+        for (int s8 = 0; s8 < 3; ++s8)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int c = 8 * s8 + q + 4 * h;
+                fKs[mt][s8][h] = to_tf32((r < nb && c < a.nth) ? (float)__ldg(a.Ks + (size_t)r * a.nth + c) : 0.f);
+            }
+    }
+#pragma unroll
+    for (int nt = 0; nt < CV_NT; ++nt) {
+        const int bb = min(blockIdx.x * CV_NL + 8 * nt + g, a.B - 1);
+        spb[nt] = __float_as_uint((float)(q < 2 ? a.u_s[(size_t)bb * 2 + q] : a.y_s[(size_t)bb * 2 + (q - 2)]));
     }
     auto load_map = [&](const double (&Mm)[12][12]) {
 #pragma unroll
@@ -461,7 +525,9 @@ k_closed_loop_cvx(const __grid_constant__ CvxMaps maps, const CvxArgs a) {
     };
     load_map(maps.Mb);
     const int nblk = (a.n_steps + 3) / 4;
-    const double bound = a.bhi[0];                                   // pure CONVEX: every box row is [-c eps_max, c eps_max]
+    uint32_t pw0 = 0u, pw1 = 0u, pw2 = 0u, pw3 = 0u;                 // Philox words of the current pair of blocks
+    // pure CONVEX: every box row is [-c eps_max, c eps_max]; the screen compares against the bound rounded towards zero
+    const unsigned bound_bits = __float_as_uint(__double2float_rz(a.bhi[0]));
     // One MPC iteration.  The window buffers alternate with the block parity, which is a compile-time constant here (the
     // loop below is unrolled by two) so that every shared-memory address is a fixed offset.
     auto block = [&](auto parity, const int t) {
@@ -473,12 +539,19 @@ k_closed_loop_cvx(const __grid_constant__ CvxMaps maps, const CvxArgs a) {
         {
             double n0, n1;
             if constexpr (PHILOX) {
-                // noise word (4 t + q) * 2 + i is word 2 (q & 1) + i of Philox call 2 t + (q >> 1)   (solve.cu)
-                uint32_t c0 = 2u * (unsigned)t + (unsigned)(q >> 1), c1 = 0u, c2 = sid_lo, c3 = sid_hi;
+                // noise word (4 t + q) * 2 + i is word 2 (q & 1) + i of Philox call 2 t + (q >> 1)   (solve.cu).  The four
+                // lanes of a loop draw the four calls of a PAIR of blocks once (lane q: call 2 t + q, t even) and hand
+                // the words round.
+                if constexpr (cur == 0) {
+                    pw0 = 2u * (unsigned)t + (unsigned)q; pw1 = 0u; pw2 = sid_lo; pw3 = sid_hi;
 #pragma unroll
-                for (int r = 0; r < 10; ++r) cv_philox_round(c0, c1, c2, c3, a.rk[2 * r], a.rk[2 * r + 1]);
-                n0 = a.eps * (2.0 * cv_unit32((q & 1) ? c2 : c0) - 3.0);
-                n1 = a.eps * (2.0 * cv_unit32((q & 1) ? c3 : c1) - 3.0);
+                    for (int r = 0; r < 10; ++r) cv_philox_round(pw0, pw1, pw2, pw3, a.rk[2 * r], a.rk[2 * r + 1]);
+                }
+                const int src = (lane & ~3) | (2 * cur + (q >> 1));
+                const uint32_t v0 = __shfl_sync(0xffffffffu, pw0, src), v1 = __shfl_sync(0xffffffffu, pw1, src);
+                const uint32_t v2 = __shfl_sync(0xffffffffu, pw2, src), v3 = __shfl_sync(0xffffffffu, pw3, src);
+                n0 = a.eps * (2.0 * cv_unit32((q & 1) ? v2 : v0) - 3.0);
+                n1 = a.eps * (2.0 * cv_unit32((q & 1) ? v3 : v1) - 3.0);
             } else {
                 const int k = 4 * t + q;
                 n0 = k < a.n_steps ? __ldg(a.w + (f0 + k) * 2) : 0.0;
@@ -487,40 +560,78 @@ k_closed_loop_cvx(const __grid_constant__ CvxMaps maps, const CvxArgs a) {
             sm.th[nxt][8 + 2 * q][lcol] = n0;
             sm.th[nxt][8 + 2 * q + 1][lcol] = n1;
         }
-        // ---- slack check s_unc = Ks theta (this warp's 16 rows x 32 loops) and gain product U = Ku theta (own n-tile)
-        double2 su[2][CV_NT], cu = make_double2(0.0, 0.0);
-#pragma unroll
-        for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-            for (int nt = 0; nt < CV_NT; ++nt) su[mt][nt] = make_double2(0.0, 0.0);
+        // ---- gain product U = Ku theta (own n-tile), FP64
+        double2 cu = make_double2(0.0, 0.0);
 #pragma unroll
         for (int ks = 0; ks < NSPK; ++ks) {
             const double *row = ks < NW / 4 ? sm.th[cur][4 * ks + q] : sm.sp[q];
-            double bv[CV_NT];
-#pragma unroll
-            for (int nt = 0; nt < CV_NT; ++nt) bv[nt] = row[8 * nt + g];
-#pragma unroll
-            for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-                for (int nt = 0; nt < CV_NT; ++nt) dmma884(su[mt][nt], aKs[mt][ks], bv[nt]);
             dmma884(cu, aKu[ks], row[8 * warp + g]);
         }
-        // ---- screening: does any slack row of any loop leave the box?  (max over this lane's two rows, one compare and
-        //      one vote per fragment column; fmax drops NaN, and a loop whose state is non-finite must not iterate anyway)
-        unsigned susp = 0u;
+        // ---- screening of the slack rows on the TF32 tensor cores (this warp's 16 rows x 32 loops): s~ = Ks theta and
+        //      A = |Ks| |theta| in one pass each; |s - s~| <= kScreenRel A (operand rounding 2^-11 + truncation 2^-10, FP32
+        //      accumulation; kScreenRel = 2^-8 leaves a factor two), so  |s~| + kScreenRel A <= bound  proves that no
+        //      row of this fragment leaves the box.  NaN/Inf anywhere in a window compare as "suspicious" (integer
+        //      compare of the bit patterns), and the exact FP64 check below decides.
+        float cs[CV_NT][4], ca[CV_NT][4];
 #pragma unroll
         for (int nt = 0; nt < CV_NT; ++nt)
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const double m = h ? fmax(fabs(su[0][nt].y), fabs(su[1][nt].y)) : fmax(fabs(su[0][nt].x), fabs(su[1][nt].x));
-                const unsigned bv = __ballot_sync(0xffffffffu, m > bound);
-                susp |= bv;                                          // (which column does not matter yet)
+            for (int i = 0; i < 4; ++i) cs[nt][i] = ca[nt][i] = 0.f;
+#pragma unroll
+        for (int s8 = 0; s8 < 3; ++s8)
+#pragma unroll
+            for (int nt = 0; nt < CV_NT; ++nt) {
+                uint32_t b0, b1;
+                if (s8 < 2) {
+                    b0 = __float_as_uint(sm.thf[cur][8 * s8 + q][8 * nt + g]);
+                    b1 = __float_as_uint(sm.thf[cur][8 * s8 + 4 + q][8 * nt + g]);
+                } else {
+                    b0 = spb[nt];
+                    b1 = 0u;
+                }
+                mma_tf32(cs[nt], fKs[0][s8][0], fKs[1][s8][0], fKs[0][s8][1], fKs[1][s8][1], b0, b1);
+                mma_tf32(ca[nt], fKs[0][s8][0] & kAbs, fKs[1][s8][0] & kAbs, fKs[0][s8][1] & kAbs, fKs[1][s8][1] & kAbs,
+                         b0 & kAbs, b1 & kAbs);
             }
-        if (lane == 0) sm.admm.vmask[cur][warp] = susp;
+        unsigned worst = 0u;
+#pragma unroll
+        for (int nt = 0; nt < CV_NT; ++nt)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) worst = max(worst, __float_as_uint(fmaf(kScreenRel, ca[nt][i], fabsf(cs[nt][i]))));
+        const bool susp = __any_sync(0xffffffffu, worst > bound_bits);
+        if (lane == 0) sm.admm.vmask[cur][warp] = susp ? 1u : 0u;
         __syncthreads();
         unsigned act32 = 0u;
+        double2 su[2][CV_NT];
+        double lo[2], hi[2];
         if ((sm.admm.vmask[cur][0] | sm.admm.vmask[cur][1] | sm.admm.vmask[cur][2] | sm.admm.vmask[cur][3]) != 0u) {
-            // rare (first blocks after a set-point change): which loops violate, which hold non-finite numbers
+            // rare (first blocks after a set-point change): the exact FP64 check - which loops violate, which hold
+            // non-finite numbers
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < CV_NT; ++nt) su[mt][nt] = make_double2(0.0, 0.0);
+#pragma unroll
+            for (int ks = 0; ks < NSPK; ++ks) {
+                const double *row = ks < NW / 4 ? sm.th[cur][4 * ks + q] : sm.sp[q];
+                double bv[CV_NT], av[2];
+#pragma unroll
+                for (int nt = 0; nt < CV_NT; ++nt) bv[nt] = row[8 * nt + g];
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) {
+                    const int r = 16 * warp + 8 * mt + g;
+                    av[mt] = r < nb ? __ldg(a.Ks + (size_t)r * a.nth + 4 * ks + q) : 0.0;
+                }
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                    for (int nt = 0; nt < CV_NT; ++nt) dmma884(su[mt][nt], av[mt], bv[nt]);
+            }
+            for (int mt = 0; mt < 2; ++mt) {
+                const int r = 16 * warp + 8 * mt + g;
+                lo[mt] = r < nb ? __ldg(a.blo + r) : -INFINITY;
+                hi[mt] = r < nb ? __ldg(a.bhi + r) : INFINITY;
+            }
             unsigned viol, bad;
             box_flags(su, lo, hi, q, viol, bad);
             if (lane == 0) { sm.admm.vmask[nxt][warp] = viol; sm.admm.bmask[cur][warp] = bad; }
@@ -536,16 +647,9 @@ k_closed_loop_cvx(const __grid_constant__ CvxMaps maps, const CvxArgs a) {
 #pragma unroll
                 for (int nt = 0; nt < CV_NT; ++nt) sm.admm.su[mt * CV_NT + nt][tid] = su[mt][nt];
             admm_thresholds(su, a.tol, a.bmax[0], sm.admm);
-            double aPhi[2][CV_KS];
-#pragma unroll
-            for (int mt = 0; mt < 2; ++mt) {
-                const int r = 16 * warp + 8 * mt + g;
-#pragma unroll
-                for (int ks = 0; ks < CV_KS; ++ks) {
-                    const int c = 4 * ks + q;
-                    aPhi[mt][ks] = (r < nb && c < nb) ? __ldg(a.Phi + (size_t)r * nb + c) : 0.0;
-                }
-            }
+            std::conditional_t<(MINB > 2), PhiStream, PhiRegs> aPhi;
+            if constexpr (MINB > 2) aPhi.load(a.Phi64, warp, g, q);
+            else aPhi.load(a.Phi, nb, warp, g, q);
             double2 tt[2][CV_NT];
             int its[CV_NT][2];
             unsigned inacc;
@@ -578,6 +682,7 @@ k_closed_loop_cvx(const __grid_constant__ CvxMaps maps, const CvxArgs a) {
         }
         // ---- planned inputs -> input rows of the next window (own n-tile)
         *reinterpret_cast<double2 *>(&sm.th[nxt][g][8 * warp + 2 * q]) = cu;
+        *reinterpret_cast<float2 *>(&sm.thf[nxt][g][8 * warp + 2 * q]) = make_float2((float)cu.x, (float)cu.y);
         __syncwarp();
         // ---- plant: [Y; x+] = Mblk [x; U], the outputs on top of the noise
         double2 d0 = *reinterpret_cast<const double2 *>(&sm.th[nxt][8 + g][8 * warp + 2 * q]), d1 = make_double2(0.0, 0.0);
@@ -589,6 +694,7 @@ k_closed_loop_cvx(const __grid_constant__ CvxMaps maps, const CvxArgs a) {
         }
         __syncwarp();                                                // every lane has read the old state
         *reinterpret_cast<double2 *>(&sm.th[nxt][8 + g][8 * warp + 2 * q]) = d0;
+        *reinterpret_cast<float2 *>(&sm.thf[nxt][8 + g][8 * warp + 2 * q]) = make_float2((float)d0.x, (float)d0.y);
         if (g < 4) *reinterpret_cast<double2 *>(&sm.x[g][8 * warp + 2 * q]) = d1;
         __syncwarp();
         // ---- record step q of loop 8 warp + g: 16 bytes per array; the four lanes of a loop write 64 contiguous bytes
@@ -620,6 +726,19 @@ k_closed_loop_cvx(const __grid_constant__ CvxMaps maps, const CvxArgs a) {
         }
         if (a.x_final) a.x_final[(size_t)b * 4 + q] = sm.x[q][lcol];
     }
+}
+
+// Set creation: the zero-padded copy of Phi the 3-CTAs-per-SM build streams its A operand from.
+int closed_loop_cvx_prepare(ddmpc_set *set, cudaStream_t st) {
+    const Plan &pl = set->plan;
+    const Dims &d = pl.d;
+    if (pl.count != 1 || !d.robust || !d.convex || d.nb <= 0 || d.nb > CV_NR) return DDMPC_OK;
+    ScratchStreamScope scope(st);
+    DDMPC_CUDA(set->cvx_phi64.alloc(sizeof(double) * CV_NR * CV_NR));
+    DDMPC_CUDA(cudaMemsetAsync(set->cvx_phi64.p, 0, sizeof(double) * CV_NR * CV_NR, st));
+    DDMPC_CUDA(cudaMemcpy2DAsync(set->cvx_phi64.p, sizeof(double) * CV_NR, pl.Phi.p, sizeof(double) * d.nb,
+                                 sizeof(double) * d.nb, d.nb, cudaMemcpyDeviceToDevice, st));
+    return DDMPC_OK;
 }
 
 // Returns DDMPC_OK when handled, -1 when this path does not apply.
@@ -655,7 +774,7 @@ int closed_loop_cvx_try(const ddmpc_set *set, const ddmpc_plant *plant, int B, c
     a.B = B; a.n_steps = n_steps; a.nb = d.nb; a.nth = d.nth; a.n_tail = rem;
     a.max_iter = max_iter > 0 ? max_iter : 1000;
     a.tol = tol > 0.0 ? tol : 1e-8;
-    a.Ku = pl.Ku.d(); a.Ks = pl.Ks.d(); a.Phi = pl.Phi.d(); a.Psi = pl.Psi.d();
+    a.Ku = pl.Ku.d(); a.Ks = pl.Ks.d(); a.Phi = pl.Phi.d(); a.Phi64 = set->cvx_phi64.d(); a.Psi = pl.Psi.d();
     a.blo = pl.lo.d(); a.bhi = pl.hi.d(); a.bmax = pl.bmax.d();
     a.x0 = x0; a.u_past0 = u_past0; a.y_past0 = y_past0; a.u_s = u_s; a.y_s = y_s; a.w = w;
     a.id0 = id0; a.eps = eps;

@@ -85,6 +85,8 @@ struct ddmpc_set {
     // tc_loop.cu: TF32 hi / lo images of the gain block and the plant block map (+ the plant in FP64) and their host key
     mutable ddmpc::DevBuf tc_ws;
     mutable std::vector<double> tc_key;
+    // cvx_loop.cu: Phi zero-padded to 64 x 64 (A operand of the ADMM iteration when it is streamed from L1), built with the set
+    ddmpc::DevBuf cvx_phi64;
     // dmma_loop.cu: packed A fragments (gain rows + block maps of the plant) and their host key
     mutable ddmpc::DevBuf dmma_ws;
     mutable std::vector<double> dmma_key;
@@ -94,7 +96,7 @@ struct ddmpc_set {
     mutable cudaStream_t stage_stream = nullptr;
     void detach_streams() {
         plan.detach_streams();
-        for (ddmpc::DevBuf *b : {&ctrl_status, &plant_dev, &fast_ksp, &gemm_ws, &dmma_ws, &tc_ws, &stage_dev}) b->detach_stream();
+        for (ddmpc::DevBuf *b : {&ctrl_status, &plant_dev, &fast_ksp, &gemm_ws, &dmma_ws, &tc_ws, &cvx_phi64, &stage_dev}) b->detach_stream();
     }
     ~ddmpc_set() {
         if (stage_host) cudaFreeHost(stage_host);

@@ -372,6 +372,7 @@ __global__ void k_poison(int count, long per, const int *__restrict__ cstat, dou
 }
 
 int closed_loop_fast_prepare(ddmpc_set *set, cudaStream_t st);   // fast_loop.cu
+int closed_loop_cvx_prepare(ddmpc_set *set, cudaStream_t st);    // cvx_loop.cu
 
 static Dims make_dims(const ddmpc_params &q) {
     Dims d{};
@@ -873,6 +874,7 @@ int set_create_device(const ddmpc_params *prm, int count, const double *u_d, siz
         DDMPC_CUDA(cudaStreamSynchronize(st));
     }
     DDMPC_TRY(closed_loop_fast_prepare(set.get(), st));
+    DDMPC_TRY(closed_loop_cvx_prepare(set.get(), st));
     DDMPC_CUDA(cudaStreamSynchronize(st));
     set->detach_streams();                  // the set may outlive `st`: it is freed on the legacy stream after a device sync
     *out = set.release();

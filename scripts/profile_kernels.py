@@ -18,7 +18,7 @@ if which in ("ws", "cvx", "admm", "perloop3"):
     B = 4096 if which == "perloop3" else 65536
     sc = S.config3_batch(B, seed=0)
     prm, plant = sc["params"], sc["plant"]
-    slack, c = (1, 1.0) if which == "cvx" else ((1, 0.3) if which == "admm" else (0, 1.0))
+    slack, c = (1, float(os.environ.get("CVX_C", "1.0"))) if which == "cvx" else ((1, 0.3) if which == "admm" else (0, 1.0))
     cs = ControllerSet(prm["n"], 2, 2, sc["u_d"], sc["y_d"], prm["L"], prm["Q"], prm["R"], prm["eps_max"], prm["lamb_alpha"],
                        prm["lamb_sigma"], c, slack, 1, 4, True, device=dev)
     if which == "admm":
