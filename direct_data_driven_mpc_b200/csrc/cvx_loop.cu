@@ -62,8 +62,8 @@ __device__ __forceinline__ double colmax8(double v) {   // max over the 8 lanes 
 }
 __device__ __forceinline__ double clipd(double v, double lo, double hi) { return fmin(fmax(v, lo), hi); }
 
-// acc (rows of this warp x 32 problems) = Phi[rows, :] * D, D = sm.d[buf]; n-tile nt is computed when bit nt of `on` is set
-// (warp-uniform), the accumulators of the others stay zero
+// acc (rows of this warp x 32 problems) = Phi[rows, :] * D, D = sm.d[buf].  (Skipping the n-tiles whose eight problems have
+// all converged was measured and dropped: the predicates cost more than the DMMAs they save, c = 0.3 went 4.0 -> 4.4 ms.)
 // A operand of the ADMM iteration: this warp's rows of Phi, either resident in registers (64 per thread) or streamed from
 // the zero-padded 64 x 64 copy (L1-resident; the closed-loop kernel's register budget goes to its per-block path).
 struct PhiRegs {
@@ -92,7 +92,7 @@ struct PhiStream {
 
 template <class PhiA>
 __device__ __forceinline__ void phi_times_d(const PhiA &aPhi, const double (*D)[CV_DS], int ks_n, int g, int q,
-                                            double2 (&acc)[2][CV_NT], unsigned on = 0xfu) {
+                                            double2 (&acc)[2][CV_NT]) {
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
@@ -100,15 +100,15 @@ __device__ __forceinline__ void phi_times_d(const PhiA &aPhi, const double (*D)[
 #pragma unroll
     for (int ks = 0; ks < CV_KS; ++ks) {
         if (ks < ks_n) {
-#pragma unroll
             const double a0 = aPhi.get(0, ks), a1 = aPhi.get(1, ks);
+            double b[CV_NT];
 #pragma unroll
-            for (int nt = 0; nt < CV_NT; ++nt)
-                if ((on >> nt) & 1u) {
-                    const double b = D[4 * ks + q][8 * nt + g];
-                    dmma884(acc[0][nt], a0, b);
-                    dmma884(acc[1][nt], a1, b);
-                }
+            for (int nt = 0; nt < CV_NT; ++nt) b[nt] = D[4 * ks + q][8 * nt + g];
+#pragma unroll
+            for (int nt = 0; nt < CV_NT; ++nt) {
+                dmma884(acc[0][nt], a0, b[nt]);
+                dmma884(acc[1][nt], a1, b[nt]);
+            }
         }
     }
 }
@@ -139,9 +139,6 @@ __device__ __forceinline__ void admm_cta(const PhiA &aPhi, const double (&lo)[2]
     for (int nt = 0; nt < CV_NT; ++nt) iters[nt][0] = iters[nt][1] = 1;
     if (tid < CV_NL) sm.red[0][tid] = sm.red[1][tid] = sm.red[2][tid] = 0ull;
     unsigned frozen = ~act & 0xffu;
-    // n-tiles whose eight problems are all frozen stop being multiplied one iteration later (by then both copies of d hold
-    // their final columns)
-    unsigned skip = 0u, full_prev = 0u;
     int cur = 0, it = 0;
     while (true) {
         const int all = __syncthreads_and(frozen == 0xffu);          // also: d[cur], su, thr, red slots are visible
@@ -149,7 +146,7 @@ __device__ __forceinline__ void admm_cta(const PhiA &aPhi, const double (&lo)[2]
         ++it;
         const int slot = it % 3;
         double2 acc[2][CV_NT];
-        phi_times_d(aPhi, sm.d[cur], ks_n, g, q, acc, ~skip & 0xfu);
+        phi_times_d(aPhi, sm.d[cur], ks_n, g, q, acc);
         double res[CV_NT][2];
 #pragma unroll
         for (int nt = 0; nt < CV_NT; ++nt) res[nt][0] = res[nt][1] = 0.0;
@@ -194,11 +191,6 @@ __device__ __forceinline__ void admm_cta(const PhiA &aPhi, const double (&lo)[2]
                 iters[nt][h] = it;
                 if (__longlong_as_double((long long)sm.red[slot][p]) <= sm.thr[p]) frozen |= 1u << (2 * nt + h);
             }
-        skip = full_prev;
-        full_prev = 0u;
-#pragma unroll
-        for (int nt = 0; nt < CV_NT; ++nt)
-            if (__all_sync(0xffffffffu, ((frozen >> (2 * nt)) & 3u) == 3u)) full_prev |= 1u << nt;
         // the slot of iteration it + 1 was last read in iteration it - 2: clear it (visible after the next barrier)
         if (tid < CV_NL) sm.red[(it + 1) % 3][tid] = 0ull;
         cur ^= 1;

@@ -412,6 +412,45 @@ def test_convex_fused_path_vs_generic_and_oracle(c):
     assert _rel(u3[:64].cpu().numpy(), u4.cpu().numpy()) < 1e-8 and (i3[:64] == i4).all()
 
 
+def test_convex_screen_never_hides_a_violation():
+    """The TF32 screen of k_closed_loop_cvx only ever SKIPS the exact FP64 slack check.  Bound placed 1e-4 (relative) below
+    / 1e-9 above the largest slack of an unconstrained run - both far inside the screen's 4e-3 margin: in the first case the
+    loops that reach it iterate (a violation of 1e-9 relative would converge in the first ADMM iteration and leave no
+    trace in `iters`), in the second nobody does; the iteration counts equal those of the generic kernel, which has no screen."""
+    import condensed_numpy as CN
+    plant_o, prm, rng, x0, u_d, y_d = O.example_scenario(0)
+    B, n_steps, nblk = 70, 41, 11
+    r = np.random.default_rng(12)
+    xs = np.tile(plant_o.x, (B, 1)) + 0.05 * r.normal(size=(B, 4))
+    us = np.tile(prm["u_s"].T, (B, 1)) * r.uniform(0.7, 1.3, (B, 1))
+    ys = us @ _plant().equilibrium_gain().T
+    up0, yp0 = np.tile(u_d[-4:].reshape(1, -1), (B, 1)), np.tile(y_d[-4:].reshape(1, -1), (B, 1))
+    w = 0.002 * r.uniform(-1, 1, (B, n_steps, 2))
+    cs, _ = _set(u_d, y_d, 1, True, 4, c=1e6)
+    u, y, st, it = cs.closed_loop(_plant(), xs, up0, yp0, us, ys, n_steps, w=w)
+    assert int(st.max()) == 0 and int(it.max()) == nblk
+    pl = CN.build_plan(4, 2, 2, u_d, y_d, 30, prm["Q"], prm["R"], prm["eps_max"], prm["lamb_alpha"], prm["lamb_sigma"], 1e6,
+                       CN.SLACK_CONVEX, CN.ROBUST, True)
+    U = np.concatenate([up0.reshape(B, 4, 2), u.cpu().numpy()], axis=1)
+    Y = np.concatenate([yp0.reshape(B, 4, 2), y.cpu().numpy()], axis=1)
+    smax = np.zeros((B, nblk))
+    for t in range(nblk):
+        th = np.concatenate([U[:, 4 * t:4 * t + 4].reshape(B, -1), Y[:, 4 * t:4 * t + 4].reshape(B, -1), us, ys], axis=1)
+        smax[:, t] = np.abs(th @ pl.Ks.T).max(axis=1)
+    top = smax.max()
+    for factor, binds in ((1.0 - 1e-4, True), (1.0 + 1e-9, False)):
+        c = top * factor / prm["eps_max"]
+        cs2, _ = _set(u_d, y_d, 1, True, 4, c=c)
+        res = {}
+        for path in ("cvx", "generic"):
+            cs2.set_option("closed_loop_path", path)
+            res[path] = cs2.closed_loop(_plant(), xs, up0, yp0, us, ys, n_steps, w=w)
+        assert (res["cvx"][3] == res["generic"][3]).all() and int(res["cvx"][2].max()) == 0
+        extra = int(res["cvx"][3].sum()) - B * nblk
+        assert (extra > 0) == binds, (factor, extra)
+        assert _rel(res["cvx"][0].cpu().numpy(), res["generic"][0].cpu().numpy()) < 1e-8
+
+
 def test_batched_reproduction_matches_reference_semantics(golden_repro):
     """reproduction.run_reproduction_batch (device data generation, shared generator order across the three
     schemes) vs the fixture produced by the reference's own functions for seed 4, plus figure-level facts."""

@@ -81,3 +81,42 @@ def test_workload_recipes_agree():
         for k in "ABCD":
             assert np.array_equal(getattr(w4["plant"], k), getattr(s4["plant"], k))
         assert w4["params"]["n_mpc_step"] == nmpc and np.array_equal(w4["params"]["Q"], s4["params"]["Q"])
+
+
+def test_tf32_screen_margin_bounds_the_rounding_error():
+    """The CONVEX closed-loop kernel screens the slack rows with a one-pass TF32 product and skips the exact FP64 check when
+    |s~| + 2^-8 * (|Ks| |theta|) <= bound (csrc/cvx_loop.cu, kScreenRel).  Emulation of that arithmetic (Ks rounded to TF32,
+    theta truncated to TF32 as the tensor core does with FP32 bit patterns, FP32 accumulation): the margin must dominate the
+    error on the four-tank gain rows for windows of every scale, with at least a factor two to spare."""
+    from oracle import ddmpc_oracle as O
+    import condensed_numpy as C
+    plant_o, prm, rng, x0, u_d, y_d = O.example_scenario(0)
+    pl = C.build_plan(4, 2, 2, u_d, y_d, 30, prm["Q"], prm["R"], prm["eps_max"], prm["lamb_alpha"], prm["lamb_sigma"], 1.0,
+                      C.SLACK_CONVEX, C.ROBUST, True)
+    Ks = pl.Ks
+
+    def rna(x):       # cvt.rna.tf32.f32: round to nearest, ties away, 10 mantissa bits
+        b = np.asarray(x, np.float32).view(np.uint32).astype(np.uint64)
+        return ((b + 0x1000) & 0xFFFFE000).astype(np.uint32).view(np.float32)
+
+    def trunc(x):     # what mma.sync .tf32 reads of an FP32 register
+        return (np.asarray(x, np.float32).view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
+
+    r = np.random.default_rng(0)
+    a_op = rna(Ks.astype(np.float32))
+    worst = 0.0
+    for scale in (1e-3, 1.0, 37.0):
+        th = scale * r.uniform(-1.5, 1.5, (Ks.shape[1], 4096))
+        thf = th.astype(np.float32)
+        b_op = trunc(thf)
+        s_t = np.zeros((Ks.shape[0], th.shape[1]), np.float32)
+        a_t = np.zeros_like(s_t)
+        for k in range(Ks.shape[1]):                               # sequential FP32 accumulation (worse than the tensor core's)
+            s_t += a_op[:, k:k + 1] * b_op[k:k + 1, :]
+            a_t += np.abs(a_op[:, k:k + 1]) * np.abs(b_op[k:k + 1, :])
+        err = np.abs(Ks @ th - s_t.astype(np.float64))
+        margin = a_t.astype(np.float64) / 256.0
+        ok = margin > 0
+        worst = max(worst, float((err[ok] / margin[ok]).max()))
+        assert (err <= margin).all()
+    assert worst < 0.5, worst
