@@ -589,15 +589,19 @@ def secondary_convex(dev, sc, fp64_peak, B=CONFIG3_LOOPS):
         solves = B * SOLVES_PER_LOOP
         iters = float(it.sum().item())
         active_loops = int((it > SOLVES_PER_LOOP).sum().item())
-        # executed work: every solve pays the gain product + plant block (640 flop) and the slack check Ks theta
-        # (2 nb n_theta); every ADMM iteration beyond the check one Phi d product (2 nb^2).  The final t = Phi d and the
-        # Psi correction of the active solves are not counted (their number is not reported by the kernel).
-        flops = solves * (640 + 2 * nb * nth) + (iters - solves) * 2 * nb * nb
+        # executed FP64 work: every solve pays the gain product + plant block (640 flop); every ADMM iteration beyond the
+        # check one Phi d product (2 nb^2).  The slack check Ks theta (2 nb n_theta per solve) runs as a one-pass TF32
+        # screen plus its modulus product on the legacy tensor path and is reported separately - it is not FP64 work; the
+        # exact FP64 re-check of the suspicious blocks, the final t = Phi d and the Psi correction of the active solves are
+        # not counted (their number is not reported by the kernel).
+        flops = solves * 640 + (iters - solves) * 2 * nb * nb
+        screen = solves * 2 * (2 * nb * nth)
         tf = flops / (ms * 1e-3) / 1e12
         out[f"c_{c}"] = {"loop_ms": ms, "solves_per_s": solves / (ms * 1e-3), "status_max": int(st.max().item()),
                          "iterations_mean_per_solve": iters / solves, "admm_iterations_total": iters - solves,
-                         "loops_with_an_active_bound": active_loops, "executed_tflops": tf,
-                         "frac_of_fp64_peak": tf / fp64_peak if fp64_peak else None}
+                         "loops_with_an_active_bound": active_loops, "executed_fp64_tflops": tf,
+                         "frac_of_fp64_peak": tf / fp64_peak if fp64_peak else None,
+                         "tf32_screen_tflops": screen / (ms * 1e-3) / 1e12}
         del cs
     # ---- the batched solve itself (ddmpc_solve_batch, no plant): B QPs of one shared CONVEX controller through the
     #      tensor-core pipeline (k_gemm products around k_admm_dmma, csrc/cvx_loop.cu), every problem with a binding box

@@ -459,8 +459,9 @@ __device__ __forceinline__ uint32_t to_tf32(float x) {
 constexpr float kScreenRel = 1.0f / 256.0f;
 constexpr uint32_t kAbs = 0x7fffffffu;
 
-// MINB = CTAs per SM the register allocation is held to (2: no spills; 3, 4: the ADMM section spills, the per-block path
-// does not - more resident warps for the latency-bound steady state).
+// MINB = CTAs per SM the register allocation is held to.  3 (168 registers, the default: option "cvx_ctas_per_sm"): the
+// ADMM section streams Phi from L1 instead of holding it in 64 registers; 2 (255 registers): Phi in registers - the
+// steady state is 12 % slower, runs dominated by ADMM iterations (c = 0.3) are 7 % faster.
 template <bool PHILOX, int MINB>
 __global__ void __launch_bounds__(128, MINB)
 k_closed_loop_cvx(const __grid_constant__ CvxMaps maps, const CvxArgs a) {
@@ -491,24 +492,29 @@ k_closed_loop_cvx(const __grid_constant__ CvxMaps maps, const CvxArgs a) {
     // ---- A fragments that stay in registers: gain rows (8 x 20), slack rows of this warp (16 x 20), plant block map
     double aKu[NSPK], aMb[2][3];
     uint32_t fKs[2][3][2], spb[CV_NT];                               // TF32 screen: slack rows, set-points
+    // (a lambda: the fragments are loaded again after an ADMM solve, so that they need not stay in registers - or be
+    //  spilled and re-read in every block - across the ADMM section, which takes all 255 registers)
+    auto load_frags = [&]() {
 #pragma unroll
-    for (int ks = 0; ks < NSPK; ++ks) aKu[ks] = __ldg(a.Ku + (size_t)g * a.nth + 4 * ks + q);
+        for (int ks = 0; ks < NSPK; ++ks) aKu[ks] = __ldg(a.Ku + (size_t)g * a.nth + 4 * ks + q);
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt) {
-        const int r = 16 * warp + 8 * mt + g;
+        for (int mt = 0; mt < 2; ++mt) {
+            const int r = 16 * warp + 8 * mt + g;
 #pragma unroll
-        for (int s8 = 0; s8 < 3; ++s8)
+            for (int s8 = 0; s8 < 3; ++s8)
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int c = 8 * s8 + q + 4 * h;
-                fKs[mt][s8][h] = to_tf32((r < nb && c < a.nth) ? (float)__ldg(a.Ks + (size_t)r * a.nth + c) : 0.f);
-            }
-    }
+                for (int h = 0; h < 2; ++h) {
+                    const int c = 8 * s8 + q + 4 * h;
+                    fKs[mt][s8][h] = to_tf32((r < nb && c < a.nth) ? (float)__ldg(a.Ks + (size_t)r * a.nth + c) : 0.f);
+                }
+        }
 #pragma unroll
-    for (int nt = 0; nt < CV_NT; ++nt) {
-        const int bb = min(blockIdx.x * CV_NL + 8 * nt + g, a.B - 1);
-        spb[nt] = __float_as_uint((float)(q < 2 ? a.u_s[(size_t)bb * 2 + q] : a.y_s[(size_t)bb * 2 + (q - 2)]));
-    }
+        for (int nt = 0; nt < CV_NT; ++nt) {
+            const int bb = min(blockIdx.x * CV_NL + 8 * nt + g, a.B - 1);
+            spb[nt] = __float_as_uint((float)(q < 2 ? a.u_s[(size_t)bb * 2 + q] : a.y_s[(size_t)bb * 2 + (q - 2)]));
+        }
+    };
+    load_frags();
     auto load_map = [&](const double (&Mm)[12][12]) {
 #pragma unroll
         for (int rt = 0; rt < 2; ++rt)
@@ -670,6 +676,9 @@ k_closed_loop_cvx(const __grid_constant__ CvxMaps maps, const CvxArgs a) {
             }
             cu.x -= corr.x;
             cu.y -= corr.y;
+            load_frags();
+            if (t == nblk - 1 && a.n_tail != 0) load_map(maps.Mt);
+            else load_map(maps.Mb);
             // (sm.admm.d is next written after the barrier at the top of a later block)
         }
         // ---- planned inputs -> input rows of the next window (own n-tile)

@@ -21,6 +21,8 @@ if which in ("ws", "cvx", "admm", "perloop3"):
     slack, c = (1, float(os.environ.get("CVX_C", "1.0"))) if which == "cvx" else ((1, 0.3) if which == "admm" else (0, 1.0))
     cs = ControllerSet(prm["n"], 2, 2, sc["u_d"], sc["y_d"], prm["L"], prm["Q"], prm["R"], prm["eps_max"], prm["lamb_alpha"],
                        prm["lamb_sigma"], c, slack, 1, 4, True, device=dev)
+    if which == "cvx" and "CVX_CTAS" in os.environ:
+        cs.set_option("cvx_ctas_per_sm", int(os.environ["CVX_CTAS"]))
     if which == "admm":
         r = np.random.default_rng(0)
         ks = r.integers(0, 396, B)
