@@ -246,6 +246,45 @@ def test_config3_full_size_properties():
         assert _rel(u[b].cpu().numpy(), u_ref) < 1e-5 and _rel(y[b].cpu().numpy(), y_ref) < 1e-5, b
 
 
+@pytest.mark.parametrize("c", [1.0, 0.3])
+def test_config3_convex_full_size_properties(c):
+    """BASELINE config 3 with the CONVEX slack bound, 65,536 loops through k_closed_loop_cvx: a loop's trajectory does not
+    depend on which loops share its CTA (the ADMM runs 32 problems in lock-step, the TF32 screen votes over the CTA) -
+    shards cut at a position that is NOT a multiple of the CTA size reproduce the full batch BIT for bit, iteration
+    counts included; every loop settles; a sample with active bounds matches the oracle's active-set solution."""
+    import torch
+    from direct_data_driven_mpc_b200 import ControllerSet, scenarios as S
+    B = 65536
+    sc = S.config3_batch(B)
+    prm, pl = sc["params"], sc["plant"]
+    cs = ControllerSet(4, 2, 2, sc["u_d"], sc["y_d"], 30, prm["Q"], prm["R"], prm["eps_max"], prm["lamb_alpha"],
+                       prm["lamb_sigma"], c, 1, 1, 4, True)
+    args = lambda lo, hi: (pl, sc["x0"][lo:hi], sc["u_past0"][lo:hi], sc["y_past0"][lo:hi], sc["u_s"][lo:hi],
+                           sc["y_s"][lo:hi], 401)
+    l0 = _launches()
+    u, y, status, iters = cs.closed_loop(*args(0, B), noise_seed=0, scenario_id0=0, noise_eps=0.002)
+    assert _launches() - l0 == 1
+    assert int(status.max()) == 0 and int(iters.min()) >= 101 and int(iters.max()) > 101
+    ys = torch.from_numpy(sc["y_s"]).to(y.device)
+    assert float((y[:, -1] - ys).abs().max()) < 0.02
+    cut = 30011                                                       # 30011 = 937 * 32 + 27: every later loop changes CTA and lane
+    ua, ya, _, ia = cs.closed_loop(*args(0, cut), noise_seed=0, scenario_id0=0, noise_eps=0.002)
+    ub, yb, _, ib = cs.closed_loop(*args(cut, B), noise_seed=0, scenario_id0=cut, noise_eps=0.002)
+    assert torch.equal(torch.cat([ua, ub]), u) and torch.equal(torch.cat([ya, yb]), y)
+    assert torch.equal(torch.cat([ia, ib]), iters)
+    active = torch.nonzero(iters > 101).flatten().cpu().numpy()
+    ids = [int(active[0]), int(active[len(active) // 2]), int(active[-1])]
+    w = O.philox_noise(0, np.array(ids), 401, 2, 0.002)
+    for j, b in enumerate(ids):
+        plant_o = O.four_tank_plant()
+        plant_o.x = sc["x0"][b].copy()
+        ctrl = O.make_controller(O.four_tank_params(), sc["u_d"], sc["y_d"], n_mpc_step=4, slack_type=O.SLACK_CONVEX, c=c)
+        ctrl.u_s, ctrl.y_s = sc["u_s"][b].reshape(-1, 1), sc["y_s"][b].reshape(-1, 1)
+        ctrl.set_past_input_output_data(sc["u_past0"][b].reshape(-1, 1), sc["y_past0"][b].reshape(-1, 1))
+        u_ref, y_ref = O.closed_loop(plant_o, ctrl, 401, w[j])
+        assert _rel(u[b].cpu().numpy(), u_ref) < 1e-5 and _rel(y[b].cpu().numpy(), y_ref) < 1e-5, b
+
+
 @pytest.mark.parametrize("n_mpc,n_steps", [(20, 47), (8, 20), (10, 10)])
 def test_config4_gemm_path_vs_generic_and_oracle(n_mpc, n_steps):
     """Large-system path (batch as the N dimension of DMMA GEMMs, block-stepped plant) vs the generic
