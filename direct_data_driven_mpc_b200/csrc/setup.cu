@@ -462,6 +462,33 @@ int pe_rank_device(cudaStream_t st, int batch, const double *X, long bsX, int N,
     return DDMPC_OK;
 }
 
+// Short data (fewer Hankel columns than rows): rows of the equality constraint "t = T x stays in range(H)", one per
+// eigenvector of W, zero for the eigenvectors that span the range (keep[k] = 1):  Aeq[k][a] = (1 - keep[k]) V[trow(perm[a])][k]
+__global__ void k_fill_Aeq(FillArgs f, const int *__restrict__ perm, const double *__restrict__ V, long bsV,
+                           const double *__restrict__ keep, long bsk, double *__restrict__ Aeq, long bsA) {
+    const int r = f.nu + f.ny, c = blockIdx.y;
+    const long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (long)r * f.nx) return;
+    const int k = (int)(e / f.nx), a = (int)(e % f.nx);
+    const int i = perm[a], ti = i < r ? i : i - f.ny;
+    Aeq[(long)c * bsA + e] = (1.0 - keep[(long)c * bsk + k]) * V[(long)c * bsV + (long)ti * r + k];
+}
+
+// dst (rows x cols, per batch entry) = src^T, src (cols x rows) with row stride lds
+__global__ void k_transpose(int rows, int cols, const double *__restrict__ src, long lds, long bs_src,
+                            double *__restrict__ dst, long bs_dst) {
+    const long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (long)rows * cols) return;
+    const int i = (int)(e / cols), k = (int)(e % cols);
+    dst[(long)blockIdx.y * bs_dst + e] = src[(long)blockIdx.y * bs_src + (long)k * lds + i];
+}
+
+// S[k][k] += keep[k]: the rows of the Schur complement that belong to no constraint become identity rows
+__global__ void k_add_diag(int n, const double *__restrict__ dvec, long bsd, double *__restrict__ S, long bsS) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) S[(long)blockIdx.y * bsS + (long)k * n + k] += dvec[(long)blockIdx.y * bsd + k];
+}
+
 static int build_robust(cudaStream_t st, Plan &pl, const FillArgs &fa, const int *perm_d, const int *invperm_d,
                         const int *bpos_d, const double *Rd, const double *Qd, int *info_d) {
     const Dims &d = pl.d;
@@ -485,9 +512,32 @@ static int build_robust(cudaStream_t st, Plan &pl, const FillArgs &fa, const int
     DDMPC_TRY(gemm(st, CW, r, r, d.cols, 1.0, Hm, tr(Hm), 0.0, pl.W.d(), r, 1, sW, nullptr, 0, true));
     DDMPC_TRY(symmetrize(st, CW, r, pl.W.d(), r, sW));
     DDMPC_TRY(copy_bcast(st, CW, sW, pl.W.d(), sW, Lw.d(), sW));
-    DDMPC_TRY(potrf(st, CW, r, Lw.d(), r, sW, info_d));
-    DDMPC_TRY(set_identity(st, CW, r, pl.Om.d(), r, sW));
-    DDMPC_TRY(potrs(st, CW, r, r, Lw.d(), r, sW, pl.Om.d(), r, sW));
+    // Short data - fewer Hankel columns than rows, which the reference accepts down to N_min (controller.py:275-283):
+    // W is singular, ||alpha||^2 = t^T W^+ t on range(H) and t = T x has to stay there.  Om becomes the pseudo-inverse
+    // (eigen-decomposition instead of Cholesky) and the null-space rows of W an equality constraint Aeq x = 0 that is
+    // resolved further down by a Schur complement on top of the same reduced Hessian.
+    const bool deficient = d.cols < r;
+    DevBuf Vw, lw, dinv, keep, Aeq, Yq, Sq, Rq, AcC, Rb;
+    const long sAq = (long)r * nx, sAe = CW == 1 ? 0 : sAq;
+    if (!deficient) {
+        DDMPC_TRY(potrf(st, CW, r, Lw.d(), r, sW, info_d));
+        DDMPC_TRY(set_identity(st, CW, r, pl.Om.d(), r, sW));
+        DDMPC_TRY(potrs(st, CW, r, r, Lw.d(), r, sW, pl.Om.d(), r, sW));
+    } else {
+        DDMPC_CUDA(Vw.alloc(sizeof(double) * CW * sW));
+        for (DevBuf *b : {&lw, &dinv, &keep}) DDMPC_CUDA(b->alloc(sizeof(double) * (size_t)CW * r));
+        DDMPC_TRY(jacobi_eig(st, CW, r, Lw.d(), r, sW, Vw.d(), r, sW, lw.d(), r));
+        k_spectrum<<<CW, 32, 0, st>>>(r, lw.d(), r, 1e-12, 1, dinv.d(), r, nullptr);
+        DDMPC_LAUNCH_CHECK();
+        k_spectrum<<<CW, 32, 0, st>>>(r, lw.d(), r, 1e-12, 0, keep.d(), r, nullptr);
+        DDMPC_LAUNCH_CHECK();
+        Mat Vm = mat(Vw.d(), r, 1, sW);
+        DDMPC_TRY(gemm(st, CW, r, r, r, 1.0, Vm, tr(Vm), 0.0, pl.Om.d(), r, 1, sW, dinv.d(), r));
+        DDMPC_CUDA(Aeq.alloc(sizeof(double) * CW * sAq));
+        dim3 g(ceil_div(sAq, 256), CW);
+        k_fill_Aeq<<<g, 256, 0, st>>>(fa, perm_d, Vw.d(), sW, keep.d(), r, Aeq.d(), sAq);
+        DDMPC_LAUNCH_CHECK();
+    }
     DDMPC_TRY(symmetrize(st, CW, r, pl.Om.d(), r, sW));
 
     // reduced Hessian (permuted [free; fixed]) and the theta maps
@@ -514,7 +564,36 @@ static int build_robust(cudaStream_t st, Plan &pl, const FillArgs &fa, const int
     DDMPC_TRY(potrf(st, C, nf, P.d(), nx, sP, info_d + C));
     DDMPC_TRY(copy_bcast(st, C, (long)nf * nth, Nn.d(), (long)nf * nth, X0f.d(), (long)nf * nth));
     DDMPC_TRY(potrs(st, C, nf, nth, P.d(), nx, sP, X0f.d(), nth, (long)nf * nth));
-    // Z = ZT + C_c^T G1 - C_c^T DT_c - DT_c^T C_c - N'^T X0f
+    Mat Af{};
+    if (deficient) {
+        Af = mat(Aeq.d(), nx, 1, sAe);                    // (r x nf): the free columns; the fixed ones follow at + nf
+        // Yq = A^-1 Af^T, S = Af Yq (+ identity on the rows without a constraint), mu = S^-1 (Af X0f + Ac C_c), X0f -= Yq mu
+        DDMPC_CUDA(Yq.alloc(sizeof(double) * (size_t)C * nf * r));
+        DDMPC_CUDA(Sq.alloc(sizeof(double) * (size_t)C * r * r));
+        DDMPC_CUDA(Rq.alloc(sizeof(double) * (size_t)C * r * nth));
+        DDMPC_CUDA(AcC.alloc(sizeof(double) * (size_t)CW * r * nth));
+        {
+            dim3 g(ceil_div((long)nf * r, 256), C);
+            k_transpose<<<g, 256, 0, st>>>(nf, r, Aeq.d(), nx, sAe, Yq.d(), (long)nf * r);
+            DDMPC_LAUNCH_CHECK();
+        }
+        DDMPC_TRY(potrs(st, C, nf, r, P.d(), nx, sP, Yq.d(), r, (long)nf * r));
+        const Mat Yqm = mat(Yq.d(), r, 1, (long)nf * r);
+        DDMPC_TRY(gemm(st, C, r, r, nf, 1.0, Af, Yqm, 0.0, Sq.d(), r, 1, (long)r * r));
+        {
+            dim3 g(ceil_div(r, 128), C);
+            k_add_diag<<<g, 128, 0, st>>>(r, keep.d(), CW == 1 ? 0 : r, Sq.d(), (long)r * r);
+            DDMPC_LAUNCH_CHECK();
+        }
+        DDMPC_TRY(symmetrize(st, C, r, Sq.d(), r, (long)r * r));
+        DDMPC_TRY(potrf(st, C, r, Sq.d(), r, (long)r * r, info_d));
+        DDMPC_TRY(gemm(st, CW, r, nth, nfix, 1.0, mat(Aeq.d() + nf, nx, 1, sAq), Ccm, 0.0, AcC.d(), nth, 1, (long)r * nth));
+        DDMPC_TRY(copy_bcast(st, C, (long)r * nth, AcC.d(), CW == 1 ? 0 : (long)r * nth, Rq.d(), (long)r * nth));
+        DDMPC_TRY(gemm(st, C, r, nth, nf, 1.0, Af, mat(X0f.d(), nth, 1, (long)nf * nth), 1.0, Rq.d(), nth, 1, (long)r * nth));
+        DDMPC_TRY(potrs(st, C, r, nth, Sq.d(), r, (long)r * r, Rq.d(), nth, (long)r * nth));
+        DDMPC_TRY(gemm(st, C, nf, nth, r, -1.0, Yqm, mat(Rq.d(), nth, 1, (long)r * nth), 1.0, X0f.d(), nth, 1, (long)nf * nth));
+    }
+    // Z = ZT + C_c^T G1 - C_c^T DT_c - DT_c^T C_c - N'^T X0f   (+ (Ac C_c)^T mu with the range constraint)
     const long sZ = (long)nth * nth;
     DDMPC_TRY(copy_bcast(st, C, sZ, ZT.d(), 0, pl.Z.d(), sZ));
     DDMPC_TRY(gemm(st, C, nth, nth, nfix, 1.0, tr(Ccm), mat(G1.d(), nth, 1, (long)nfix * nth), 1.0, pl.Z.d(), nth, 1, sZ));
@@ -522,6 +601,9 @@ static int build_robust(cudaStream_t st, Plan &pl, const FillArgs &fa, const int
     DDMPC_TRY(gemm(st, C, nth, nth, nfix, -1.0, tr(DTcm), Ccm, 1.0, pl.Z.d(), nth, 1, sZ));
     DDMPC_TRY(gemm(st, C, nth, nth, nf, -1.0, tr(mat(Nn.d(), nth, 1, (long)nf * nth)),
                    mat(X0f.d(), nth, 1, (long)nf * nth), 1.0, pl.Z.d(), nth, 1, sZ));
+    if (deficient)
+        DDMPC_TRY(gemm(st, C, nth, nth, r, 1.0, tr(mat(AcC.d(), nth, 1, CW == 1 ? 0 : (long)r * nth)),
+                       mat(Rq.d(), nth, 1, (long)r * nth), 1.0, pl.Z.d(), nth, 1, sZ));
     DDMPC_TRY(symmetrize(st, C, nth, pl.Z.d(), nth, sZ));
 
     if (nb > 0) {
@@ -531,6 +613,13 @@ static int build_robust(cudaStream_t st, Plan &pl, const FillArgs &fa, const int
         k_fill_Bt<<<g, 256, 0, st>>>(nf, nb, bpos_d, Y.d(), (long)nf * nb);
         DDMPC_LAUNCH_CHECK();
         DDMPC_TRY(potrs(st, C, nf, nb, P.d(), nx, sP, Y.d(), nb, (long)nf * nb));
+        if (deficient) {   // the response to a force on the box rows, with the range constraint: Y -= Yq S^-1 (Af Y)
+            DDMPC_CUDA(Rb.alloc(sizeof(double) * (size_t)C * r * nb));
+            DDMPC_TRY(gemm(st, C, r, nb, nf, 1.0, Af, mat(Y.d(), nb, 1, (long)nf * nb), 0.0, Rb.d(), nb, 1, (long)r * nb));
+            DDMPC_TRY(potrs(st, C, r, nb, Sq.d(), r, (long)r * r, Rb.d(), nb, (long)r * nb));
+            DDMPC_TRY(gemm(st, C, nf, nb, r, -1.0, mat(Yq.d(), r, 1, (long)nf * r), mat(Rb.d(), nb, 1, (long)r * nb), 1.0,
+                           Y.d(), nb, 1, (long)nf * nb));
+        }
         k_lam_rho<<<C, 256, 0, st>>>(nf, nb, d.nbs, d.nbu, bpos_d, Y.d(), (long)nf * nb, pl.blo.d(), pl.bhi.d(), pl.Lam.d(),
                                      Mm.d(), pl.rho2.d(), pl.rs.d(), pl.lo.d(), pl.hi.d(), pl.bmax.d());
         DDMPC_LAUNCH_CHECK();
@@ -846,8 +935,10 @@ int set_create_device(const ddmpc_params *prm, int count, const double *u_d, siz
         DDMPC_TRY(build_robust(st, pl, fa, perm_d.i(), invperm_d.i(), bpos_d.i(), R, Q, info_d.i()));
         std::vector<int> info(3 * count);
         DDMPC_CUDA(cudaMemcpy(info.data(), info_d.p, sizeof(int) * 3 * count, cudaMemcpyDeviceToHost));
+        // slot 0: Cholesky of W, one per data set - or, with short data (build_robust), of the Schur complement, one per controller
+        const bool per_ctrl = pl.data_count != 1 || d.cols < d.r;
         for (int c = 0; c < count; ++c)
-            if (pl.status[c] == DDMPC_OK && (info[pl.data_count == 1 ? 0 : c] || info[count + c] || info[2 * count + c]))
+            if (pl.status[c] == DDMPC_OK && (info[per_ctrl ? c : 0] || info[count + c] || info[2 * count + c]))
                 pl.status[c] = DDMPC_ERR_FACTORIZATION;
     } else {
         DDMPC_TRY(build_nominal(st, pl, fa, perm_d.i(), invperm_d.i(), u_d, (long)ud_stride, y_d, (long)yd_stride, R, Q));

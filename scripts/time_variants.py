@@ -45,7 +45,8 @@ def build_experiments() -> C.CDLL:
     csrc = os.path.dirname(_lib.LIB_PATH)
     if not os.path.exists(out) or os.path.getmtime(out) < os.path.getmtime(src):
         subprocess.run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler",
-                        "-fPIC", "-shared", "-o", out, src, "-L" + csrc, "-lddmpc"], check=True)
+                        "-fPIC", "-shared", "-o", out, src, "-L" + csrc, "-lddmpc", "-Xlinker", "-rpath", "-Xlinker",
+                        "$ORIGIN/../direct_data_driven_mpc_b200/csrc"], check=True)
     C.CDLL(_lib.LIB_PATH, mode=C.RTLD_GLOBAL)
     lib = C.CDLL(out)
     vp, i32, f64, u64 = C.c_void_p, C.c_int, C.c_double, C.c_uint64

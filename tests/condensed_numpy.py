@@ -88,8 +88,18 @@ def build_plan(n, m, p, u_d, y_d, L, Q, R, eps_max, lamb_alpha, lamb_sigma, c, s
         T[:nu, :nu] = np.eye(nu)
         T[nu:, nu:nu + ny] = np.eye(ny)
         T[nu:, nu + ny:] = np.eye(ny)
-        Lw = np.linalg.cholesky(W)
-        Om = sla.cho_solve((Lw, True), np.eye(r))
+        # Short data (fewer Hankel columns than rows: N - L - n + 1 < (L + n)(m + p), allowed by the reference down to
+        # N_min): W is singular, t = T x must stay in range(H) and ||alpha||^2 = t^T W^+ t there.  Null-space rows of W
+        # become the equality constraint Aeq x = 0, resolved by a Schur complement on top of the same reduced Hessian.
+        lam_w, V_w = np.linalg.eigh(W)
+        null = lam_w <= 1e-12 * lam_w.max()
+        Aeq = None
+        if null.any():
+            Om = (V_w[:, ~null] / lam_w[~null]) @ V_w[:, ~null].T
+            Aeq = V_w[:, null].T @ T
+        else:
+            Lw = np.linalg.cholesky(W)
+            Om = sla.cho_solve((Lw, True), np.eye(r))
         Om = 0.5 * (Om + Om.T)
         pl.Om = Om
         P = D + (lamb_alpha * eps_max) * (T.T @ Om @ T)
@@ -98,6 +108,12 @@ def build_plan(n, m, p, u_d, y_d, L, Q, R, eps_max, lamb_alpha, lamb_sigma, c, s
         Nmat = P[np.ix_(free, fix)] @ Cth[fix, :] - (D @ Tile)[free, :]
         La = np.linalg.cholesky(A)
         X0f = -sla.cho_solve((La, True), Nmat)          # x_f = X0f theta
+        if Aeq is not None:
+            Af, Ac = Aeq[:, free], Aeq[:, fix]
+            Yq = sla.cho_solve((La, True), Af.T)
+            Sq = Af @ Yq
+            Sq = 0.5 * (Sq + Sq.T)
+            X0f = X0f - Yq @ np.linalg.solve(Sq, Af @ X0f + Ac @ Cth[fix, :])
         X0 = np.zeros((nx, nth))
         X0[free] = X0f
         X0[fix] = Cth[fix]
@@ -133,6 +149,8 @@ def build_plan(n, m, p, u_d, y_d, L, Q, R, eps_max, lamb_alpha, lamb_sigma, c, s
             Bsel = np.zeros((nb, len(free)))
             Bsel[np.arange(nb), bidx] = 1.0
             Y = sla.cho_solve((La, True), Bsel.T)       # A^-1 B^T
+            if Aeq is not None:
+                Y = Y - Yq @ np.linalg.solve(Sq, Af @ Y)
             Lam = Bsel @ Y
             dg = np.diag(Lam)
             rs = np.ones(nb)                            # group equilibration as in k_lam_rho (first non-empty group = 1)

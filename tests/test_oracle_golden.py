@@ -150,6 +150,36 @@ def test_condensed_formulation_equals_literal_kkt(slack, term, c):
         assert abs(cost - so.cost) <= 1e-8 * max(1.0, abs(so.cost))
 
 
+@pytest.mark.parametrize("N,slack,term,c", [(113, O.SLACK_NONE, True, 1.0), (150, O.SLACK_NONE, False, 1.0),
+                                            (150, O.SLACK_CONVEX, True, 0.3)])
+def test_condensed_formulation_with_short_data_equals_literal_kkt(N, slack, term, c):
+    """Fewer Hankel columns than rows (the reference accepts N down to N_min = 113 here, controller.py:275-283): W = H H^T
+    is singular; the condensation then uses W^+ and keeps t in range(H) by a Schur complement (what setup.cu build_robust
+    does on the device).  Same optimum as the literal KKT system, which never forms W."""
+    plant = O.four_tank_plant()
+    params = O.four_tank_params()
+    rng = np.random.default_rng(1)
+    plant.x = rng.uniform(-1, 1, 4)
+    u_d, y_d = O.generate_initial_input_output_data(plant, N, [-1, 1], rng)
+    assert N - 34 + 1 < 136
+    qp = _qp(slack, O.ROBUST, term, u_d, y_d, c)
+    pl = CN.build_plan(4, 2, 2, u_d, y_d, 30, params["Q"], params["R"], params["eps_max"], params["lamb_alpha"],
+                       params["lamb_sigma"], c, slack, CN.ROBUST, term)
+    r = np.random.default_rng(N)
+    active = 0
+    for _ in range(3):
+        k = int(r.integers(0, N - 4))
+        up, yp = u_d[k:k + 4].reshape(-1, 1), y_d[k:k + 4].reshape(-1, 1)
+        us, ys = params["u_s"] * r.uniform(0.5, 1.5), params["y_s"] * r.uniform(0.5, 1.5)
+        so = qp.solve(up, yp, us, ys)
+        u, cost, st, it = CN.solve(pl, CN.make_theta(4, 2, 2, up, yp, us, ys), tol=1e-10, max_iter=5000)
+        active += it > 1
+        assert st == "optimal"
+        assert np.abs(u - so.optimal_u).max() <= 1e-8 * max(1.0, np.abs(so.optimal_u).max())
+        assert abs(cost - so.cost) <= 1e-8 * max(1.0, abs(so.cost))
+    assert slack == O.SLACK_NONE or active > 0
+
+
 @pytest.mark.parametrize("slack,term,box", [(O.SLACK_NONE, True, (-3.0, [5.0, 4.0])), (O.SLACK_CONVEX, True, (-3.0, 5.0)),
                                             (O.SLACK_NONE, False, (None, 6.0)), (O.SLACK_CONVEX, False, ([-1.0, -2.0], None))])
 def test_input_box_condensed_admm_equals_oracle_active_set(slack, term, box):
