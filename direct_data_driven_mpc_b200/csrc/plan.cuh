@@ -29,7 +29,7 @@ struct Plan {
     int count = 0;
     int data_count = 0;   // 1 when every controller shares one (u_d, y_d): H, W, Om exist once (lambda sweeps), else count
     DevBuf H;      // (r, cols)      stacked Hankel [H_u; H_y]   (HLn_ud / HLn_yd)
-    DevBuf Om;     // (r, r)         W^-1, W = H H^T             (robust; alpha recovery)
+    DevBuf Om;     // (r, r)         W^-1 (W^+ with short / rank-deficient data), W = H H^T   (robust; alpha recovery)
     DevBuf W;      // (r, r)         Gram matrix (kept for inspection)
     DevBuf Ku;     // (Lm, nth)      optimal_u = Ku theta
     DevBuf Z;      // (nth, nth)     unconstrained optimal cost = theta^T Z theta
@@ -50,6 +50,7 @@ struct Plan {
     DevBuf Fnz;    // (1) int        1 when F has a non-zero entry (rank-deficient data); 0 = every window is feasible
     DevBuf lamA, lamS;  // per-controller lamb_alpha*eps_max, lamb_sigma
     std::vector<int> pe_rank, status;
+    bool range_constrained = false;   // robust setup with a singular W: t kept in range(H) by a Schur complement (setup.cu)
     void detach_streams() {
         for (DevBuf *b : {&H, &Om, &W, &Ku, &Z, &X0, &Ks, &Phi, &Psi, &Lam, &Yf, &rho2, &rs, &lo, &hi, &bmax, &blo, &bhi,
                           &umin, &umax, &ymin, &ymax, &F, &Fnz, &lamA, &lamS})

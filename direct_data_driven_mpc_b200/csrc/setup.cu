@@ -516,11 +516,24 @@ static int build_robust(cudaStream_t st, Plan &pl, const FillArgs &fa, const int
     // W is singular, ||alpha||^2 = t^T W^+ t on range(H) and t = T x has to stay there.  Om becomes the pseudo-inverse
     // (eigen-decomposition instead of Cholesky) and the null-space rows of W an equality constraint Aeq x = 0 that is
     // resolved further down by a Schur complement on top of the same reduced Hessian.
-    const bool deficient = d.cols < r;
+    // The same path takes over when W has enough columns but is numerically singular all the same (noise-free data
+    // under a ROBUST controller): its Cholesky factorisation fails for some data set of the set.
+    bool deficient = d.cols < r;
     DevBuf Vw, lw, dinv, keep, Aeq, Yq, Sq, Rq, AcC, Rb;
     const long sAq = (long)r * nx, sAe = CW == 1 ? 0 : sAq;
     if (!deficient) {
         DDMPC_TRY(potrf(st, CW, r, Lw.d(), r, sW, info_d));
+        std::vector<int> hinfo(CW);
+        DDMPC_CUDA(cudaMemcpyAsync(hinfo.data(), info_d, sizeof(int) * CW, cudaMemcpyDeviceToHost, st));
+        DDMPC_CUDA(cudaStreamSynchronize(st));
+        for (int v : hinfo) deficient = deficient || v != 0;
+        if (deficient) {
+            DDMPC_CUDA(cudaMemsetAsync(info_d, 0, sizeof(int) * C, st));
+            DDMPC_TRY(copy_bcast(st, CW, sW, pl.W.d(), sW, Lw.d(), sW));
+        }
+    }
+    pl.range_constrained = deficient;
+    if (!deficient) {
         DDMPC_TRY(set_identity(st, CW, r, pl.Om.d(), r, sW));
         DDMPC_TRY(potrs(st, CW, r, r, Lw.d(), r, sW, pl.Om.d(), r, sW));
     } else {
@@ -936,7 +949,7 @@ int set_create_device(const ddmpc_params *prm, int count, const double *u_d, siz
         std::vector<int> info(3 * count);
         DDMPC_CUDA(cudaMemcpy(info.data(), info_d.p, sizeof(int) * 3 * count, cudaMemcpyDeviceToHost));
         // slot 0: Cholesky of W, one per data set - or, with short data (build_robust), of the Schur complement, one per controller
-        const bool per_ctrl = pl.data_count != 1 || d.cols < d.r;
+        const bool per_ctrl = pl.data_count != 1 || pl.range_constrained;
         for (int c = 0; c < count; ++c)
             if (pl.status[c] == DDMPC_OK && (info[per_ctrl ? c : 0] || info[count + c] || info[2 * count + c]))
                 pl.status[c] = DDMPC_ERR_FACTORIZATION;

@@ -238,20 +238,23 @@ def test_config5_lambda_horizon_grid_vs_oracle(L):
         assert abs(float(cost[c]) - so.cost) <= 1e-6 * max(1.0, abs(so.cost))
 
 
-@pytest.mark.parametrize("N,slack,c", [(113, 0, 1.0), (150, 0, 1.0), (150, 1, 0.3)])
-def test_short_data_robust_setup_vs_oracle(N, slack, c):
+@pytest.mark.parametrize("N,slack,c,exact", [(113, 0, 1.0, False), (150, 0, 1.0, False), (150, 1, 0.3, False),
+                                             (400, 0, 1.0, True)])
+def test_short_data_robust_setup_vs_oracle(N, slack, c, exact):
     """Fewer Hankel columns than rows (N - L - n + 1 < (L + n)(m + p)): the reference accepts N down to N_min = 113 for the
     four-tank configuration (controller.py:275-283), where the Gram matrix W of the stacked Hankel matrix is singular.
     The setup then works with the pseudo-inverse of W and keeps t = [ubar; ybar + sigma] in range(H) through a Schur
     complement (setup.cu build_robust): optimal inputs, cost and the primal alpha against the literal-KKT oracle, for a
-    grid of three (lambda_alpha, lambda_sigma) controllers that share the data, then a closed loop."""
+    grid of three (lambda_alpha, lambda_sigma) controllers that share the data, then a closed loop.  `exact`: enough
+    columns, but noise-free data under the ROBUST controller - W is singular all the same (rank m (L + n) + n_x = 72 of
+    136), its Cholesky factorisation fails and the same path takes over."""
     from direct_data_driven_mpc_b200 import ControllerSet, LTIPlant
     prm = O.four_tank_params()
-    plant = O.four_tank_plant()
+    plant = O.Plant(**{**O.FOUR_TANK, "eps_max": 0.0}) if exact else O.four_tank_plant()
     rng = np.random.default_rng(1)
     plant.x = rng.uniform(-1, 1, 4)
     u_d, y_d = O.generate_initial_input_output_data(plant, N, [-1, 1], rng)
-    assert N - 34 + 1 < 136
+    assert exact or N - 34 + 1 < 136
     la = np.array([50.0, 5.0, 500.0])
     ls = np.array([1000.0, 100.0, 1e4])
     cs = ControllerSet(4, 2, 2, u_d, y_d, 30, prm["Q"], prm["R"], prm["eps_max"], la, ls, c, slack, 1, 4, True, count=3)
