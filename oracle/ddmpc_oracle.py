@@ -311,7 +311,13 @@ class OracleQP:
         K[:self.nz, self.nz:] = self.Aeq.T
         K[self.nz:, :self.nz] = self.Aeq
         self.K = K
-        if self._cache_factor:
+        self._pinv = None
+        if self.robust and self.lamb_alpha * self.eps_max == 0.0:
+            # eps_max = 0 under a ROBUST controller (controller_creation.py:129-136 anticipates it): alpha carries no
+            # weight, the KKT matrix is singular in the alpha directions of null(H) while (ubar, ybar, sigma) stay
+            # unique - any KKT point will do, the minimum-norm one is taken
+            self._pinv = np.linalg.pinv(K, rcond=1e-13)
+        elif self._cache_factor:
             self._lu = sla.lu_factor(K)
 
     def _rhs(self, u_past, y_past, u_s, y_s):
@@ -329,6 +335,8 @@ class OracleQP:
         return q, np.concatenate(b), const
 
     def _kkt_solve(self, rhs):
+        if self._pinv is not None:
+            return self._pinv @ rhs
         if self._lu is not None:
             return sla.lu_solve(self._lu, rhs)
         return np.linalg.solve(self.K, rhs)

@@ -238,26 +238,29 @@ def test_config5_lambda_horizon_grid_vs_oracle(L):
         assert abs(float(cost[c]) - so.cost) <= 1e-6 * max(1.0, abs(so.cost))
 
 
-@pytest.mark.parametrize("N,slack,c,exact", [(113, 0, 1.0, False), (150, 0, 1.0, False), (150, 1, 0.3, False),
-                                             (400, 0, 1.0, True)])
-def test_short_data_robust_setup_vs_oracle(N, slack, c, exact):
+@pytest.mark.parametrize("N,slack,c,mode", [(113, 0, 1.0, "short"), (150, 0, 1.0, "short"), (150, 1, 0.3, "short"),
+                                            (400, 0, 1.0, "exact"), (400, 0, 1.0, "eps0")])
+def test_short_data_robust_setup_vs_oracle(N, slack, c, mode):
     """Fewer Hankel columns than rows (N - L - n + 1 < (L + n)(m + p)): the reference accepts N down to N_min = 113 for the
     four-tank configuration (controller.py:275-283), where the Gram matrix W of the stacked Hankel matrix is singular.
     The setup then works with the pseudo-inverse of W and keeps t = [ubar; ybar + sigma] in range(H) through a Schur
     complement (setup.cu build_robust): optimal inputs, cost and the primal alpha against the literal-KKT oracle, for a
-    grid of three (lambda_alpha, lambda_sigma) controllers that share the data, then a closed loop.  `exact`: enough
-    columns, but noise-free data under the ROBUST controller - W is singular all the same (rank m (L + n) + n_x = 72 of
-    136), its Cholesky factorisation fails and the same path takes over."""
+    grid of three (lambda_alpha, lambda_sigma) controllers that share the data, then a closed loop.
+    "exact": enough columns, but noise-free data under the ROBUST controller - W is singular all the same (rank
+    m (L + n) + n_x = 72 of 136), its Cholesky factorisation fails and the same path takes over.
+    "eps0": the noise-free configuration the reference's YAML loader anticipates (controller_creation.py:129-136:
+    eps_max = 0, lamb_alpha = 1000, so alpha carries no weight at all)."""
     from direct_data_driven_mpc_b200 import ControllerSet, LTIPlant
     prm = O.four_tank_params()
-    plant = O.Plant(**{**O.FOUR_TANK, "eps_max": 0.0}) if exact else O.four_tank_plant()
+    eps = 0.0 if mode == "eps0" else prm["eps_max"]
+    plant = O.four_tank_plant() if mode == "short" else O.Plant(**{**O.FOUR_TANK, "eps_max": 0.0})
     rng = np.random.default_rng(1)
     plant.x = rng.uniform(-1, 1, 4)
     u_d, y_d = O.generate_initial_input_output_data(plant, N, [-1, 1], rng)
-    assert exact or N - 34 + 1 < 136
-    la = np.array([50.0, 5.0, 500.0])
+    assert mode != "short" or N - 34 + 1 < 136
+    la = np.array([1000.0, 1000.0, 1000.0]) if mode == "eps0" else np.array([50.0, 5.0, 500.0])
     ls = np.array([1000.0, 100.0, 1e4])
-    cs = ControllerSet(4, 2, 2, u_d, y_d, 30, prm["Q"], prm["R"], prm["eps_max"], la, ls, c, slack, 1, 4, True, count=3)
+    cs = ControllerSet(4, 2, 2, u_d, y_d, 30, prm["Q"], prm["R"], eps, la, ls, c, slack, 1, 4, True, count=3)
     assert (cs.statuses() == 0).all()
     r = np.random.default_rng(N)
     ks = r.integers(0, N - 4, 3)
@@ -269,29 +272,30 @@ def test_short_data_robust_setup_vs_oracle(N, slack, c, exact):
     if slack:
         assert int(it.max()) > 1                                   # the slack bound binds
     for k in range(3):
-        qp = O.OracleQP(4, 2, 2, u_d, y_d, 30, prm["Q"], prm["R"], prm["eps_max"], la[k], ls[k], c, slack, O.ROBUST, True)
+        qp = O.OracleQP(4, 2, 2, u_d, y_d, 30, prm["Q"], prm["R"], eps, la[k], ls[k], c, slack, O.ROBUST, True)
         so = qp.solve(up[k], yp[k], us[k], ys[k])
         rel = np.abs(u[k].cpu().numpy() - so.optimal_u).max() / max(1.0, np.abs(so.optimal_u).max())
         assert rel < (1e-5 if slack else 1e-7), (N, k, rel)
         assert abs(float(cost[k]) - so.cost) <= (1e-5 if slack else 1e-6) * max(1.0, abs(so.cost)), (N, k)
-    # full primal: alpha = H^T W^+ t is the minimum-norm (and, the cost being strictly convex in alpha, the unique) alpha
+    # full primal: alpha = H^T W^+ t is the minimum-norm alpha - the unique one whenever alpha carries weight
     ub, yb, sg, al = cs.solve_full_batch(up, yp, us, ys, ctrl_idx=np.arange(3), tol=1e-9)
-    so = O.OracleQP(4, 2, 2, u_d, y_d, 30, prm["Q"], prm["R"], prm["eps_max"], la[0], ls[0], c, slack, O.ROBUST, True).solve(
+    so = O.OracleQP(4, 2, 2, u_d, y_d, 30, prm["Q"], prm["R"], eps, la[0], ls[0], c, slack, O.ROBUST, True).solve(
         up[0], yp[0], us[0], ys[0])
     tolp = 1e-4 if slack else 1e-6
-    assert np.abs(al[0].cpu().numpy() - so.alpha.reshape(-1)).max() < tolp * max(1.0, np.abs(so.alpha).max())
+    if mode != "eps0":
+        assert np.abs(al[0].cpu().numpy() - so.alpha.reshape(-1)).max() < tolp * max(1.0, np.abs(so.alpha).max())
     assert np.abs(sg[0].cpu().numpy() - so.sigma.reshape(-1)).max() < tolp * max(1.0, np.abs(so.sigma).max())
     assert np.abs(yb[0].cpu().numpy() - so.ybar.reshape(-1)).max() < tolp * max(1.0, np.abs(so.ybar).max())
     # closed loop with the first controller
     n_steps = 41
-    w = 0.002 * rng.uniform(-1, 1, (2, n_steps, 2))
+    w = eps * rng.uniform(-1, 1, (2, n_steps, 2))
     xs = np.stack([plant.x, plant.x + 0.05])
-    pl = LTIPlant(**{k: O.FOUR_TANK[k] for k in "ABCD"}, eps_max=0.002)
+    pl = LTIPlant(**{k: O.FOUR_TANK[k] for k in "ABCD"}, eps_max=eps)
     uu, yy, st, _ = cs.closed_loop(pl, xs, np.tile(u_d[-4:].reshape(1, -1), (2, 1)), np.tile(y_d[-4:].reshape(1, -1), (2, 1)),
                                    us[:2], ys[:2], n_steps, w=w, ctrl_idx=np.zeros(2, dtype=np.int32))
     assert int(st.max()) == 0
     for b in range(2):
-        ctrl = O.make_controller(prm, u_d, y_d, slack_type=slack, c=c)
+        ctrl = O.make_controller(prm, u_d, y_d, slack_type=slack, c=c, eps_max=eps, lamb_alpha=la[0])
         po = O.four_tank_plant()
         po.x = xs[b].copy()
         u_ref, y_ref = O.closed_loop(po, ctrl, n_steps, w[b])

@@ -150,6 +150,26 @@ def test_condensed_formulation_equals_literal_kkt(slack, term, c):
         assert abs(cost - so.cost) <= 1e-8 * max(1.0, abs(so.cost))
 
 
+def test_condensed_formulation_with_zero_alpha_weight_equals_literal_kkt():
+    """eps_max = 0 under a ROBUST controller, noise-free data (controller_creation.py:129-136 sets lamb_alpha = 1000 for
+    it): alpha carries no weight, W is singular.  (ubar, ybar, sigma) stay unique; the condensation with W^+ and the range
+    constraint finds them, the oracle takes the minimum-norm KKT point."""
+    plant = O.Plant(**{**O.FOUR_TANK, "eps_max": 0.0})
+    params = O.four_tank_params()
+    rng = np.random.default_rng(1)
+    plant.x = rng.uniform(-1, 1, 4)
+    u_d, y_d = O.generate_initial_input_output_data(plant, 400, [-1, 1], rng)
+    qp = O.OracleQP(4, 2, 2, u_d, y_d, 30, params["Q"], params["R"], 0.0, 1000.0, 1000.0, 1.0, O.SLACK_NONE, O.ROBUST, True)
+    pl = CN.build_plan(4, 2, 2, u_d, y_d, 30, params["Q"], params["R"], 0.0, 1000.0, 1000.0, 1.0, O.SLACK_NONE, CN.ROBUST, True)
+    for k in (10, 200, 390):
+        up, yp = u_d[k:k + 4].reshape(-1, 1), y_d[k:k + 4].reshape(-1, 1)
+        so = qp.solve(up, yp, params["u_s"], params["y_s"])
+        u, cost, st, it = CN.solve(pl, CN.make_theta(4, 2, 2, up, yp, params["u_s"], params["y_s"]))
+        assert so.status == "optimal" and st == "optimal"
+        assert np.abs(u - so.optimal_u).max() <= 1e-8 * max(1.0, np.abs(so.optimal_u).max())
+        assert abs(cost - so.cost) <= 1e-8 * max(1.0, abs(so.cost))
+
+
 @pytest.mark.parametrize("N,slack,term,c", [(113, O.SLACK_NONE, True, 1.0), (150, O.SLACK_NONE, False, 1.0),
                                             (150, O.SLACK_CONVEX, True, 0.3)])
 def test_condensed_formulation_with_short_data_equals_literal_kkt(N, slack, term, c):
