@@ -4,6 +4,10 @@
 #pragma once
 #include "fast_common.cuh"
 
+#ifndef WS_PHILOX_ROUNDS
+#define WS_PHILOX_ROUNDS 10   // (experiments build this header with fewer rounds to measure what the drawing costs)
+#endif
+
 namespace ddmpc {
 
 // ===========================================================================
@@ -21,7 +25,7 @@ namespace ddmpc {
 // is the first instead of the last summand of y.
 // ===========================================================================
 // NOSTORE (experiments only): the kernel without its trajectory stores, a measurement aid.
-template <int N, int M, int P, int NX, int NMPC, bool PHILOX, int MW, bool MD = false, bool NOSTORE = false>
+template <int N, int M, int P, int NX, int NMPC, bool PHILOX, int MW, int MD = 0, bool NOSTORE = false>
 __global__ void __launch_bounds__(32 * (MW + 1), 7)
 k_closed_loop_ws(const __grid_constant__ MmaCoef<N, M, P, NX, NMPC> cfp, const FastArgs a, const int n_tail) {
     constexpr int R = NMPC * M, NW = N * (M + P), LPT = 2, TP = 36, NT = 4;
@@ -30,10 +34,15 @@ k_closed_loop_ws(const __grid_constant__ MmaCoef<N, M, P, NX, NMPC> cfp, const F
     constexpr int WPG = MW == 4 ? 2 : 1;                       // math warps per loop group (they split its n-tiles)
     constexpr int NTW = NT / WPG;                              // n-tiles (of 8 loops) per math warp and loop group
     static_assert(MW == 1 || MW == 2 || MW == 4, "one, two or four math warps");
-    // MD (opt-in, DDMPC_WS_MATH_DRAWS=1): every math warp draws the Philox noise of its own loops and the i/o warp only
-    // records.  Measured slower (0.263 vs 0.240 ms): the math warps, not the i/o warp, are the critical path.
-    constexpr bool MATH_DRAWS = MD && PHILOX;
-    static_assert(!MD || MW >= 2, "math warps draw their own noise only with one loop group per warp");
+    // MD = 1 (experiments): every math warp draws the Philox noise of its own loops and the i/o warp only records.
+    // Measured slower (0.263 vs 0.240 ms): all of the drawing is too much for the math warps.
+    // MD = 2: the drawing is SHARED - a math lane draws the first Philox call of its loop and block, the i/o lane the
+    // second one of its two loops (source-level stall attribution showed the math warps waiting at the block barrier for
+    // the i/o warp a third of the time).
+    constexpr bool MATH_DRAWS = MD != 0 && PHILOX;
+    constexpr bool HALF = MD == 2 && PHILOX;
+    static_assert(MD == 0 || MW >= 2, "math warps draw their own noise only with one loop group per warp");
+    static_assert(MD != 2 || (MW == 2 && (NMPC * P) / 4 == 2), "shared drawing: two Philox calls per loop and block");
     static_assert(M == 2 && P == 2 && R == 8 && NMPC == N, "shape not supported by the warp-specialised kernel");
     static_assert(NW % 4 == 0 && (N * M) % 4 == 0 && KB % 4 == 0 && NX % 4 == 0 && RB <= 16 && RY == 8, "fragment tiling");
     __shared__ __align__(16) double csp_s[R][LPT][TP];         // set-point term of the planned inputs
@@ -107,11 +116,11 @@ k_closed_loop_ws(const __grid_constant__ MmaCoef<N, M, P, NX, NMPC> cfp, const F
             for (int l = 0; l < LPT; ++l) {
                 if constexpr (PHILOX) {
 #pragma unroll
-                    for (int cc = 0; cc < RY / 4; ++cc) {
+                    for (int cc = HALF ? 1 : 0; cc < RY / 4; ++cc) {
                         uint32_t c0 = (uint32_t)(((unsigned)tb * (unsigned)RY) >> 2) + (uint32_t)cc, c1 = 0u,
                                  c2 = sid_lo[l], c3 = sid_hi[l];
 #pragma unroll
-                        for (int r = 0; r < 10; ++r) philox_round(c0, c1, c2, c3, a.rk[2 * r], a.rk[2 * r + 1]);
+                        for (int r = 0; r < WS_PHILOX_ROUNDS; ++r) philox_round(c0, c1, c2, c3, a.rk[2 * r], a.rk[2 * r + 1]);
                         wy_s[buf][4 * cc + 0][l][SW(4 * cc + 0, tl)] = a.eps * (2.0 * unit32_fast(c0) - 3.0);
                         wy_s[buf][4 * cc + 1][l][SW(4 * cc + 1, tl)] = a.eps * (2.0 * unit32_fast(c1) - 3.0);
                         wy_s[buf][4 * cc + 2][l][SW(4 * cc + 2, tl)] = a.eps * (2.0 * unit32_fast(c2) - 3.0);
@@ -161,11 +170,11 @@ k_closed_loop_ws(const __grid_constant__ MmaCoef<N, M, P, NX, NMPC> cfp, const F
                 }
             }
         };
-        if (!MATH_DRAWS) draw(0, 0);
+        if (!MATH_DRAWS || HALF) draw(0, 0);
         __syncthreads();                                   // window, state and noise of block 0 are in place
         for (int t = 0; t < nblk; ++t) {
             if (t > 0) record(t - 1, NMPC);
-            if (!MATH_DRAWS && t + 1 < nblk) draw(t + 1, (t + 1) % 3);
+            if ((!MATH_DRAWS || HALF) && t + 1 < nblk) draw(t + 1, (t + 1) % 3);
             __syncthreads();                               // block t is complete
         }
         record(nblk - 1, n_tail ? n_tail : NMPC);
@@ -205,7 +214,7 @@ k_closed_loop_ws(const __grid_constant__ MmaCoef<N, M, P, NX, NMPC> cfp, const F
             : "d"(av), "d"(bv));
     };
     // noise of block tb for the warp's own loops: lane = (column, Philox call); see the i/o warp's draw()
-    constexpr int CPL = RY / 4 / WPG;                      // Philox calls per lane and block
+    constexpr int CPL = HALF ? 1 : RY / 4 / WPG;           // Philox calls per lane and block
     const int ncol = WPG == 2 ? 8 * t80 + (tl >> 1) : tl, ncc0 = WPG == 2 ? (tl & 1) : 0;
     const unsigned long long nsid = a.id0 + (unsigned long long)min(blockIdx.x * 64 + 2 * ncol + l0, a.B - 1);
     auto mdraw = [&](const int tb, const int buf) {
@@ -215,7 +224,7 @@ k_closed_loop_ws(const __grid_constant__ MmaCoef<N, M, P, NX, NMPC> cfp, const F
             uint32_t c0 = (uint32_t)(((unsigned)tb * (unsigned)RY) >> 2) + (uint32_t)ncc, c1 = 0u, c2 = (uint32_t)nsid,
                      c3 = (uint32_t)(nsid >> 32);
 #pragma unroll
-            for (int r = 0; r < 10; ++r) philox_round(c0, c1, c2, c3, a.rk[2 * r], a.rk[2 * r + 1]);
+            for (int r = 0; r < WS_PHILOX_ROUNDS; ++r) philox_round(c0, c1, c2, c3, a.rk[2 * r], a.rk[2 * r + 1]);
             wy_s[buf][4 * ncc + 0][l0][SW(4 * ncc + 0, ncol)] = a.eps * (2.0 * unit32_fast(c0) - 3.0);
             wy_s[buf][4 * ncc + 1][l0][SW(4 * ncc + 1, ncol)] = a.eps * (2.0 * unit32_fast(c1) - 3.0);
             wy_s[buf][4 * ncc + 2][l0][SW(4 * ncc + 2, ncol)] = a.eps * (2.0 * unit32_fast(c2) - 3.0);
