@@ -697,15 +697,16 @@ k_jacobi_smem(int n, double *__restrict__ A, long ld, long bsA, double *__restri
     lam += (long)blockIdx.x * bsl;
     const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, W = T >> 5;
     const int n2 = n + (n & 1), np2 = n2 / 2;
-    double *As = sh;                                  // n x n
-    double *cs_c = As + (size_t)n * n, *cs_s = cs_c + np2, *red = cs_s + np2;   // red[64]
+    const int lds = n | 1;                            // odd row stride: a column read by 32 lanes (rows) hits 32 different banks
+    double *As = sh;                                  // n x lds
+    double *cs_c = As + (size_t)n * lds, *cs_s = cs_c + np2, *red = cs_s + np2;   // red[64]
     int *pq = reinterpret_cast<int *>(red + 64);      // (p, q) of the pairs of the current round
     __shared__ int done;
     __shared__ double prev_off;
     if (threadIdx.x == 0) prev_off = 1e300;
     for (int i = warp; i < n; i += W)
         for (int j = lane; j < n; j += 32) {
-            As[(size_t)i * n + j] = A[(long)i * ld + j];
+            As[(size_t)i * lds + j] = A[(long)i * ld + j];
             if (V) V[(long)i * ldv + j] = (i == j) ? 1.0 : 0.0;
         }
     __syncthreads();
@@ -713,7 +714,7 @@ k_jacobi_smem(int n, double *__restrict__ A, long ld, long bsA, double *__restri
         double off = 0.0, tot = 0.0;
         for (int i = warp; i < n; i += W)
             for (int j = lane; j < n; j += 32) {
-                const double v = As[(size_t)i * n + j];
+                const double v = As[(size_t)i * lds + j];
                 tot += v * v;
                 if (i != j) off += v * v;
             }
@@ -739,9 +740,9 @@ k_jacobi_smem(int n, double *__restrict__ A, long ld, long bsA, double *__restri
                 jacobi_pair(n2, r, k, p, q);
                 double c = 1.0, s = 0.0;
                 if (q < n) {
-                    const double apq = As[(size_t)p * n + q];
+                    const double apq = As[(size_t)p * lds + q];
                     if (fabs(apq) > 1e-300) {
-                        const double tau = (As[(size_t)q * n + q] - As[(size_t)p * n + p]) / (2.0 * apq);
+                        const double tau = (As[(size_t)q * lds + q] - As[(size_t)p * lds + p]) / (2.0 * apq);
                         const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
                         c = 1.0 / sqrt(1.0 + t * t);
                         s = t * c;
@@ -753,17 +754,17 @@ k_jacobi_smem(int n, double *__restrict__ A, long ld, long bsA, double *__restri
                 pq[2 * k + 1] = q;
             }
             __syncthreads();
-            // column rotations  A <- A J : a warp per row, a lane per pair
-            for (int i = warp; i < n; i += W) {
-                double *arow = As + (size_t)i * n;
-                for (int k = lane; k < np2; k += 32) {
-                    const double s = cs_s[k];
-                    if (s == 0.0) continue;
-                    const double c = cs_c[k];
-                    const int p = pq[2 * k], q = pq[2 * k + 1];
-                    const double ap = arow[p], aq = arow[q];
-                    arow[p] = c * ap - s * aq;
-                    arow[q] = s * ap + c * aq;
+            // column rotations  A <- A J : a warp per pair, lanes down the two columns (conflict-free with the odd stride;
+            // a lane per pair along a row costs ~4 shared-memory wavefronts per access and was 3/4 of the kernel's time)
+            for (int k = warp; k < np2; k += W) {
+                const double s = cs_s[k];
+                if (s == 0.0) continue;
+                const double c = cs_c[k];
+                double *cp = As + pq[2 * k], *cq = As + pq[2 * k + 1];
+                for (int i = lane; i < n; i += 32) {
+                    const double ap = cp[(size_t)i * lds], aq = cq[(size_t)i * lds];
+                    cp[(size_t)i * lds] = c * ap - s * aq;
+                    cq[(size_t)i * lds] = s * ap + c * aq;
                 }
             }
             __syncthreads();
@@ -775,7 +776,7 @@ k_jacobi_smem(int n, double *__restrict__ A, long ld, long bsA, double *__restri
                 if (s == 0.0) continue;
                 const double c = cs_c[k];
                 const int p = pq[2 * k], q = pq[2 * k + 1];
-                double *rp = As + (size_t)p * n, *rq = As + (size_t)q * n;
+                double *rp = As + (size_t)p * lds, *rq = As + (size_t)q * lds;
                 for (int j = lane; j < n; j += 32) {
                     const double ap = rp[j], aq = rq[j];
                     rp[j] = c * ap - s * aq;
@@ -793,7 +794,7 @@ k_jacobi_smem(int n, double *__restrict__ A, long ld, long bsA, double *__restri
             __syncthreads();
         }
     }
-    for (int i = tid; i < n; i += T) lam[i] = As[(size_t)i * n + i];
+    for (int i = tid; i < n; i += T) lam[i] = As[(size_t)i * lds + i];
     // (A is documented as destroyed: its copy in global memory is left as it was)
     if (V) {                                          // V^T -> V, in place
         __syncthreads();
@@ -811,7 +812,7 @@ inline int jacobi_eig(cudaStream_t st, int batch, int n, double *A, long ld, lon
     if (n <= 0 || batch <= 0) return DDMPC_OK;
     {
         const int n2s = n + (n & 1);
-        const size_t shs = sizeof(double) * ((size_t)n * n + n2s + 64) + sizeof(int) * (size_t)n2s;
+        const size_t shs = sizeof(double) * ((size_t)n * (n | 1) + n2s + 64) + sizeof(int) * (size_t)n2s;
         if (shs <= 200 * 1024) {
             // (set on every call: the kernel is a per-translation-unit static, a shared "done" flag would not do)
             if (shs > 48 * 1024)
