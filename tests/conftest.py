@@ -49,4 +49,4 @@ def golden_hankel():
 def refclass():
     """Fixtures produced by the UNMODIFIED reference controller class (tests/golden/make_golden_refclass.py)."""
     return {k: np.load(os.path.join(GOLDEN, f"refclass_{k}.npz")) for k in
-            ("example_seed0", "reproduction_seed4", "variants", "errors", "config4")}
+            ("example_seed0", "reproduction_seed4", "variants", "errors", "config4", "short_data")}

@@ -292,15 +292,62 @@ def fixture_config4(n_steps=3):
     np.savez_compressed(os.path.join(HERE, "refclass_config4.npz"), **out)
 
 
+def fixture_short_data(seed=2):
+    """Data the reference class accepts although the Gram matrix of the stacked Hankel matrix is singular: N down to
+    N_min = 113 (fewer Hankel columns than rows), noise-free data under the ROBUST controller, and the eps_max = 0
+    configuration controller_creation.py:129-136 anticipates (lamb_alpha = 1000: alpha carries no weight).  A short closed
+    loop of the reference class per case, every solve recorded."""
+    out = {}
+    cases = [  # name, N, plant noise, eps_max, lamb_alpha, slack, c
+        ("nmin", 113, 0.002, 0.002, 50.0, SlackVarConstraintTypes.NONE, 1.0),
+        ("n150", 150, 0.002, 0.002, 50.0, SlackVarConstraintTypes.NONE, 1.0),
+        ("n150_convex", 150, 0.002, 0.002, 50.0, SlackVarConstraintTypes.CONVEX, 0.3),
+        ("exact", 400, 0.0, 0.002, 50.0, SlackVarConstraintTypes.NONE, 1.0),
+        ("eps0", 400, 0.0, 0.0, 1000.0, SlackVarConstraintTypes.NONE, 1.0),
+    ]
+    for name, N, noise, eps, lam_a, slack, c in cases:
+        model = LTISystemModel(config_file=MODEL_YAML, model_key_value="FourTankSystem")
+        model.eps_max = noise
+        cfg = get_data_driven_mpc_controller_params(CTRL_YAML, "data_driven_mpc_params", m=2, p=2)
+        rng = np.random.default_rng(seed)
+        model.set_state(rng.uniform(-1.0, 1.0, 4))
+        u_d = rng.uniform(-1.0, 1.0, (N, 2))
+        y_d = model.simulate(U=u_d, W=noise * rng.uniform(-1.0, 1.0, (N, 2)), steps=N)
+        x_loop0 = model.get_state().copy()
+        ctrl = DirectDataDrivenMPCController(
+            n=4, m=2, p=2, u_d=u_d, y_d=y_d, L=30, Q=cfg["Q"], R=cfg["R"], u_s=cfg["u_s"], y_s=cfg["y_s"], eps_max=eps,
+            lamb_alpha=lam_a, lamb_sigma=cfg["lamb_sigma"], c=c, slack_var_constraint_type=slack,
+            controller_type=DataDrivenMPCType.ROBUST, n_mpc_step=4, use_terminal_constraint=True)
+        n_steps = 21
+        u, y, w, log = run_loop(model, ctrl, n_steps, rng)
+        assert all(l[4] == "optimal" for l in log), name
+        oc = O.OracleController(4, 2, 2, u_d, y_d, 30, cfg["Q"], cfg["R"], cfg["u_s"], cfg["y_s"], eps, lam_a, cfg["lamb_sigma"], c,
+                                {SlackVarConstraintTypes.NONE: O.SLACK_NONE, SlackVarConstraintTypes.CONVEX: O.SLACK_CONVEX}[slack],
+                                O.ROBUST, 4, True)
+        po = O.four_tank_plant()
+        po.eps_max = noise
+        po.x = x_loop0.copy()
+        uo, yo = O.closed_loop(po, oc, n_steps, w)
+        print(f"short data {name}: N {N}, Hankel columns {N - 33} of 136 rows: oracle vs reference class: u {rel(uo, u):.2e}  y {rel(yo, y):.2e}")
+        out.update({f"{name}_u_d": u_d, f"{name}_y_d": y_d, f"{name}_x0": x_loop0, f"{name}_w": w, f"{name}_u": u, f"{name}_y": y,
+                    f"{name}_opt_u": np.stack([l[2] for l in log]), f"{name}_cost": np.array([l[3] for l in log]),
+                    f"{name}_params": np.array([N, noise, eps, lam_a, 1.0 if slack == SlackVarConstraintTypes.CONVEX else 0.0, c])})
+    np.savez_compressed(os.path.join(HERE, "refclass_short_data.npz"), **out)
+
+
 if __name__ == "__main__":
     if "--config4-only" in sys.argv:
         fixture_config4()
+        sys.exit(0)
+    if "--short-data-only" in sys.argv:
+        fixture_short_data()
         sys.exit(0)
     fixture_errors()
     fixture_variants()
     fixture_example()
     fixture_reproduction()
     fixture_config4()
+    fixture_short_data()
     for f in sorted(os.listdir(HERE)):
         if f.startswith("refclass_"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

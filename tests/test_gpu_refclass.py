@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 from oracle import ddmpc_oracle as O
-from test_refclass_golden import VARIANTS
+from test_refclass_golden import SHORT_DATA, VARIANTS
 
 pytestmark = pytest.mark.gpu
 
@@ -130,3 +130,38 @@ def test_config4_large_problem_vs_reference_class(refclass, n_mpc):
     uo, cost, st, _ = cs.solve_batch(sc["u_past0"], sc["y_past0"], prm["u_s"].T, prm["y_s"].T)
     assert _rel(uo.cpu().numpy()[0], g[f"opt_u_{n_mpc}"][0]) < 1e-8              # first solve: the whole L*m prediction
     assert abs(float(cost[0]) - g[f"cost_{n_mpc}"][0]) <= 1e-7 * max(1.0, abs(g[f"cost_{n_mpc}"][0]))
+
+
+@pytest.mark.parametrize("name", SHORT_DATA)
+def test_singular_gram_matrix_cases_vs_reference_class(refclass, name):
+    """Data the reference class accepts although W = H H^T is singular - N = N_min = 113 and N = 150 (fewer Hankel columns
+    than rows), noise-free data under the ROBUST controller, the eps_max = 0 configuration of the YAML loader: the drop-in
+    class driven step by step exactly as the reference's loop drives it (controller_operation.py:269-305) against the
+    recorded run of the unmodified reference class, every solve (whole prediction and problem.value) included."""
+    from direct_data_driven_mpc_b200 import DataDrivenMPCType, DirectDataDrivenMPCController, SlackVarConstraintTypes
+    g = refclass["short_data"]
+    N, noise, eps, lam_a, convex, c = g[f"{name}_params"]
+    prm = O.four_tank_params()
+    ctrl = DirectDataDrivenMPCController(
+        n=4, m=2, p=2, u_d=g[f"{name}_u_d"], y_d=g[f"{name}_y_d"], L=30, Q=prm["Q"], R=prm["R"], u_s=prm["u_s"], y_s=prm["y_s"],
+        eps_max=float(eps), lamb_alpha=float(lam_a), lamb_sigma=prm["lamb_sigma"], c=float(c),
+        slack_var_constraint_type=SlackVarConstraintTypes.CONVEX if convex else SlackVarConstraintTypes.NONE,
+        controller_type=DataDrivenMPCType.ROBUST, n_mpc_step=4, use_terminal_constraint=True)
+    plant = O.four_tank_plant()
+    plant.x = g[f"{name}_x0"].copy()
+    w = g[f"{name}_w"]
+    n_steps = w.shape[0]
+    u, y, opt, cost = np.zeros((n_steps, 2)), np.zeros((n_steps, 2)), [], []
+    for t in range(0, n_steps, 4):
+        ctrl.update_and_solve_data_driven_mpc()
+        assert ctrl.get_problem_solve_status() in ("optimal", "optimal_inaccurate")
+        opt.append(np.asarray(ctrl.optimal_u).reshape(-1).copy())
+        cost.append(ctrl.get_optimal_cost_value())
+        for k in range(t, min(t + 4, n_steps)):
+            u[k] = ctrl.get_optimal_control_input_at_step(n_step=k - t).reshape(-1)
+            y[k] = plant.simulate_step(u[k], w[k])
+            ctrl.store_input_output_measurement(u[k].reshape(-1, 1), y[k].reshape(-1, 1))
+    tol = 1e-5 if convex else 1e-7
+    assert _rel(u, g[f"{name}_u"]) < tol and _rel(y, g[f"{name}_y"]) < tol, (name, _rel(u, g[f"{name}_u"]))
+    assert _rel(np.stack(opt), g[f"{name}_opt_u"]) < tol
+    assert np.abs(np.array(cost) - g[f"{name}_cost"]).max() <= 1e-5 * max(1.0, np.abs(g[f"{name}_cost"]).max())

@@ -103,3 +103,25 @@ def test_config4_large_problem(refclass, n_mpc):
     u, y = O.closed_loop(po, oc, g[f"w_{n_mpc}"].shape[0], g[f"w_{n_mpc}"])
     assert _rel(u, g[f"u_{n_mpc}"]) < 1e-9 and _rel(y, g[f"y_{n_mpc}"]) < 1e-9
     assert _rel(oc.history[0][2], g[f"opt_u_{n_mpc}"][0]) < 1e-9
+
+
+SHORT_DATA = ["nmin", "n150", "n150_convex", "exact", "eps0"]
+
+
+@pytest.mark.parametrize("name", SHORT_DATA)
+def test_singular_gram_matrix_cases_vs_reference_class(refclass, name):
+    """Data the reference class accepts although W = H H^T is singular (N down to N_min, noise-free data, eps_max = 0):
+    the oracle's closed loop against the recorded run of the unmodified class, every solve of it included."""
+    g = refclass["short_data"]
+    N, noise, eps, lam_a, convex, c = g[f"{name}_params"]
+    prm = O.four_tank_params()
+    ctrl = O.OracleController(4, 2, 2, g[f"{name}_u_d"], g[f"{name}_y_d"], 30, prm["Q"], prm["R"], prm["u_s"], prm["y_s"], eps, lam_a,
+                              prm["lamb_sigma"], c, O.SLACK_CONVEX if convex else O.SLACK_NONE, O.ROBUST, 4, True)
+    plant = O.four_tank_plant()
+    plant.x = g[f"{name}_x0"].copy()
+    u, y = O.closed_loop(plant, ctrl, g[f"{name}_u"].shape[0], g[f"{name}_w"])
+    assert _rel(u, g[f"{name}_u"]) < 1e-9 and _rel(y, g[f"{name}_y"]) < 1e-9
+    opt = np.stack([h[2] for h in ctrl.history])
+    cost = np.array([h[3] for h in ctrl.history])
+    assert _rel(opt, g[f"{name}_opt_u"]) < 1e-8
+    assert np.abs(cost - g[f"{name}_cost"]).max() <= 1e-6 * max(1.0, np.abs(g[f"{name}_cost"]).max())
