@@ -856,7 +856,26 @@ def main():
             shard_times = {"error": repr(exc)}
     if rank == 0 and world == 1 and not args.no_secondary:
         secondary = {}
-        for name, fn in (("config4", lambda: secondary_config4(dev, fp64_peak=fp64_dmma)),
+
+        def secondary_step_major():
+            """The same workload with the trajectories stored step-major (n_steps, B, m): an OPTION for consumers that stay on
+            the device (the headline keeps the reference's per-loop layout).  Same numbers, other strides."""
+            us_, ys_ = u_sys.view(N_STEPS, B, 2), y_sys.view(N_STEPS, B, 2)
+            run = lambda: cs.closed_loop(plant, x0, up0, yp0, us, ys, N_STEPS, w=None, noise_seed=0, scenario_id0=id0,
+                                         noise_eps=0.002, out=(us_, ys_), layout="step_major")
+            run()
+            ms = median_ms(run, reps=20)
+            alg = B * N_STEPS * 4 * 8
+            out = {"workload": "config 3, trajectories stored (n_steps, B, m)", "loop_ms": ms,
+                   "solves_per_s": B * SOLVES_PER_LOOP / (ms * 1e-3), "achieved_gbs": alg / (ms * 1e-3) / 1e9,
+                   "frac_of_hbm_peak": alg / (ms * 1e-3) / 1e9 / peak if peak else None,
+                   "coalesced_store_floor_ms": floor_coal,
+                   "kernel": "k_closed_loop_ws, trajectory_layout = 1", "loop_major_ms": k_ms}
+            step()                                        # the headline buffers hold the loop-major result again
+            return out
+
+        for name, fn in (("step_major_layout", secondary_step_major),
+                         ("config4", lambda: secondary_config4(dev, fp64_peak=fp64_dmma)),
                          ("config2", lambda: secondary_config2(dev)),
                          ("config5", lambda: secondary_config5(dev)),
                          ("convex", lambda: secondary_convex(dev, sc, fp64_dmma, min(B, CONFIG3_LOOPS)))):

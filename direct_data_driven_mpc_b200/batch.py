@@ -255,13 +255,21 @@ class ControllerSet:
     def closed_loop(self, plant: LTIPlant, x0, u_past0, y_past0, u_s, y_s, n_steps: int, w=None,
                     noise_seed: int = 0, scenario_id0: int = 0, noise_eps: Optional[float] = None, ctrl_idx=None,
                     tol: float = 1e-8, max_iter: int = 2000, out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
-                    want_x_final: bool = False, check_idx: bool = True):
+                    want_x_final: bool = False, check_idx: bool = True, layout: str = "loop_major"):
         """B closed loops of ``n_steps`` steps, in lockstep on the device.
 
         w: (B, n_steps, p) pre-scaled noise (parity mode) or None for device Philox noise
         ``noise_eps * U(-1, 1)`` keyed by (noise_seed, scenario_id0 + b).
         Returns (u_sys (B, n_steps, m), y_sys (B, n_steps, p), status (B), iters (B)[, x_final]).
+
+        layout="step_major" (k_closed_loop_ws only: one shared ROBUST controller without slack bound, four-tank n-step
+        shape): the trajectories are STORED as (n_steps, B, m) - a warp then writes 1 KB runs instead of 32-byte pieces
+        6.4 KB apart, see DESIGN.md 3.1 - and returned as (B, n_steps, m) VIEWS of that storage (same indexing, different
+        strides); ``out`` buffers, when given, are the (n_steps, B, m) storage.
         """
+        if layout not in ("loop_major", "step_major"):
+            raise ValueError("layout must be 'loop_major' or 'step_major'")
+        step_major = layout == "step_major"
         dev = self.device
         x0t = _dev_f64(x0, dev)
         B = x0t.shape[0]
@@ -273,8 +281,9 @@ class ControllerSet:
         wt = None if w is None else _dev_f64(w, dev, (B, n_steps, self.p))
         ci = self._ctrl_idx(ctrl_idx, B, dev, check_idx)
         if out is None:
-            u_sys = torch.empty(B, n_steps, self.m, dtype=torch.float64, device=dev)
-            y_sys = torch.empty(B, n_steps, self.p, dtype=torch.float64, device=dev)
+            shape = (lambda c: (n_steps, B, c)) if step_major else (lambda c: (B, n_steps, c))
+            u_sys = torch.empty(*shape(self.m), dtype=torch.float64, device=dev)
+            y_sys = torch.empty(*shape(self.p), dtype=torch.float64, device=dev)
         else:
             u_sys, y_sys = out
         status = torch.empty(B, dtype=torch.int32, device=dev)
@@ -283,11 +292,19 @@ class ControllerSet:
         eps = plant.eps_max if noise_eps is None else noise_eps
         ps = plant.c_struct()
         with torch.cuda.device(dev):
-            _lib.check(_lib.lib.ddmpc_closed_loop_batch(
-                self._h, C.byref(ps), B, _ptr(ci), x0t.data_ptr(), up.data_ptr(), yp.data_ptr(), us.data_ptr(),
-                ys.data_ptr(), _ptr(wt), noise_seed, scenario_id0, float(eps), n_steps, tol, max_iter,
-                u_sys.data_ptr(), y_sys.data_ptr(), status.data_ptr(), iters.data_ptr(), _ptr(xf),
-                torch.cuda.current_stream().cuda_stream))
+            if step_major:
+                self.set_option("trajectory_layout", 1)
+            try:
+                _lib.check(_lib.lib.ddmpc_closed_loop_batch(
+                    self._h, C.byref(ps), B, _ptr(ci), x0t.data_ptr(), up.data_ptr(), yp.data_ptr(), us.data_ptr(),
+                    ys.data_ptr(), _ptr(wt), noise_seed, scenario_id0, float(eps), n_steps, tol, max_iter,
+                    u_sys.data_ptr(), y_sys.data_ptr(), status.data_ptr(), iters.data_ptr(), _ptr(xf),
+                    torch.cuda.current_stream().cuda_stream))
+            finally:
+                if step_major:
+                    self.set_option("trajectory_layout", 0)
+        if step_major:
+            u_sys, y_sys = u_sys.permute(1, 0, 2), y_sys.permute(1, 0, 2)
         if want_x_final:
             return u_sys, y_sys, status, iters, xf
         return u_sys, y_sys, status, iters

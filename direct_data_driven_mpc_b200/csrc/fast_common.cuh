@@ -29,6 +29,7 @@ struct FastArgs {
     const double *Ks, *Phi, *Psi;   // (nb, nth), (nb, nb), (L*m, nb)
     double bound, tol;
     int nb, nth, max_iter;
+    int step_major;      // 1: trajectories stored (n_steps, B, m) instead of (B, n_steps, m); k_closed_loop_ws only
 };
 
 __device__ __forceinline__ void philox_round(uint32_t &c0, uint32_t &c1, uint32_t &c2, uint32_t &c3, uint32_t k0,

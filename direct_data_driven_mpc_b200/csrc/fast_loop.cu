@@ -607,6 +607,7 @@ static int launch_fast(const ddmpc_set *set, const ddmpc_plant *plant, const Fas
                       ((reinterpret_cast<uintptr_t>(a.y_sys) & 31) == 0);
     // loops per thread: 2 once the batch is large enough to keep every SM busy with half the warps
     const int lpt = set->opt_lpt == 1 || set->opt_lpt == 2 ? set->opt_lpt : (a.B >= 16384 ? 2 : 1);
+    if (d.convex && set->opt_layout == 1) return -1;          // step-major trajectories: k_closed_loop_ws only
     if (d.convex) {
         // fused CONVEX path: slack rows through the tensor-core solve (needs LPT = 2 and 8 planned-input rows)
         constexpr bool CVX_OK = (NMPC * M == 8) && (NMPC % N == 0) && ((N * M) % 4 == 0) && ((N * P) % 4 == 0) &&
@@ -636,6 +637,7 @@ static int launch_fast(const ddmpc_set *set, const ddmpc_plant *plant, const Fas
         if constexpr (MMA_OK) {
             // (its serial chain is 0.071 ms for any batch up to 8192 loops: the fastest kernel from ~6000 loops on)
             const bool want_ws = set->opt_path == DDMPC_PATH_WS || set->opt_path == DDMPC_PATH_AUTO;
+            a.step_major = set->opt_layout;
             if (want_ws && pair) {
                 MmaCoef<N, M, P, NX, NMPC> mc;
                 for (int k = 0; k < NMPC * M; ++k)
@@ -657,7 +659,7 @@ static int launch_fast(const ddmpc_set *set, const ddmpc_plant *plant, const Fas
                 return DDMPC_OK;
             }
         }
-        if (set->opt_path == DDMPC_PATH_WS) return -1;      // asked for explicitly but not available for this shape
+        if (set->opt_path == DDMPC_PATH_WS || set->opt_layout == 1) return -1;   // asked for explicitly but not available for this shape
     }
     const int tpb = lpt == 1 ? 64 : 32;
     const dim3 grid(ceil_div(a.B, 64));

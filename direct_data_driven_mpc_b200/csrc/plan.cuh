@@ -67,7 +67,7 @@ struct ddmpc_set {
     ddmpc::Plan plan;
     // ddmpc_set_option(): kernel selection of ddmpc_closed_loop_batch (DDMPC_PATH_*), CTA size of the config-4 kernel,
     // loops per thread of the hybrid kernel (0 = automatic)
-    int opt_path = 0, opt_dmma_warps = 1, opt_lpt = 0, opt_solve = 0, opt_cvx_ctas = 3, opt_tc_passes = 3;
+    int opt_path = 0, opt_dmma_warps = 1, opt_lpt = 0, opt_solve = 0, opt_cvx_ctas = 3, opt_tc_passes = 3, opt_layout = 0;
     // per-controller setup verdicts on the device (count ints, DDMPC_OK or the error): kernels report failed
     // controllers as DDMPC_SOLVE_NONFINITE with NaN outputs instead of finite garbage
     ddmpc::DevBuf ctrl_status;

@@ -1111,6 +1111,9 @@ int ddmpc_set_option(ddmpc_set *set, const char *name, int value) {
     } else if (nm == "cvx_ctas_per_sm") {
         if (value != 2 && value != 3) return fail(DDMPC_ERR_INVALID_ARG, "set_option: cvx_ctas_per_sm must be 2 or 3");
         set->opt_cvx_ctas = value;
+    } else if (nm == "trajectory_layout") {
+        if (value != 0 && value != 1) return fail(DDMPC_ERR_INVALID_ARG, "set_option: trajectory_layout must be 0 (loop-major) or 1 (step-major)");
+        set->opt_layout = value;
     } else if (nm == "tc_passes") {
         if (value < 1 || value > 3) return fail(DDMPC_ERR_INVALID_ARG, "set_option: tc_passes must be 1, 2 or 3");
         set->opt_tc_passes = value;

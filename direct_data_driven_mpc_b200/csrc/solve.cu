@@ -862,6 +862,19 @@ int ddmpc_closed_loop_batch(const ddmpc_set *set, const ddmpc_plant *plant, int 
     cudaStream_t st = (cudaStream_t)stream;
     const int nxp = plant->n_x;
     const int path = set->opt_path;
+    if (set->opt_layout == 1) {
+        // step-major trajectories (n_steps, B, m): an option for consumers that stay on the device; only the warp-specialised
+        // kernel of the four-tank n-step shape writes them
+        const int rc = (path == DDMPC_PATH_AUTO || path == DDMPC_PATH_WS)
+                           ? closed_loop_fast_try(set, plant, B, ctrl_idx, x0, u_past0, y_past0, u_s, y_s, w, noise_seed,
+                                                  scenario_id0, noise_eps, n_steps, u_sys, y_sys, status, iters, x_final, tol,
+                                                  max_iter, st)
+                           : -1;
+        if (rc != -1) return rc;
+        return fail(DDMPC_ERR_NOT_IMPLEMENTED,
+                    "trajectory_layout = step-major is implemented by k_closed_loop_ws only (one shared ROBUST controller without "
+                    "slack bound, four-tank n-step shape, paths auto / ws)");
+    }
     if (path != DDMPC_PATH_GENERIC) {
         if (path == DDMPC_PATH_TC) {   // opt-in: config-4 shape on tcgen05 / TMEM with TF32x3 arithmetic
             const int rc = closed_loop_tc_try(set, plant, B, ctrl_idx, x0, u_past0, y_past0, u_s, y_s, w, noise_seed,

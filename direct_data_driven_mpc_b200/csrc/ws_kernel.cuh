@@ -140,6 +140,48 @@ k_closed_loop_ws(const __grid_constant__ MmaCoef<N, M, P, NX, NMPC> cfp, const F
         // record the `steps` trajectory elements of block tb (full 32-byte sectors, see emit())
         auto record = [&](const int tb, const int steps) {
             const int ub = tb & 1, yb = tb % 3;
+            if (a.step_major) {
+                // (n_steps, B, m): the two loops of a lane are neighbours, a warp writes 1024 contiguous bytes per step
+                const size_t e0 = (size_t)blockIdx.x * 64 + 2 * tl;
+                const bool l0 = e0 < (size_t)a.B, l1 = e0 + 1 < (size_t)a.B;
+#pragma unroll
+                for (int s = 0; s < NMPC; ++s) {
+                    if (s < steps && l0 && !NOSTORE) {
+                        const size_t e = (size_t)(tb * NMPC + s) * a.B + e0;
+                        double u[LPT][M], y[LPT][P];
+#pragma unroll
+                        for (int l = 0; l < LPT; ++l) {
+#pragma unroll
+                            for (int i = 0; i < M; ++i) u[l][i] = up_s[ub][s * M + i][l][SW(s * M + i, tl)];
+#pragma unroll
+                            for (int i = 0; i < P; ++i) y[l][i] = wy_s[yb][s * P + i][l][SW(s * P + i, tl)];
+                        }
+                        if (l1 && (e & 1) == 0) {
+                            asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(a.u_sys + e * 2), "d"(u[0][0]),
+                                         "d"(u[0][1]), "d"(u[1][0]), "d"(u[1][1])
+                                         : "memory");
+                            asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(a.y_sys + e * 2), "d"(y[0][0]),
+                                         "d"(y[0][1]), "d"(y[1][0]), "d"(y[1][1])
+                                         : "memory");
+                        } else {
+                            *reinterpret_cast<double2 *>(a.u_sys + e * 2) = make_double2(u[0][0], u[0][1]);
+                            *reinterpret_cast<double2 *>(a.y_sys + e * 2) = make_double2(y[0][0], y[0][1]);
+                            if (l1) {
+                                *reinterpret_cast<double2 *>(a.u_sys + (e + 1) * 2) = make_double2(u[1][0], u[1][1]);
+                                *reinterpret_cast<double2 *>(a.y_sys + (e + 1) * 2) = make_double2(y[1][0], y[1][1]);
+                            }
+                        }
+                    }
+                }
+                // (the verdict below reads the last outputs from (py): keep it current)
+#pragma unroll
+                for (int l = 0; l < LPT; ++l) {
+                    const int sl = steps - 1;
+#pragma unroll
+                    for (int i = 0; i < P; ++i) py[l][i] = wy_s[yb][sl * P + i][l][SW(sl * P + i, tl)];
+                }
+                return;
+            }
 #pragma unroll
             for (int l = 0; l < LPT; ++l) {
 #pragma unroll
@@ -182,7 +224,7 @@ k_closed_loop_ws(const __grid_constant__ MmaCoef<N, M, P, NX, NMPC> cfp, const F
         for (int l = 0; l < LPT; ++l) {
             if (!live[l]) continue;
             const size_t fl = f0[l] + a.n_steps - 1;
-            if ((fl & 1) == 0) {                           // an unpaired final element is still in (pu, py)
+            if ((fl & 1) == 0 && !a.step_major) {          // an unpaired final element is still in (pu, py)
                 *reinterpret_cast<double2 *>(a.u_sys + fl * 2) = make_double2(pu[l][0], pu[l][1]);
                 *reinterpret_cast<double2 *>(a.y_sys + fl * 2) = make_double2(py[l][0], py[l][1]);
             }

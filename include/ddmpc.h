@@ -228,7 +228,11 @@ enum {
 };
 /* Per-set options: "closed_loop_path" (DDMPC_PATH_*), "dmma_warps" (1, 2 or 4: CTA size of the config-4 kernel),
  * "loops_per_thread" (0 = automatic, 1, 2: hybrid kernel), "solve_path" (0 = automatic, 1 = thread / CTA per solve kernels,
- * 2 = tensor-core ADMM pipeline where it applies), "cvx_ctas_per_sm" (2 or 3: register budget of k_closed_loop_cvx).  Not thread-safe against running calls on the same set. */
+ * 2 = tensor-core ADMM pipeline where it applies), "cvx_ctas_per_sm" (2 or 3: register budget of k_closed_loop_cvx), "tc_passes" (1..3: TF32 passes of the tcgen05 path),
+ * "trajectory_layout" (0 = u_sys [B, n_steps, m] / y_sys [B, n_steps, p] as documented at ddmpc_closed_loop_batch - the
+ * reference's per-loop arrays stacked; 1 = step-major [n_steps, B, m] / [n_steps, B, p] for consumers that stay on the
+ * device: written by k_closed_loop_ws only, DDMPC_ERR_NOT_IMPLEMENTED elsewhere).  Not thread-safe against running calls
+ * on the same set. */
 int ddmpc_set_option(ddmpc_set *set, const char *name, int value);
 
 /* Number of controllers of the set whose setup failed (not persistently exciting / factorisation); their indices

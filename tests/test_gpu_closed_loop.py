@@ -538,6 +538,36 @@ def test_fused_four_tank_kernels_match_each_other():
         cs.set_option("closed_loop_path", "auto")
 
 
+def test_step_major_trajectory_layout_is_the_same_numbers():
+    """layout="step_major": k_closed_loop_ws stores (n_steps, B, m) - coalesced 1 KB runs per warp and step - and the API
+    returns (B, n_steps, m) views of it.  Bit-identical to the loop-major result: even and odd batch sizes (an odd B
+    breaks the 32-byte alignment of every other step), a ragged last CTA, a partial last block, uploaded noise; paths that
+    cannot write the layout refuse."""
+    import torch
+    plant_o, prm, rng, x0, u_d, y_d = O.example_scenario(0)
+    cs, _ = _set(u_d, y_d)
+    r = np.random.default_rng(15)
+    for B, n_steps, up in ((16384 + 70, 401, False), (8192 + 33, 42, False), (6401, 13, True)):
+        xs = np.tile(plant_o.x, (B, 1)) + 0.05 * r.normal(size=(B, 4))
+        us = np.tile(prm["u_s"].T, (B, 1)) * r.uniform(0.7, 1.3, (B, 1))
+        ys = us @ _plant().equilibrium_gain().T
+        up0, yp0 = np.tile(u_d[-4:].reshape(1, -1), (B, 1)), np.tile(y_d[-4:].reshape(1, -1), (B, 1))
+        kw = dict(w=0.002 * r.uniform(-1, 1, (B, n_steps, 2))) if up else dict(noise_seed=3, scenario_id0=11, noise_eps=0.002)
+        cs.set_option("closed_loop_path", "ws")
+        u1, y1, s1, i1, x1 = cs.closed_loop(_plant(), xs, up0, yp0, us, ys, n_steps, want_x_final=True, **kw)
+        l0 = _launches()
+        u2, y2, s2, i2, x2 = cs.closed_loop(_plant(), xs, up0, yp0, us, ys, n_steps, want_x_final=True, layout="step_major", **kw)
+        assert _launches() - l0 == 1
+        assert u2.shape == u1.shape and not u2.is_contiguous() and u2.permute(1, 0, 2).is_contiguous()
+        assert torch.equal(u1, u2) and torch.equal(y1, y2) and torch.equal(x1, x2) and torch.equal(s1, s2) and torch.equal(i1, i2)
+    cs.set_option("closed_loop_path", "perloop")
+    with pytest.raises(NotImplementedError):
+        cs.closed_loop(_plant(), xs, up0, yp0, us, ys, 13, layout="step_major", noise_seed=1, noise_eps=0.002)
+    cs.set_option("closed_loop_path", "auto")
+    u3, _, _, _ = cs.closed_loop(_plant(), xs, up0, yp0, us, ys, 13, noise_seed=1, noise_eps=0.002)   # the option did not stick
+    assert u3.is_contiguous()
+
+
 @pytest.mark.parametrize("path", ["auto", "perloop", "fast"])
 def test_warp_specialised_kernel_vs_oracle(path):
     """Large-batch paths (k_closed_loop_ws by default; the 8-lanes-per-loop and hybrid kernels when forced) against the
