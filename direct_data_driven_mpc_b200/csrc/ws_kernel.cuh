@@ -25,8 +25,11 @@ namespace ddmpc {
 // is the first instead of the last summand of y.
 // ===========================================================================
 // NOSTORE (experiments only): the kernel without its trajectory stores, a measurement aid.
-template <int N, int M, int P, int NX, int NMPC, bool PHILOX, int MW, int MD = 0, bool NOSTORE = false>
-__global__ void __launch_bounds__(32 * (MW + 1), 7)
+// IOW = 2 (experiments): the i/o work on TWO warps, one drawing, one recording (the review's lever: CTAs of 2 + 2 warps,
+// roles swapped on bit 2 of the hardware warp slot so that the math warps of successive CTAs alternate between the
+// scheduler pairs).
+template <int N, int M, int P, int NX, int NMPC, bool PHILOX, int MW, int MD = 0, bool NOSTORE = false, int IOW = 1>
+__global__ void __launch_bounds__(32 * (MW + IOW), 7)
 k_closed_loop_ws(const __grid_constant__ MmaCoef<N, M, P, NX, NMPC> cfp, const FastArgs a, const int n_tail) {
     constexpr int R = NMPC * M, NW = N * (M + P), LPT = 2, TP = 36, NT = 4;
     constexpr int KB = NX + R, RB = NMPC * P + NX, RY = NMPC * P;
@@ -65,17 +68,19 @@ k_closed_loop_ws(const __grid_constant__ MmaCoef<N, M, P, NX, NMPC> cfp, const F
     if (threadIdx.x == 0) {
         unsigned slot;
         asm volatile("mov.u32 %0, %%warpid;" : "=r"(slot));
-        swap_s = MW == 1 ? (slot >> 2) & 1 : 0;
+        swap_s = (MW == 1 || IOW == 2) ? (slot >> 2) & 1 : 0;
     }
     __syncthreads();
-    const int warp = (threadIdx.x >> 5) ^ swap_s;
+    static_assert(IOW == 1 || (IOW == 2 && MW == 2 && MD == 0), "two i/o warps: with two math warps, i/o warps draw");
+    const int warp = IOW == 2 ? (threadIdx.x >> 5) ^ (swap_s << 1) : (threadIdx.x >> 5) ^ swap_s;
     const int l0 = MW == 1 ? 0 : warp / WPG;       // first loop group of this math warp
     const int t80 = (warp % WPG) * NTW;            // its first n-tile inside the group
     const int cb = g ^ (((q >> 1) & 1) << 2);      // swizzled column of a B-fragment element (row = 4ks + q)
     const int cc2 = (2 * q) ^ (((g >> 1) & 1) << 2);  // swizzled column of a C-fragment pair (row = g)
 
-    if (warp == MW) {
+    if (warp >= MW) {
         // ------------------------------------------------------------------ i/o warp: thread tl owns loops 2tl, 2tl+1
+        const bool do_draw = IOW == 1 || warp == MW, do_rec = IOW == 1 || warp == MW + 1;
         int b[LPT];
         bool live[LPT];
         size_t f0[LPT];
@@ -91,6 +96,7 @@ k_closed_loop_ws(const __grid_constant__ MmaCoef<N, M, P, NX, NMPC> cfp, const F
             sid_lo[l] = (uint32_t)sid;
             sid_hi[l] = (uint32_t)(sid >> 32);
             pu[l][0] = pu[l][1] = py[l][0] = py[l][1] = 0.0;
+            if (!do_draw) continue;                  // (the drawing warp sets the CTA's state up)
 #pragma unroll
             for (int i = 0; i < NX; ++i) x_s[i][l][SW(i, tl)] = a.x0[(size_t)b[l] * NX + i];
 #pragma unroll
@@ -212,13 +218,14 @@ k_closed_loop_ws(const __grid_constant__ MmaCoef<N, M, P, NX, NMPC> cfp, const F
                 }
             }
         };
-        if (!MATH_DRAWS || HALF) draw(0, 0);
+        if ((!MATH_DRAWS || HALF) && do_draw) draw(0, 0);
         __syncthreads();                                   // window, state and noise of block 0 are in place
         for (int t = 0; t < nblk; ++t) {
-            if (t > 0) record(t - 1, NMPC);
-            if ((!MATH_DRAWS || HALF) && t + 1 < nblk) draw(t + 1, (t + 1) % 3);
+            if (t > 0 && do_rec) record(t - 1, NMPC);
+            if ((!MATH_DRAWS || HALF) && do_draw && t + 1 < nblk) draw(t + 1, (t + 1) % 3);
             __syncthreads();                               // block t is complete
         }
+        if (!do_rec) return;
         record(nblk - 1, n_tail ? n_tail : NMPC);
 #pragma unroll
         for (int l = 0; l < LPT; ++l) {

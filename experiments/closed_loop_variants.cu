@@ -753,6 +753,8 @@ extern "C" int ddmpc_exp_closed_loop(const ddmpc_set *set, const ddmpc_plant *pl
     else if (v == "ws2md") EXP_RUN((k_closed_loop_ws<N, M, P, NX, NMPC, false, 2>), (k_closed_loop_ws<N, M, P, NX, NMPC, true, 2, 1>), g64, 96);
     else if (v == "ws2mh" && nostore) EXP_RUN((k_closed_loop_ws<N, M, P, NX, NMPC, false, 2, 0, true>), (k_closed_loop_ws<N, M, P, NX, NMPC, true, 2, 2, true>), g64, 96);
     else if (v == "ws2mh") EXP_RUN((k_closed_loop_ws<N, M, P, NX, NMPC, false, 2>), (k_closed_loop_ws<N, M, P, NX, NMPC, true, 2, 2>), g64, 96);
+    else if (v == "ws2io2" && nostore) EXP_RUN((k_closed_loop_ws<N, M, P, NX, NMPC, false, 2, 0, true, 2>), (k_closed_loop_ws<N, M, P, NX, NMPC, true, 2, 0, true, 2>), g64, 128);
+    else if (v == "ws2io2") EXP_RUN((k_closed_loop_ws<N, M, P, NX, NMPC, false, 2, 0, false, 2>), (k_closed_loop_ws<N, M, P, NX, NMPC, true, 2, 0, false, 2>), g64, 128);
     else if (v == "ws2" && nostore) EXP_RUN((k_closed_loop_ws<N, M, P, NX, NMPC, false, 2, 0, true>), (k_closed_loop_ws<N, M, P, NX, NMPC, true, 2, 0, true>), g64, 96);
     else if (v == "ws2") EXP_RUN((k_closed_loop_ws<N, M, P, NX, NMPC, false, 2>), (k_closed_loop_ws<N, M, P, NX, NMPC, true, 2>), g64, 96);
     else return fail(DDMPC_ERR_INVALID_ARG, "exp: unknown variant '%s'", variant);
