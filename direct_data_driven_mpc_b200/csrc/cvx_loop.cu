@@ -429,6 +429,10 @@ struct CvxSmem {
     double sp[4][CV_DS];       // set-points [u_s; y_s]
     double x[4][CV_DS];        // plant state
     float thf[2][16][CV_FS];   // FP32 copy of the windows: B operand of the TF32 screen
+    double cmax[16];           // level-0 screen: max_j |Ks[j][k]| over the slack rows, per window entry k
+    double gss[CV_NR][4];      // level-0 screen: slack rows at a set-point, s_ss = gss [u_s; y_s]
+    double smax_ss[CV_NL];     // level-0 screen: max_j |s_ss,j| of each loop
+    unsigned qflag[2][4];      // level-0 verdict per warp for the window of that parity (0 = provably inside the box)
     AdmmSmem admm;
 };
 
@@ -489,6 +493,56 @@ k_closed_loop_cvx(const __grid_constant__ CvxMaps maps, const CvxArgs a) {
         sm.sp[q][lcol] = q < 2 ? a.u_s[(size_t)b * 2 + q] : a.y_s[(size_t)b * 2 + (q - 2)];
     }
     if (tid < CV_NL) { sm.admm.extra[tid] = 0; sm.admm.stat[tid] = DDMPC_SOLVE_OPTIMAL; }
+    // ---- level-0 screen (see the block loop): column maxima of |Ks| over the window entries, and the slack rows at a
+    //      set-point as a 4-column map of [u_s; y_s] (the window of a settled loop is its set-point repeated)
+    if (tid < 16) {
+        double m = 0.0;
+        for (int j = 0; j < a.nb; ++j) m = fmax(m, fabs(__ldg(a.Ks + (size_t)j * a.nth + tid)));
+        sm.cmax[tid] = m;
+    }
+    for (int e = tid; e < CV_NR * 4; e += 128) {
+        const int j = e >> 2, i = e & 3;
+        double gsum = 0.0;
+        if (j < a.nb) {
+            const double *row = a.Ks + (size_t)j * a.nth;
+            const int base = i < 2 ? i : 8 + (i - 2);                 // window entries of channel i: base + 2 t, t = 0..3
+#pragma unroll
+            for (int tt = 0; tt < 4; ++tt) gsum += __ldg(row + base + 2 * tt);
+            gsum += __ldg(row + 16 + i);                             // its set-point column
+        }
+        sm.gss[j][i] = gsum;
+    }
+    __syncthreads();
+    {
+        // the four lanes of a loop share its 64 rows
+        const double u0 = sm.sp[0][lcol], u1 = sm.sp[1][lcol], y0 = sm.sp[2][lcol], y1 = sm.sp[3][lcol];
+        double m = 0.0;
+        for (int j = q; j < CV_NR; j += 4)
+            m = fmax(m, fabs(sm.gss[j][0] * u0 + sm.gss[j][1] * u1 + sm.gss[j][2] * y0 + sm.gss[j][3] * y1));
+        m = fmax(m, __shfl_xor_sync(0xffffffffu, m, 1));
+        m = fmax(m, __shfl_xor_sync(0xffffffffu, m, 2));
+        if (q == 0) sm.smax_ss[lcol] = m;
+    }
+    __syncwarp();
+    // Level-0 screen of the window in buffer `par` (a compile-time constant at every call site).  For every slack row j:
+    //   |s_j(theta)| = |s_ss,j + sum_k Ks[j][k] (theta_k - theta_ss,k)| <= max_j |s_ss,j| + sum_k cmax[k] |theta_k - theta_ss,k|
+    // with theta_ss the window of the settled loop (its set-point repeated; the set-point entries of theta cancel).  Twenty
+    // multiply-adds per loop prove "inside the box" for a settled loop, where the TF32 screen costs 24 tensor-core MMAs per
+    // warp and the exact check 40 FP64 ones.  Lane (g, q) holds window step q of loop 8 warp + g; NaN fails the test.
+    const double thr0 = a.bhi[0] * (1.0 - 1e-9);
+    auto level0 = [&](auto par_c) {
+        constexpr int par = decltype(par_c)::value;
+        const double d = sm.cmax[2 * q] * fabs(sm.th[par][2 * q][lcol] - sm.sp[0][lcol]) +
+                         sm.cmax[2 * q + 1] * fabs(sm.th[par][2 * q + 1][lcol] - sm.sp[1][lcol]) +
+                         sm.cmax[8 + 2 * q] * fabs(sm.th[par][8 + 2 * q][lcol] - sm.sp[2][lcol]) +
+                         sm.cmax[8 + 2 * q + 1] * fabs(sm.th[par][8 + 2 * q + 1][lcol] - sm.sp[3][lcol]);
+        double tot = d + __shfl_xor_sync(0xffffffffu, d, 1);
+        tot += __shfl_xor_sync(0xffffffffu, tot, 2);
+        const bool fail = !(sm.smax_ss[lcol] + tot <= thr0);
+        const unsigned any = __any_sync(0xffffffffu, fail) ? 1u : 0u;
+        if (lane == 0) sm.qflag[par][warp] = any;
+    };
+    level0(std::integral_constant<int, 0>{});
     // ---- A fragments that stay in registers: gain rows (8 x 20), slack rows of this warp (16 x 20), plant block map
     double aKu[NSPK], aMb[2][3];
     uint32_t fKs[2][3][2], spb[CV_NT];                               // TF32 screen: slack rows, set-points
@@ -532,6 +586,8 @@ k_closed_loop_cvx(const __grid_constant__ CvxMaps maps, const CvxArgs a) {
         constexpr int cur = decltype(parity)::value, nxt = cur ^ 1;
         if (t == nblk - 1 && a.n_tail != 0) load_map(maps.Mt);       // last, partial block (controller_operation.py:278)
         __syncthreads();                                             // window / state / set-points of all 32 loops are in place
+        // level-0 verdicts of the four warps for this window (written at the end of the previous block)
+        const bool quiet = (sm.qflag[cur][0] | sm.qflag[cur][1] | sm.qflag[cur][2] | sm.qflag[cur][3]) == 0u;
         // ---- measurement noise of (loop, step q): parked in the output rows of the next window, where the plant
         //      product's accumulators start from it
         {
@@ -570,6 +626,10 @@ k_closed_loop_cvx(const __grid_constant__ CvxMaps maps, const CvxArgs a) {
         //      accumulation; kScreenRel = 2^-8 leaves a factor two), so  |s~| + kScreenRel A <= bound  proves that no
         //      row of this fragment leaves the box.  NaN/Inf anywhere in a window compare as "suspicious" (integer
         //      compare of the bit patterns), and the exact FP64 check below decides.
+        unsigned act32 = 0u;
+        double2 su[2][CV_NT];
+        double lo[2], hi[2];
+        if (!quiet) {                                                // CTA-uniform
         float cs[CV_NT][4], ca[CV_NT][4];
 #pragma unroll
         for (int nt = 0; nt < CV_NT; ++nt)
@@ -599,9 +659,6 @@ k_closed_loop_cvx(const __grid_constant__ CvxMaps maps, const CvxArgs a) {
         const bool susp = __any_sync(0xffffffffu, worst > bound_bits);
         if (lane == 0) sm.admm.vmask[cur][warp] = susp ? 1u : 0u;
         __syncthreads();
-        unsigned act32 = 0u;
-        double2 su[2][CV_NT];
-        double lo[2], hi[2];
         if ((sm.admm.vmask[cur][0] | sm.admm.vmask[cur][1] | sm.admm.vmask[cur][2] | sm.admm.vmask[cur][3]) != 0u) {
             // rare (first blocks after a set-point change): the exact FP64 check - which loops violate, which hold
             // non-finite numbers
@@ -638,6 +695,7 @@ k_closed_loop_cvx(const __grid_constant__ CvxMaps maps, const CvxArgs a) {
             const unsigned ball = sm.admm.bmask[cur][0] | sm.admm.bmask[cur][1] | sm.admm.bmask[cur][2] | sm.admm.bmask[cur][3];
             act32 = vall & ~ball;
         }
+        }   // !quiet
         if (act32 != 0u) {                                           // CTA-uniform: some loop violates its slack bound
             // ---- box-row ADMM on the tensor cores, then the correction of the planned inputs  U -= Psi[0:8, :] t
 #pragma unroll
@@ -704,6 +762,7 @@ k_closed_loop_cvx(const __grid_constant__ CvxMaps maps, const CvxArgs a) {
             *reinterpret_cast<double2 *>(a.u_sys + (f0 + k) * 2) = make_double2(sm.th[nxt][2 * q][lcol], sm.th[nxt][2 * q + 1][lcol]);
             *reinterpret_cast<double2 *>(a.y_sys + (f0 + k) * 2) = make_double2(sm.th[nxt][8 + 2 * q][lcol], sm.th[nxt][8 + 2 * q + 1][lcol]);
         }
+        level0(std::integral_constant<int, nxt>{});                  // verdict for the next block's window
     };
     {
         int t = 0;
