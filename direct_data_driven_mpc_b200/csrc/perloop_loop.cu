@@ -80,6 +80,7 @@ k_closed_loop_perloop(const __grid_constant__ PlMaps<NMPC * P + NX, NX + NMPC * 
                                                            // their (broadcast) 16-byte pieces from disjoint banks
     __shared__ __align__(16) double ex_s[16][S];
     __shared__ __align__(16) double box_s[BOX ? 16 : 1][BOX ? 3 : 1][BOX ? 64 : 2];   // per loop: ADMM iterate d (then t), z, w
+    __shared__ double lv0_s[BOX ? 16 : 1][BOX ? NW + 1 : 1];   // per loop: level-0 screen, cmax (NW) and max |s_ss|
     const int lane = threadIdx.x & 31, k = lane & (G - 1);
     const int slot = threadIdx.x >> 3;                     // loop slot in the CTA
     double *ex = ex_s[slot];
@@ -129,6 +130,49 @@ k_closed_loop_perloop(const __grid_constant__ PlMaps<NMPC * P + NX, NX + NMPC * 
     for (int j = 0; j < NWY; ++j) win[NWU + j] = a.y_past0[(size_t)b * NWY + j];
 #pragma unroll
     for (int j = 0; j < NX; ++j) x[j] = a.x0[(size_t)b * NX + j];
+
+    // ---- BOX, level-0 screen (cvx_loop.cu has the same test for a shared controller): with theta_ss the window of the
+    //      settled loop (its set-point repeated),  |s_j(theta)| <= max_j |s_ss,j| + sum_k cmax_k |theta_k - theta_ss,k|,
+    //      cmax_k = max_j |Ks[j][k]|.  Both constants cost one pass over the loop's own Ks (what the exact check reads in
+    //      EVERY block: 9.6 KB per four-tank loop); the test itself is NW multiply-adds.
+    double thr0 = 0.0;
+    if constexpr (BOX) {
+        const int nb = a.nb;
+        const double *Ksc = a.Ks + (size_t)c * nb * a.nth;
+        double cm[NW], sss = 0.0;
+#pragma unroll
+        for (int j = 0; j < NW; ++j) cm[j] = 0.0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int r = k + G * i;
+            if (r < nb) {
+                const double *row = Ksc + (size_t)r * a.nth;
+                double acc = 0.0;
+#pragma unroll
+                for (int j = 0; j < NW; ++j) {
+                    const double kv = __ldg(row + j);
+                    cm[j] = fmax(cm[j], fabs(kv));
+                    acc = fma(kv, j < NWU ? sp[j % M] : sp[M + (j - NWU) % P], acc);
+                }
+#pragma unroll
+                for (int j = 0; j < NSP; ++j) acc = fma(__ldg(row + NW + j), sp[j], acc);
+                sss = fmax(sss, fabs(acc));
+            }
+        }
+#pragma unroll
+        for (int o = 1; o < G; o <<= 1) {
+#pragma unroll
+            for (int j = 0; j < NW; ++j) cm[j] = fmax(cm[j], __shfl_xor_sync(0xffffffffu, cm[j], o));
+            sss = fmax(sss, __shfl_xor_sync(0xffffffffu, sss, o));
+        }
+        if (k == 0) {
+#pragma unroll
+            for (int j = 0; j < NW; ++j) lv0_s[slot][j] = cm[j];
+            lv0_s[slot][NW] = sss;
+        }
+        __syncwarp();
+        thr0 = __ldg(a.bhi + (size_t)c * nb) * (1.0 - 1e-9);
+    }
 
     const double *Fc = nullptr;
     int fnz = 0;
@@ -213,7 +257,15 @@ k_closed_loop_perloop(const __grid_constant__ PlMaps<NMPC * P + NX, NX + NMPC * 
             for (int j = 0; j < NW; ++j) acc[j & 3] = fma(Kw[i][j], win[j], acc[j & 3]);
             u_own[i] = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + csp[i];
         }
+        bool check_box = BOX;
         if constexpr (BOX) {
+            double b0 = lv0_s[slot][NW];
+#pragma unroll
+            for (int j = 0; j < NW; ++j)
+                b0 = fma(lv0_s[slot][j], fabs(win[j] - (j < NWU ? sp[j % M] : sp[M + (j - NWU) % P])), b0);
+            check_box = !__all_sync(0xffffffffu, b0 <= thr0);        // (NaN fails the test) warp-uniform
+        }
+        if (check_box) {
             // ---- slack rows of this loop, rows k + 8 i: s_unc = Ks theta
             const int nb = a.nb;
             const double *Ksc = a.Ks + (size_t)c * nb * a.nth, *loc = a.blo + (size_t)c * nb, *hic = a.bhi + (size_t)c * nb;
