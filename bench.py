@@ -580,7 +580,7 @@ def secondary_convex(dev, sc, fp64_peak, B=CONFIG3_LOOPS):
     bufs = (torch.empty(B, N_STEPS, 2, dtype=torch.float64, device=dev), torch.empty(B, N_STEPS, 2, dtype=torch.float64, device=dev))
     out = {"workload": f"config 3 with slack CONVEX, {B} loops x 401 steps, tol 1e-8", "fp64_peak_tflops": fp64_peak}
     nb, nth = 60, 20
-    for c in (1.0, 0.3):
+    for c in (1.0, 0.3, 100.0):      # (c = 100: the bound never binds - what the screens and the loop cost by themselves)
         cs = ControllerSet(prm["n"], 2, 2, sc["u_d"], sc["y_d"], prm["L"], prm["Q"], prm["R"], prm["eps_max"],
                            prm["lamb_alpha"], prm["lamb_sigma"], c, 1, 1, 4, True, device=dev)
         run = lambda: cs.closed_loop(*args, noise_seed=0, noise_eps=0.002, out=bufs)
