@@ -851,3 +851,35 @@ def test_dmma_kernel_cta_sizes_agree_bitwise(n_mpc):
         outs.append((u.cpu().numpy(), y.cpu().numpy(), xf.cpu().numpy()))
     for o in outs[1:]:
         assert all(np.array_equal(a, b) for a, b in zip(o, outs[0]))
+
+
+def test_randomised_batch_sizes_and_step_counts_agree_across_kernels():
+    """Differential test: seeded random (batch size, step count, noise mode, slack) cases - batch sizes around the CTA and
+    warp granularities of every kernel (1, 7, 31..33, 63..65, 6143..6145 loops), step counts from 1 - through every kernel
+    that accepts the case, against the generic thread-per-loop kernel: same status and iteration counts, trajectories to 1e-9."""
+    import torch
+    plant_o, prm, rng, x0, u_d, y_d = O.example_scenario(0)
+    r = np.random.default_rng(2026)
+    sizes = [1, 7, 31, 32, 33, 63, 64, 65, 127, 1000, 6143, 6144, 6145]
+    sets = {0: _set(u_d, y_d)[0], 1: _set(u_d, y_d, 1, True, 4, c=0.5)[0]}
+    for case in range(14):
+        B = int(sizes[case % len(sizes)])
+        n_steps = int(r.choice([1, 2, 3, 4, 5, 8, 9, 17, 40, 41]))
+        slack = int(case % 3 == 2)
+        cs = sets[slack]
+        xs = np.tile(plant_o.x, (B, 1)) + 0.05 * r.normal(size=(B, 4))
+        us = np.tile(prm["u_s"].T, (B, 1)) * r.uniform(0.7, 1.3, (B, 1))
+        ys = us @ _plant().equilibrium_gain().T
+        up0, yp0 = np.tile(u_d[-4:].reshape(1, -1), (B, 1)), np.tile(y_d[-4:].reshape(1, -1), (B, 1))
+        kw = dict(w=0.002 * r.uniform(-1, 1, (B, n_steps, 2))) if case % 2 else dict(noise_seed=case, scenario_id0=3 * case, noise_eps=0.002)
+        cs.set_option("closed_loop_path", "generic")
+        u0, y0, s0, i0, xf0 = cs.closed_loop(_plant(), xs, up0, yp0, us, ys, n_steps, want_x_final=True, **kw)
+        paths = ("auto", "cvx", "fast", "perloop") if slack else ("auto", "ws", "fast", "perloop")
+        for path in paths:
+            cs.set_option("closed_loop_path", path)
+            u1, y1, s1, i1, xf1 = cs.closed_loop(_plant(), xs, up0, yp0, us, ys, n_steps, want_x_final=True, **kw)
+            tag = (case, B, n_steps, slack, path)
+            assert torch.equal(s0, s1) and torch.equal(i0, i1), tag
+            assert _rel(u1.cpu().numpy(), u0.cpu().numpy()) < 1e-9 and _rel(y1.cpu().numpy(), y0.cpu().numpy()) < 1e-9, tag
+            assert _rel(xf1.cpu().numpy(), xf0.cpu().numpy()) < 1e-9, tag
+        cs.set_option("closed_loop_path", "auto")
