@@ -28,10 +28,13 @@ namespace ddmpc {
 // IOW = 2 (experiments): the i/o work on TWO warps, one drawing, one recording (the review's lever: CTAs of 2 + 2 warps,
 // roles swapped on bit 2 of the hardware warp slot so that the math warps of successive CTAs alternate between the
 // scheduler pairs).
-template <int N, int M, int P, int NX, int NMPC, bool PHILOX, int MW, int MD = 0, bool NOSTORE = false, int IOW = 1>
-__global__ void __launch_bounds__(32 * (MW + IOW), 7)
+// LPT_ = 1 (experiments, with MW = 1): CTAs of 32 loops - one math warp with four n-tiles, one i/o warp whose lanes own ONE
+// loop each - 14 CTAs per SM instead of 7, the i/o work of a block on twice as many warps.
+template <int N, int M, int P, int NX, int NMPC, bool PHILOX, int MW, int MD = 0, bool NOSTORE = false, int IOW = 1, int LPT_ = 2>
+__global__ void __launch_bounds__(32 * (MW + IOW), LPT_ == 1 ? 14 : 7)
 k_closed_loop_ws(const __grid_constant__ MmaCoef<N, M, P, NX, NMPC> cfp, const FastArgs a, const int n_tail) {
-    constexpr int R = NMPC * M, NW = N * (M + P), LPT = 2, TP = 36, NT = 4;
+    constexpr int R = NMPC * M, NW = N * (M + P), LPT = LPT_, TP = 36, NT = 4;
+    static_assert(LPT_ == 2 || (LPT_ == 1 && MW == 1 && MD == 0 && IOW == 1), "one loop per i/o lane: 1 + 1 warps");
     constexpr int KB = NX + R, RB = NMPC * P + NX, RY = NMPC * P;
     constexpr int LM = MW == 1 ? LPT : 1;                      // loop groups (of 32 loops) per math warp
     constexpr int WPG = MW == 4 ? 2 : 1;                       // math warps per loop group (they split its n-tiles)
@@ -88,7 +91,7 @@ k_closed_loop_ws(const __grid_constant__ MmaCoef<N, M, P, NX, NMPC> cfp, const F
         double pu[LPT][M], py[LPT][P];           // previous trajectory element (sector pairing)
 #pragma unroll
         for (int l = 0; l < LPT; ++l) {
-            b[l] = blockIdx.x * 64 + 2 * tl + l;
+            b[l] = blockIdx.x * (32 * LPT) + LPT * tl + l;
             live[l] = b[l] < a.B;
             if (!live[l]) b[l] = 0;              // dead slots replay loop 0 and never store
             f0[l] = (size_t)b[l] * a.n_steps;
@@ -146,7 +149,7 @@ k_closed_loop_ws(const __grid_constant__ MmaCoef<N, M, P, NX, NMPC> cfp, const F
         // record the `steps` trajectory elements of block tb (full 32-byte sectors, see emit())
         auto record = [&](const int tb, const int steps) {
             const int ub = tb & 1, yb = tb % 3;
-            if (a.step_major) {
+            if (a.step_major && LPT == 2) {
                 // (n_steps, B, m): the two loops of a lane are neighbours, a warp writes 1024 contiguous bytes per step
                 const size_t e0 = (size_t)blockIdx.x * 64 + 2 * tl;
                 const bool l0 = e0 < (size_t)a.B, l1 = e0 + 1 < (size_t)a.B;
@@ -154,7 +157,7 @@ k_closed_loop_ws(const __grid_constant__ MmaCoef<N, M, P, NX, NMPC> cfp, const F
                 for (int s = 0; s < NMPC; ++s) {
                     if (s < steps && l0 && !NOSTORE) {
                         const size_t e = (size_t)(tb * NMPC + s) * a.B + e0;
-                        double u[LPT][M], y[LPT][P];
+                        double u[2][M], y[2][P];
 #pragma unroll
                         for (int l = 0; l < LPT; ++l) {
 #pragma unroll

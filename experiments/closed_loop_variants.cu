@@ -753,6 +753,8 @@ extern "C" int ddmpc_exp_closed_loop(const ddmpc_set *set, const ddmpc_plant *pl
     else if (v == "ws2md") EXP_RUN((k_closed_loop_ws<N, M, P, NX, NMPC, false, 2>), (k_closed_loop_ws<N, M, P, NX, NMPC, true, 2, 1>), g64, 96);
     else if (v == "ws2mh" && nostore) EXP_RUN((k_closed_loop_ws<N, M, P, NX, NMPC, false, 2, 0, true>), (k_closed_loop_ws<N, M, P, NX, NMPC, true, 2, 2, true>), g64, 96);
     else if (v == "ws2mh") EXP_RUN((k_closed_loop_ws<N, M, P, NX, NMPC, false, 2>), (k_closed_loop_ws<N, M, P, NX, NMPC, true, 2, 2>), g64, 96);
+    else if (v == "ws1l1" && nostore) EXP_RUN((k_closed_loop_ws<N, M, P, NX, NMPC, false, 1, 0, true, 1, 1>), (k_closed_loop_ws<N, M, P, NX, NMPC, true, 1, 0, true, 1, 1>), ceil_div(B, 32), 64);
+    else if (v == "ws1l1") EXP_RUN((k_closed_loop_ws<N, M, P, NX, NMPC, false, 1, 0, false, 1, 1>), (k_closed_loop_ws<N, M, P, NX, NMPC, true, 1, 0, false, 1, 1>), ceil_div(B, 32), 64);
     else if (v == "ws2io2" && nostore) EXP_RUN((k_closed_loop_ws<N, M, P, NX, NMPC, false, 2, 0, true, 2>), (k_closed_loop_ws<N, M, P, NX, NMPC, true, 2, 0, true, 2>), g64, 128);
     else if (v == "ws2io2") EXP_RUN((k_closed_loop_ws<N, M, P, NX, NMPC, false, 2, 0, false, 2>), (k_closed_loop_ws<N, M, P, NX, NMPC, true, 2, 0, false, 2>), g64, 128);
     else if (v == "ws2" && nostore) EXP_RUN((k_closed_loop_ws<N, M, P, NX, NMPC, false, 2, 0, true>), (k_closed_loop_ws<N, M, P, NX, NMPC, true, 2, 0, true>), g64, 96);

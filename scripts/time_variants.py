@@ -27,6 +27,8 @@ VARIANTS = [
     ("ws, 4 math warps", None, "ws4", 0),
     ("ws, 1 math warp", None, "ws1", 0),
     ("ws, math warps draw", None, "ws2md", 0),
+    ("ws, 32-loop CTAs (1 + 1 warps)", None, "ws1l1", 0),
+    ("ws, 32-loop CTAs, no stores", None, "ws1l1", 1),
     ("ws, 2 + 2 warps (draw | record)", None, "ws2io2", 0),
     ("ws, 2 + 2 warps, no stores", None, "ws2io2", 1),
     ("ws, drawing shared", None, "ws2mh", 0),
