@@ -292,8 +292,8 @@ class ControllerSet:
         eps = plant.eps_max if noise_eps is None else noise_eps
         ps = plant.c_struct()
         with torch.cuda.device(dev):
-            if step_major:
-                self.set_option("trajectory_layout", 1)
+            # (set on every call: a layout left behind by a direct set_option() must not reinterpret these buffers)
+            self.set_option("trajectory_layout", 1 if step_major else 0)
             try:
                 _lib.check(_lib.lib.ddmpc_closed_loop_batch(
                     self._h, C.byref(ps), B, _ptr(ci), x0t.data_ptr(), up.data_ptr(), yp.data_ptr(), us.data_ptr(),
