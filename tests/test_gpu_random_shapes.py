@@ -80,6 +80,7 @@ def test_random_shape_closed_loops_vs_oracle(case):
     assert int(st.max()) <= 1, (name, st)                            # optimal / optimal_inaccurate
     if slack == O.SLACK_CONVEX:
         assert int(it.max()) > (n_steps + n_mpc - 1) // n_mpc, name   # the slack bound binds somewhere
+    worst = 0.0
     for b in range(B):
         k = b if per_loop else 0
         ctrl = O.OracleController(n, m, p, ud[k], yd[k], L, Q, R, u_s[b].reshape(-1, 1), y_s[b].reshape(-1, 1), eps if robust else None,
@@ -89,3 +90,5 @@ def test_random_shape_closed_loops_vs_oracle(case):
         po.x = xs[b].copy()
         u_ref, y_ref = O.closed_loop(po, ctrl, n_steps, w[b])
         assert _rel(u[b], u_ref) < tol and _rel(y[b], y_ref) < tol, (name, b, _rel(u[b], u_ref), _rel(y[b], y_ref))
+        worst = max(worst, _rel(u[b], u_ref), _rel(y[b], y_ref))
+    print(f"{name}: worst relative deviation from the oracle {worst:.2e} (tolerance {tol:.0e})")
