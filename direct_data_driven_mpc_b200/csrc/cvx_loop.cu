@@ -630,72 +630,72 @@ k_closed_loop_cvx(const __grid_constant__ CvxMaps maps, const CvxArgs a) {
         double2 su[2][CV_NT];
         double lo[2], hi[2];
         if (!quiet) {                                                // CTA-uniform
-        float cs[CV_NT][4], ca[CV_NT][4];
+            float cs[CV_NT][4], ca[CV_NT][4];
 #pragma unroll
-        for (int nt = 0; nt < CV_NT; ++nt)
+            for (int nt = 0; nt < CV_NT; ++nt)
 #pragma unroll
-            for (int i = 0; i < 4; ++i) cs[nt][i] = ca[nt][i] = 0.f;
+                for (int i = 0; i < 4; ++i) cs[nt][i] = ca[nt][i] = 0.f;
 #pragma unroll
-        for (int s8 = 0; s8 < 3; ++s8)
+            for (int s8 = 0; s8 < 3; ++s8)
 #pragma unroll
-            for (int nt = 0; nt < CV_NT; ++nt) {
-                uint32_t b0, b1;
-                if (s8 < 2) {
-                    b0 = __float_as_uint(sm.thf[cur][8 * s8 + q][8 * nt + g]);
-                    b1 = __float_as_uint(sm.thf[cur][8 * s8 + 4 + q][8 * nt + g]);
-                } else {
-                    b0 = spb[nt];
-                    b1 = 0u;
+                for (int nt = 0; nt < CV_NT; ++nt) {
+                    uint32_t b0, b1;
+                    if (s8 < 2) {
+                        b0 = __float_as_uint(sm.thf[cur][8 * s8 + q][8 * nt + g]);
+                        b1 = __float_as_uint(sm.thf[cur][8 * s8 + 4 + q][8 * nt + g]);
+                    } else {
+                        b0 = spb[nt];
+                        b1 = 0u;
+                    }
+                    mma_tf32(cs[nt], fKs[0][s8][0], fKs[1][s8][0], fKs[0][s8][1], fKs[1][s8][1], b0, b1);
+                    mma_tf32(ca[nt], fKs[0][s8][0] & kAbs, fKs[1][s8][0] & kAbs, fKs[0][s8][1] & kAbs, fKs[1][s8][1] & kAbs,
+                             b0 & kAbs, b1 & kAbs);
                 }
-                mma_tf32(cs[nt], fKs[0][s8][0], fKs[1][s8][0], fKs[0][s8][1], fKs[1][s8][1], b0, b1);
-                mma_tf32(ca[nt], fKs[0][s8][0] & kAbs, fKs[1][s8][0] & kAbs, fKs[0][s8][1] & kAbs, fKs[1][s8][1] & kAbs,
-                         b0 & kAbs, b1 & kAbs);
-            }
-        unsigned worst = 0u;
+            unsigned worst = 0u;
 #pragma unroll
-        for (int nt = 0; nt < CV_NT; ++nt)
+            for (int nt = 0; nt < CV_NT; ++nt)
 #pragma unroll
-            for (int i = 0; i < 4; ++i) worst = max(worst, __float_as_uint(fmaf(kScreenRel, ca[nt][i], fabsf(cs[nt][i]))));
-        const bool susp = __any_sync(0xffffffffu, worst > bound_bits);
-        if (lane == 0) sm.admm.vmask[cur][warp] = susp ? 1u : 0u;
-        __syncthreads();
-        if ((sm.admm.vmask[cur][0] | sm.admm.vmask[cur][1] | sm.admm.vmask[cur][2] | sm.admm.vmask[cur][3]) != 0u) {
-            // rare (first blocks after a set-point change): the exact FP64 check - which loops violate, which hold
-            // non-finite numbers
-#pragma unroll
-            for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-                for (int nt = 0; nt < CV_NT; ++nt) su[mt][nt] = make_double2(0.0, 0.0);
-#pragma unroll
-            for (int ks = 0; ks < NSPK; ++ks) {
-                const double *row = ks < NW / 4 ? sm.th[cur][4 * ks + q] : sm.sp[q];
-                double bv[CV_NT], av[2];
-#pragma unroll
-                for (int nt = 0; nt < CV_NT; ++nt) bv[nt] = row[8 * nt + g];
-#pragma unroll
-                for (int mt = 0; mt < 2; ++mt) {
-                    const int r = 16 * warp + 8 * mt + g;
-                    av[mt] = r < nb ? __ldg(a.Ks + (size_t)r * a.nth + 4 * ks + q) : 0.0;
-                }
+                for (int i = 0; i < 4; ++i) worst = max(worst, __float_as_uint(fmaf(kScreenRel, ca[nt][i], fabsf(cs[nt][i]))));
+            const bool susp = __any_sync(0xffffffffu, worst > bound_bits);
+            if (lane == 0) sm.admm.vmask[cur][warp] = susp ? 1u : 0u;
+            __syncthreads();
+            if ((sm.admm.vmask[cur][0] | sm.admm.vmask[cur][1] | sm.admm.vmask[cur][2] | sm.admm.vmask[cur][3]) != 0u) {
+                // rare (first blocks after a set-point change): the exact FP64 check - which loops violate, which hold
+                // non-finite numbers
 #pragma unroll
                 for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-                    for (int nt = 0; nt < CV_NT; ++nt) dmma884(su[mt][nt], av[mt], bv[nt]);
+                    for (int nt = 0; nt < CV_NT; ++nt) su[mt][nt] = make_double2(0.0, 0.0);
+#pragma unroll
+                for (int ks = 0; ks < NSPK; ++ks) {
+                    const double *row = ks < NW / 4 ? sm.th[cur][4 * ks + q] : sm.sp[q];
+                    double bv[CV_NT], av[2];
+#pragma unroll
+                    for (int nt = 0; nt < CV_NT; ++nt) bv[nt] = row[8 * nt + g];
+#pragma unroll
+                    for (int mt = 0; mt < 2; ++mt) {
+                        const int r = 16 * warp + 8 * mt + g;
+                        av[mt] = r < nb ? __ldg(a.Ks + (size_t)r * a.nth + 4 * ks + q) : 0.0;
+                    }
+#pragma unroll
+                    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                        for (int nt = 0; nt < CV_NT; ++nt) dmma884(su[mt][nt], av[mt], bv[nt]);
+                }
+                for (int mt = 0; mt < 2; ++mt) {
+                    const int r = 16 * warp + 8 * mt + g;
+                    lo[mt] = r < nb ? __ldg(a.blo + r) : -INFINITY;
+                    hi[mt] = r < nb ? __ldg(a.bhi + r) : INFINITY;
+                }
+                unsigned viol, bad;
+                box_flags(su, lo, hi, q, viol, bad);
+                if (lane == 0) { sm.admm.vmask[nxt][warp] = viol; sm.admm.bmask[cur][warp] = bad; }
+                __syncthreads();
+                const unsigned vall = sm.admm.vmask[nxt][0] | sm.admm.vmask[nxt][1] | sm.admm.vmask[nxt][2] | sm.admm.vmask[nxt][3];
+                const unsigned ball = sm.admm.bmask[cur][0] | sm.admm.bmask[cur][1] | sm.admm.bmask[cur][2] | sm.admm.bmask[cur][3];
+                act32 = vall & ~ball;
             }
-            for (int mt = 0; mt < 2; ++mt) {
-                const int r = 16 * warp + 8 * mt + g;
-                lo[mt] = r < nb ? __ldg(a.blo + r) : -INFINITY;
-                hi[mt] = r < nb ? __ldg(a.bhi + r) : INFINITY;
-            }
-            unsigned viol, bad;
-            box_flags(su, lo, hi, q, viol, bad);
-            if (lane == 0) { sm.admm.vmask[nxt][warp] = viol; sm.admm.bmask[cur][warp] = bad; }
-            __syncthreads();
-            const unsigned vall = sm.admm.vmask[nxt][0] | sm.admm.vmask[nxt][1] | sm.admm.vmask[nxt][2] | sm.admm.vmask[nxt][3];
-            const unsigned ball = sm.admm.bmask[cur][0] | sm.admm.bmask[cur][1] | sm.admm.bmask[cur][2] | sm.admm.bmask[cur][3];
-            act32 = vall & ~ball;
         }
-        }   // !quiet
         if (act32 != 0u) {                                           // CTA-uniform: some loop violates its slack bound
             // ---- box-row ADMM on the tensor cores, then the correction of the planned inputs  U -= Psi[0:8, :] t
 #pragma unroll
